@@ -1,0 +1,245 @@
+/*
+ * libb200np -- C ABI of the B200-native (sm_100a) neural-process hot path.
+ *
+ * The reference (boschresearch/what-matters-for-meta-learning) has no FFI: its hot path is Python
+ * nn.Modules calling ATen/cuDNN/cuBLAS.  This header is the boundary a maintainer binds instead
+ * (ctypes stub: what-matters-for-meta-learning_b200/b200np/lib.py).  Each
+ * entry point names the reference call site(s) it replaces.  File:line are relative to the
+ * reference checkout.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (or int32 where stated); the caller
+ *     owns all memory, including workspaces (size them with the *_workspace functions);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, never synchronise,
+ *     never allocate, and are CUDA-graph capturable;
+ *   - return value 0 = success, negative = B200NP_E_* (b200np_strerror gives the text);
+ *   - CNN activations are NHWC ("pixel-major": [image][y][x][channel]); network inputs stay NCHW
+ *     as the reference's datasets deliver them.
+ */
+#ifndef B200NP_H
+#define B200NP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NP_OK 0
+#define B200NP_E_BADARG (-1)    /* dimension / pointer / alignment precondition violated */
+#define B200NP_E_LAUNCH (-2)    /* cudaLaunch / cudaGetLastError reported a failure        */
+#define B200NP_E_WORKSPACE (-3) /* workspace too small                                     */
+#define B200NP_E_UNSUPPORTED (-4)
+
+/* precision of tensor-core contractions: fp32-grade split (3 tf32 passes) or one tf32 pass,
+ * or the CUDA-core fp32 kernels (used for validation and for shapes tensor cores do not fit) */
+#define B200NP_PREC_FP32_SIMT 0
+#define B200NP_PREC_TF32X3 1
+#define B200NP_PREC_TF32 2
+
+#define B200NP_ACT_NONE 0
+#define B200NP_ACT_RELU 1
+#define B200NP_ACT_TANH 2
+
+const char* b200np_strerror(int code);
+int b200np_version(void);
+/* 1 if the current device is compute capability 10.x, 0 otherwise, negative on CUDA error */
+int b200np_device_ok(void);
+/* number of CUDA kernels this library has enqueued in this process (bench.py's gpu_launches) */
+long long b200np_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Small-Cin direct convolution (stem).  Replaces nn.Conv2d 5x5 s2 p2 + ReLU at
+ * networks/models.py:93-95,160-162 and the first conv of encoder_w0
+ * (networks/CNPShapeNet1D.py:47-48).  x NCHW [N,Cin,H,W] (Cin<=4), w torch layout
+ * [Cout,Cin,R,R], y NHWC [N,H/stride,W/stride,Cout].
+ * ------------------------------------------------------------------------------------------ */
+int b200np_conv_small_fwd(const float* x, const float* w, const float* bias, float* y, int N,
+                          int Cin, int H, int W, int Cout, int R, int stride, int pad, int relu,
+                          void* stream);
+size_t b200np_conv_small_wgrad_workspace(int N, int Cin, int H, int W, int Cout, int R, int stride,
+                                         int pad);
+/* dy NHWC is the gradient w.r.t. the pre-activation output; writes dw [Cout,Cin,R,R], db [Cout] */
+int b200np_conv_small_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int Cin,
+                            int H, int W, int Cout, int R, int stride, int pad, void* ws,
+                            size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Channel-dense NHWC convolutions as implicit GEMM (pixels x Cout x taps*Cin).
+ * Replace the cuDNN calls behind BasicBlock.forward (networks/ResNet.py:58-74), the residual
+ * 1x1 projection (:200-204), encoder_w0's 2nd/3rd convs (networks/CNPShapeNet1D.py:49-53) and
+ * their autograd backward.
+ *
+ * Packed weights (made by b200np_pack_conv_weight from torch [Cout,Cin,R,R]):
+ *   wf [R*R][Cout][Cin]  -- forward / wgrad order
+ *   wd [R*R][Cin][Cout]  -- data-gradient order
+ * ------------------------------------------------------------------------------------------ */
+int b200np_pack_conv_weight(const float* w, float* wf, float* wd, int Cout, int Cin, int R,
+                            void* stream);
+
+/* y = act( conv_RxR(x; wf, stride, pad=R/2) + bias  [+ conv_1x1(xs; wsf, stride_s) + bias_s] )
+ * x  [N,H,W,Cin], y [N,H/stride,W/stride,Cout]; optional skip source xs [N,OH*stride_s,OW*stride_s,Cs]
+ * (pass xs = NULL to disable).  This one call is conv1 (+ReLU) or conv2 + downsample + add + ReLU
+ * of a BasicBlock. */
+int b200np_conv_fwd(const float* x, const float* wf, const float* bias, float* y, int N, int H, int W,
+                    int Cin, int Cout, int R, int stride, const float* xs, const float* wsf,
+                    const float* bias_s, int Cs, int stride_s, int act, int precision, void* stream);
+
+/* dx = relu_mask(act_saved) * ( dgrad_RxR(dy; wd, stride) [+ dgrad_1x1(dys; wsd, stride_s)] )
+ * dy [N,H/stride,W/stride,Cout] -> dx [N,H,W,Cin]; `mask_src` (same shape as dx, may be NULL) is
+ * the saved post-ReLU activation whose positivity gates the gradient; optional second gradient
+ * source dys [N,H/stride_s,W/stride_s,Cs] through a 1x1 stride_s conv (the skip projection). */
+int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, const float* mask_src, int N, int H,
+                      int W, int Cin, int Cout, int R, int stride, const float* dys, const float* wsd,
+                      int Cs, int stride_s, int precision, void* stream);
+
+size_t b200np_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int stride);
+/* dw [Cout,Cin,R,R] (torch layout) = sum over pixels of dy (x) im2col(x);  db [Cout] = sum dy
+ * (db may be NULL).  x [N,H,W,Cin], dy [N,H/stride,W/stride,Cout]. */
+int b200np_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W,
+                      int Cin, int Cout, int R, int stride, int precision, void* ws, size_t ws_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pooling / flatten at the end of the CNN (networks/models.py:105-113, networks/ResNet.py:151-152)
+ * and encoder_w0's MaxPool2d(2,2) + nn.Flatten (networks/CNPShapeNet1D.py:51,54).
+ * ------------------------------------------------------------------------------------------ */
+/* AdaptiveMaxPool2d((2,2)) on NHWC [N,H,W,C] (H,W even) + NCHW-order flatten:
+ * out[n, c*4 + oh*2 + ow]; idx (int32, same shape) = h*W + w of the FIRST maximum (torch rule) */
+int b200np_adaptive_maxpool2x2_flatten_fwd(const float* x, float* out, int32_t* idx, int N, int H,
+                                           int W, int C, void* stream);
+/* dx [N,H,W,C] = relu_mask(x_saved) * scatter(dout by idx) (zero elsewhere) */
+int b200np_adaptive_maxpool2x2_flatten_bwd(const float* dout, const int32_t* idx, const float* x_saved,
+                                           float* dx, int N, int H, int W, int C, void* stream);
+/* NHWC [N,H,W,C] <-> NCHW-order flatten [N, C*H*W]  (img_agg == "reshape"; nn.Flatten) */
+int b200np_nhwc_to_nchw_flat(const float* x, float* out, int N, int H, int W, int C, void* stream);
+/* dx = relu_mask(x_saved) * unflatten(dout); x_saved may be NULL (no mask) */
+int b200np_nchw_flat_to_nhwc(const float* dout, const float* x_saved, float* dx, int N, int H, int W,
+                             int C, void* stream);
+/* MaxPool2d(2,2) NHWC [N,H,W,C] -> [N,H/2,W/2,C]; idx int8 in {0,1,2,3} (= dy*2+dx, first max) */
+int b200np_maxpool2x2_fwd(const float* x, float* y, int8_t* idx, int N, int H, int W, int C,
+                          void* stream);
+/* dx [N,H,W,C] = relu_mask(x_saved) * scatter(dy by idx) */
+int b200np_maxpool2x2_bwd(const float* dy, const int8_t* idx, const float* x_saved, float* dx, int N,
+                          int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense layers.  Replace nn.Linear / torch.cat / ReLU / Tanh chains:
+ * transform_y, task_encoder, mu, fc_mu (networks/CNPDistractor.py:43-57, models.py:139-145),
+ * EncoderFC, r_to_z, decoder0 (models.py:27-60, CNPShapeNet1D.py:58-72), the per-head
+ * AttnLinear projections and _W (ANPDistractor.py:83-100), FAVOR+ feature GEMMs.
+ *
+ * One strided, grouped GEMM covers all of them:
+ *   for g in [0,groups):  C_g[m,n] = act( alpha * sum_k A_g(m,k) * B_g(k,n)
+ *                                         + bias_g[n] + beta * C_g[m,n]
+ *                                         + row_scale[m] * addend[m,n] )
+ *   A_g(m,k) = A[g][m*a_rs + k*a_cs],  B_g(k,n) = B[g][k*b_rs + n*b_cs],  C row stride ldc.
+ * One of (a_rs,a_cs) and one of (b_rs,b_cs) must be 1.  Pointer tables are HOST arrays of
+ * `groups` device pointers (groups <= 8); bias / addend / row_scale may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200np_gemm_desc {
+  const float* A[8];
+  const float* B[8];
+  float* C[8];
+  const float* bias[8];
+  int groups;
+  int M, N, K;
+  long long a_rs, a_cs, b_rs, b_cs, ldc;
+  float alpha, beta;
+  int act;
+  const float* row_scale; /* [M] (group 0 only), with addend [M,N] row stride ld_add */
+  const float* addend;
+  long long ld_add;
+  int precision;
+} b200np_gemm_desc;
+int b200np_gemm(const b200np_gemm_desc* d, void* stream);
+
+/* dz = dy * act'(y)  (ReLU: y>0; Tanh: 1-y^2), elementwise over n floats; dz may alias dy */
+int b200np_act_bwd(const float* dy, const float* y, float* dz, long long n, int act, void* stream);
+/* out[c] = sum_r x[r*ld + c], r<rows, c<cols  (bias gradients); deterministic two-stage */
+size_t b200np_colsum_workspace(long long rows, int cols);
+int b200np_colsum(const float* x, float* out, long long rows, int cols, long long ld, void* ws,
+                  size_t ws_bytes, void* stream);
+/* utility elementwise ops used between kernels (no library calls on the hot path) */
+int b200np_fill(float* x, long long n, float value, void* stream);
+int b200np_axpy(float* y, const float* x, long long n, float a, void* stream); /* y += a*x */
+/* y[r, :] = x[r / rep, :] (rep consecutive copies of each row; the reference's .repeat) */
+int b200np_repeat_rows(const float* x, float* y, long long rows_in, int rep, int cols, void* stream);
+/* x[r,:] = sum over the rep copies of dy (backward of repeat_rows) */
+int b200np_repeat_rows_bwd(const float* dy, float* dx, long long rows_in, int rep, int cols,
+                           void* stream);
+/* y = scale[0] * x  with the scalar read from device memory (no host sync) */
+int b200np_scale_by_device_scalar(const float* x, const float* scale, float* y, long long n,
+                                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CNP context aggregation (networks/CNPDistractor.py:96-103, CNPShapeNet1D.py:115-120,
+ * CondNeuralProcess.py:94-101): feats [T,nc,D] -> out [T,D].
+ * mode 0 = mean, 1 = max (idx int32 [T,D] = FIRST maximal context index, bit-exact with
+ * torch.max(dim=1)).
+ * ------------------------------------------------------------------------------------------ */
+int b200np_ctx_aggregate_fwd(const float* feats, float* out, int32_t* idx, int T, int nc, int D,
+                             int mode, void* stream);
+int b200np_ctx_aggregate_bwd(const float* dout, const int32_t* idx, float* dfeats, int T, int nc, int D,
+                             int mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FAVOR+ (Performer) attention exactly as networks/fast_attention.py:74-99,151-156 computes it
+ * (math: SURVEY.md appendix A; constants c = d^-1/4, rho = M^-1/2, eps = 1e-4 derived inside).
+ * Head-projected inputs are laid out [T, n, H, d]: row r = (t*n + i)*H + h.  The feature
+ * pre-activations U = c*xq*P^T [T*nt*H, M] and W = c*xk*P^T [T*nc*H, M] come from b200np_gemm
+ * (row stride ldu >= M).  The exp / eps / normalised product are fused into the attention
+ * kernels; the reference's [T,H,M,d] "context" tensor (232 MB) is never built.
+ * ------------------------------------------------------------------------------------------ */
+/* per row of x [R,d] and U [R,ldu]: diag = c^2 |x|^2 / 2 (:86-89), rowmax = max_f U, argmax = first
+ * maximal feature (:93).  For keys, b200np_reduce(rowmax, op=max) gives the global stabiliser (:97). */
+int b200np_favor_rowstats(const float* x, const float* U, float* diag, float* rowmax, int32_t* argmax,
+                          long long R, int d, int M, long long ldu, void* stream);
+/* out[0] = max (op 0) or sum (op 1) of x[0..n) -- single block, deterministic */
+int b200np_reduce(const float* x, long long n, float* out, int op, void* stream);
+/* One CTA per (task, head).  A = Q'K'^T [T,H,nt,nc] and Dn = rowsum(A) [T,H,nt] are saved for the
+ * backward; out [T,nt,d,H] (feature-major, head-minor: the order `_W` consumes,
+ * networks/ANPDistractor.py:98-99).  g = device scalar holding the (all-reduced) key max.
+ * ties (device float, accumulated) counts elements of W equal to g (torch.max() tie rule). */
+int b200np_favor_attn_fwd(const float* U, const float* W, const float* sq, const float* mq,
+                          const float* tk, const float* g, const float* v, float* out, float* A,
+                          float* Dn, float* ties, int T, int H, int nt, int nc, int d, int M,
+                          long long ldu, void* stream);
+/* Gradients of the fused part.  dU [T*nt*H, ldu], dW [T*nc*H, ldu] are gradients w.r.t. the
+ * pre-activations INCLUDING the row-argmax routing for queries; ds_c2 [Rq] = c^2 * ds and
+ * dt_c2 [Rk] = c^2 * dt multiply xq / xk in the final GEMM epilogue; dg_part [T*H] = per-(task,head)
+ * shares of d loss / d g (sum them with b200np_reduce, all-reduce across ranks, then fix up). */
+int b200np_favor_attn_bwd(const float* d_out, const float* U, const float* W, const float* sq,
+                          const float* mq, const int32_t* amq, const float* tk, const float* g,
+                          const float* v, const float* out, const float* A, const float* Dn, float* dU,
+                          float* dW, float* dv, float* ds_c2, float* dt_c2, float* dg_part, int T, int H,
+                          int nt, int nc, int d, int M, long long ldu, void* stream);
+/* dW[r,f] += dg[0] / ties[0] wherever W[r,f] == g[0]  (global-argmax routing, even tie split) */
+int b200np_favor_key_fixup(float* dW, const float* W, const float* g, const float* dg, const float* ties,
+                           long long R, int M, long long ldu, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Losses (trainer/losses.py:32-80).  mu [R,out], y [R,L]; loss (device scalar) = mean over R rows;
+ * dmu [R,out] = d loss / d mu (may be NULL for evaluation).
+ *   kind 0: distractor  mean ||y - mu||_2            (:35-36)
+ *   kind 1: quaternion  mean min(|q-mu^|_1,|-q-mu^|_1), mu^ = mu/||mu||   (:50-57)
+ *   kind 2: azimuth     mean sum (y[:2]-mu)^2        (:59-61)
+ *   kind 3: degree error (evaluation only, no gradient)                  (:63-76)
+ * ------------------------------------------------------------------------------------------ */
+int b200np_loss_fwd_bwd(const float* mu, const float* y, float* loss, float* dmu, long long R, int out,
+                        int L, int kind, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused Adam over a flat fp32 parameter segment (torch.optim.Adam semantics, train.py:52-56):
+ * m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * `grad_scale` multiplies g first (1/world_size after a SUM all-reduce).
+ * ------------------------------------------------------------------------------------------ */
+int b200np_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, float grad_scale,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NP_H */

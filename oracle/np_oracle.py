@@ -338,7 +338,7 @@ class OracleTrainer:
         mu, loss = self.forward_loss(ctx_x, ctx_y, tgt_x, tgt_y)
         loss.backward()
         self.opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     def grads(self):
         return {k: (None if v.grad is None else v.grad.detach().clone())

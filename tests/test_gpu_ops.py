@@ -1,0 +1,295 @@
+"""Per-kernel parity (GPU): every C-ABI op against the same op in PyTorch fp64 on the CPU
+(the oracle for single ops is torch itself: F.conv2d / F.linear / max_pool / autograd).
+
+Tolerances: integer results (argmax indices) bit-exact; fp32 CUDA-core kernels and the TF32X3
+(fp32-grade) tensor-core kernels <= 2e-5 relative L2; single-pass TF32 <= 3e-3 (its own bound).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+PRECS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+TOL = {"fp32": 2e-5, "tf32x3": 2e-5, "tf32": 3e-3}
+
+
+def _ops():
+    from b200np import ops
+    return ops
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g, dtype=torch.float64) * scale)
+
+
+def nhwc(t):  # NCHW fp64 cpu -> NHWC fp32 cuda
+    return t.permute(0, 2, 3, 1).contiguous().float().cuda()
+
+
+def from_nhwc(t):
+    return t.permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,r,cout,hw", [(1, 5, 64, 32), (3, 5, 64, 16), (1, 3, 32, 32), (1, 5, 64, 128)])
+def test_conv_small_fwd_and_wgrad(cin, r, cout, hw):
+    ops = _ops()
+    N = 3
+    x, w, b = rnd(N, cin, hw, hw, seed=1), rnd(cout, cin, r, r, seed=2, scale=0.2), rnd(cout, seed=3)
+    w.requires_grad_(True), b.requires_grad_(True)
+    ref = F.relu(F.conv2d(x, w, b, stride=2, padding=r // 2))
+    y = ops.conv_small_fwd(x.float().cuda(), w.detach().float().cuda(), b.detach().float().cuda())
+    assert rel(from_nhwc(y), ref) < 2e-6
+    dy = rnd(*ref.shape, seed=4) * (ref > 0)  # gradient w.r.t. the pre-activation
+    pre = F.conv2d(x, w, b, stride=2, padding=r // 2)
+    pre.backward(dy)
+    dw, db = ops.conv_small_wgrad(x.float().cuda(), nhwc(dy), w.shape)
+    assert rel(dw, w.grad) < 1e-5
+    assert rel(db, b.grad) < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("cin,cout,hw,n", [(64, 64, 16, 3), (64, 64, 4, 5), (64, 64, 2, 70), (32, 48, 16, 2), (48, 64, 8, 2)])
+def test_conv_block_ops(prec, cin, cout, hw, n):
+    """3x3 s2 / 3x3 s1 / fused skip projection: forward, data gradient (with ReLU mask), weight grad."""
+    ops = _ops()
+    P, tol = PRECS[prec], TOL[prec]
+    if prec != "fp32" and (cin, cout) != (64, 64):
+        tol = TOL["fp32"]  # these shapes route to the CUDA-core kernels in every mode
+    x = rnd(n, cin, hw, hw, seed=1).abs()
+    w1, b1 = rnd(cout, cin, 3, 3, seed=2, scale=0.05).requires_grad_(), rnd(cout, seed=3, scale=0.1).requires_grad_()
+    x.requires_grad_(True)
+    # --- conv 3x3 stride 2 + ReLU
+    pre1 = F.conv2d(x, w1, b1, stride=2, padding=1)
+    h = F.relu(pre1)
+    xg = nhwc(x.detach())
+    wf1, wd1 = ops.pack_conv_weight(w1.detach().float().cuda())
+    hg = ops.conv_fwd(xg, wf1, b1.detach().float().cuda(), 3, 2, 1, P)
+    assert rel(from_nhwc(hg), h) < tol
+    if hw < 4:
+        return
+    if cin == cout:
+        # --- conv 3x3 stride 1 + 1x1 stride-2 skip projection + add + ReLU (one launch)
+        w2, b2 = rnd(cout, cout, 3, 3, seed=4, scale=0.05).requires_grad_(), rnd(cout, seed=5, scale=0.1).requires_grad_()
+        ws, bs = rnd(cout, cin, 1, 1, seed=6, scale=0.1).requires_grad_(), rnd(cout, seed=7, scale=0.1).requires_grad_()
+        y = F.relu(F.conv2d(h, w2, b2, padding=1) + F.conv2d(x, ws, bs, stride=2))
+        wf2, wd2 = ops.pack_conv_weight(w2.detach().float().cuda())
+        wfs, wds = ops.pack_conv_weight(ws.detach().float().cuda())
+        hgx = nhwc(h.detach())
+        yg = ops.conv_fwd(hgx, wf2, b2.detach().float().cuda(), 3, 1, 1, P,
+                          skip=(xg, wfs, bs.detach().float().cuda(), 2))
+        assert rel(from_nhwc(yg), y) < tol
+        gy = rnd(*y.shape, seed=8)
+        y.backward(gy)
+        dz = (gy * (y > 0)).detach()        # gradient at the pre-activation of the block output
+        dzg = nhwc(dz)
+        dw2, db2 = ops.conv_wgrad(hgx, dzg, 3, 1, P)
+        dws, _ = ops.conv_wgrad(xg, dzg, 1, 2, P, want_db=False)
+        assert rel(dw2, w2.grad) < tol and rel(db2, b2.grad) < 1e-5 and rel(dws, ws.grad) < tol
+        dh = ops.conv_dgrad(dzg, wd2, hgx.shape, 3, 1, P, mask_src=hgx)
+        # reference dh: gradient at conv1's pre-activation
+        hh = h.detach().requires_grad_()
+        F.conv2d(hh, w2.detach(), None, padding=1).backward(dz)
+        dh_ref = hh.grad * (h > 0)
+        assert rel(from_nhwc(dh), dh_ref) < tol
+        dw1, db1 = ops.conv_wgrad(xg, dh, 3, 2, P)
+        assert rel(dw1, w1.grad) < tol and rel(db1, b1.grad) < 2e-5
+        dx = ops.conv_dgrad(dh, wd1, xg.shape, 3, 2, P, mask_src=xg, skip=(dzg, wds, 2))
+        assert rel(from_nhwc(dx), x.grad * (x > 0)) < tol
+    else:
+        gy = rnd(*h.shape, seed=8)
+        h.backward(gy)
+        dz = nhwc((gy * (h > 0)).detach())
+        dw1, db1 = ops.conv_wgrad(xg, dz, 3, 2, P)
+        assert rel(dw1, w1.grad) < tol and rel(db1, b1.grad) < 2e-5
+        dx = ops.conv_dgrad(dz, wd1, xg.shape, 3, 2, P, mask_src=None)
+        assert rel(from_nhwc(dx), x.grad) < tol
+
+
+def test_pools_and_flatten():
+    ops = _ops()
+    x = rnd(5, 64, 4, 4, seed=1)
+    x[0, :, :, :] = 0.0          # all-equal window: first index wins
+    x[1, 3, 0, 0] = x[1, 3, 0, 1] = 7.0   # tie inside a window
+    x = F.relu(x).requires_grad_()
+    ref, idx = F.adaptive_max_pool2d(x, (2, 2), return_indices=True)
+    xg = nhwc(x.detach())
+    out, gi = ops.amp2_flatten_fwd(xg)
+    assert torch.equal(out.cpu().double(), ref.reshape(5, -1).double().float().double())
+    assert torch.equal(gi.cpu().long(), idx.reshape(5, -1))
+    g = rnd(5, 256, seed=2)
+    ref.reshape(5, -1).backward(g)
+    dx = ops.amp2_flatten_bwd(g.float().cuda(), gi, xg, torch.empty_like(xg))
+    assert rel(from_nhwc(dx), x.grad * (x > 0)) < 1e-6
+    # reshape path
+    x2 = rnd(3, 64, 2, 2, seed=3)
+    flat = ops.nhwc_to_nchw_flat(nhwc(x2))
+    assert torch.equal(flat.cpu(), x2.reshape(3, -1).float())
+    back = ops.nchw_flat_to_nhwc(flat, None, torch.empty(3, 2, 2, 64, device="cuda"), mask=False)
+    assert torch.equal(from_nhwc(back).cpu(), x2.float())
+    # MaxPool2d(2,2)
+    x3 = F.relu(rnd(2, 48, 8, 8, seed=4))
+    x3[0, 0, 0:2, 0:2] = 1.5
+    x3.requires_grad_()
+    ref3, idx3 = F.max_pool2d(x3, 2, return_indices=True)
+    y3, i3 = ops.maxpool2x2_fwd(nhwc(x3.detach()))
+    assert torch.equal(from_nhwc(y3).cpu(), ref3.float())
+    iy, ix = idx3 // 8, idx3 % 8
+    assert torch.equal(from_nhwc(i3).cpu().long(), (iy % 2) * 2 + ix % 2)
+    g3 = rnd(*ref3.shape, seed=5)
+    ref3.backward(g3)
+    d3 = ops.maxpool2x2_bwd(nhwc(g3), i3, nhwc(x3.detach()))
+    assert rel(from_nhwc(d3), x3.grad * (x3 > 0)) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(420, 256, 272), (37, 2, 256), (300, 100, 80), (1000, 1419, 256), (5, 16, 2)])
+def test_gemm_forward_roles(M, N, K):
+    ops = _ops()
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.1), rnd(N, seed=3)
+    xg, wg, bg = x.float().cuda(), w.float().cuda(), b.float().cuda()
+    y = torch.empty(M, N, device="cuda")
+    ops.gemm(xg.data_ptr(), wg.data_ptr(), y.data_ptr(), M, N, K, K, 1, 1, K, N, bias=bg.data_ptr(), act=1)
+    assert rel(y, F.relu(F.linear(x, w, b))) < 2e-6
+    dz = rnd(M, N, seed=4)
+    dzg = dz.float().cuda()
+    dx = torch.empty(M, K, device="cuda")
+    ops.gemm(dzg.data_ptr(), wg.data_ptr(), dx.data_ptr(), M, K, N, N, 1, K, 1, K)
+    assert rel(dx, dz @ w) < 2e-6
+    dw = torch.empty(N, K, device="cuda")
+    ops.gemm(dzg.data_ptr(), xg.data_ptr(), dw.data_ptr(), N, K, M, 1, N, K, 1, K)
+    assert rel(dw, dz.t() @ x) < 2e-6
+    db = ops.colsum(dzg, M, N, N)
+    assert rel(db, dz.sum(0)) < 2e-6
+    # beta / tanh / row_scale*addend epilogue
+    add, rs = rnd(M, N, seed=5), rnd(M, seed=6)
+    y2 = y.clone()
+    ops.gemm(xg.data_ptr(), wg.data_ptr(), y2.data_ptr(), M, N, K, K, 1, 1, K, N, alpha=0.5, beta=1.0, act=2,
+             row_scale=rs.float().cuda(), addend=add.float().cuda(), ld_add=N)
+    ref2 = torch.tanh(0.5 * (x @ w.t()) + F.relu(F.linear(x, w, b)) + rs[:, None] * add)
+    assert rel(y2, ref2) < 5e-6
+
+
+def test_gemm_grouped_heads():
+    ops = _ops()
+    rows, K, d, H = 45, 256, 256, 8
+    x = rnd(rows, K, seed=1)
+    ws = [rnd(d, K, seed=10 + h, scale=0.06) for h in range(H)]
+    bs = [rnd(d, seed=20 + h) for h in range(H)]
+    xg = x.float().cuda()
+    wg = [w.float().cuda() for w in ws]
+    bg = [b.float().cuda() for b in bs]
+    y = torch.empty(rows, H * d, device="cuda")
+    ops.gemm([xg.data_ptr()] * H, [w.data_ptr() for w in wg], [y.data_ptr() + 4 * h * d for h in range(H)],
+             rows, d, K, K, 1, 1, K, H * d, bias=[b.data_ptr() for b in bg])
+    ref = torch.cat([F.linear(x, w, b) for w, b in zip(ws, bs)], dim=1)
+    assert rel(y, ref) < 2e-6
+
+
+def test_elementwise_and_reductions():
+    ops = _ops()
+    x = rnd(1000, 37, seed=1).float().cuda()
+    y = F.relu(rnd(1000, 37, seed=2)).float().cuda()
+    assert torch.equal(ops.act_bwd(x, y, 1), x * (y > 0))
+    t = torch.tanh(rnd(1000, 37, seed=3)).float().cuda()
+    assert rel(ops.act_bwd(x, t, 2), x.double().cpu() * (1 - t.double().cpu() ** 2)) < 1e-6
+    r = ops.repeat_rows(x[:10].contiguous(), 7)
+    assert torch.equal(r, x[:10].repeat_interleave(7, dim=0))
+    assert rel(ops.repeat_rows_bwd(r, 7), 7 * x[:10].double().cpu()) < 1e-6
+    assert float(ops.reduce(x.view(-1), 0)) == float(x.max())
+    assert abs(float(ops.reduce(x.view(-1), 1)) - float(x.double().sum())) < 1e-2
+    z = ops.zeros((5, 3), x)
+    assert float(z.abs().sum()) == 0.0
+    ops.axpy(z, torch.ones(5, 3, device="cuda"), 2.5)
+    assert float(z.sum()) == 37.5
+    s = torch.tensor([3.0], device="cuda")
+    assert torch.equal(ops.scale_by_device_scalar(x, s), 3.0 * x)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_ctx_aggregate(mode):
+    ops = _ops()
+    f = F.relu(rnd(6, 15, 256, seed=1))
+    f[:, :, :40] = 0.0            # post-ReLU ties at zero are common: FIRST index must win
+    f[2, 3, 50] = f[2, 9, 50] = 9.0
+    f.requires_grad_()
+    fg = f.detach().float().cuda()
+    out, idx = ops.ctx_aggregate_fwd(fg, mode)
+    if mode == 0:
+        ref = f.mean(1)
+        assert rel(out, ref) < 1e-6
+    else:
+        ref, ridx = f.max(1)
+        assert torch.equal(out.cpu(), ref.float())
+        assert torch.equal(idx.cpu().long(), ridx)
+    g = rnd(6, 256, seed=2)
+    ref.backward(g)
+    df = ops.ctx_aggregate_bwd(g.float().cuda(), idx, 6, 15, 256, mode)
+    assert rel(df, f.grad) < 1e-6
+
+
+@pytest.mark.parametrize("task,kind", [("distractor", 0), ("shapenet_3d", 1), ("shapenet_1d", 2)])
+def test_losses_against_reference_golden(task, kind, golden):
+    ops = _ops()
+    mu = torch.from_numpy(golden[f"loss/{task}/mu"]).cuda()
+    y = torch.from_numpy(golden[f"loss/{task}/y"]).cuda()
+    loss, dmu = ops.loss_fwd_bwd(mu.contiguous(), y.contiguous(), kind)
+    ref = float(golden[f"loss/{task}/loss"])
+    assert abs(float(loss) - ref) < 2e-6 * abs(ref)
+    assert rel(dmu, torch.from_numpy(golden[f"loss/{task}/dmu"])) < 2e-6
+    if task == "shapenet_1d":
+        lt, _ = ops.loss_fwd_bwd(mu.contiguous(), y.contiguous(), 3, want_grad=False)
+        ref_t = float(golden[f"loss/{task}/loss_test"])
+        assert abs(float(lt) - ref_t) < 1e-4 * abs(ref_t)
+
+
+def test_adam_matches_torch():
+    ops = _ops()
+    n = 10007
+    p0, gs = rnd(n, seed=1).float(), [rnd(n, seed=10 + i).float() for i in range(3)]
+    p_ref = p0.clone().requires_grad_()
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p, m, v = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for i, g in enumerate(gs):
+        p_ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g.cuda(), m, v, n, 1e-3, 0.9, 0.999, 1e-8, 0.0, i + 1)
+    assert rel(p, p_ref) < 1e-6
+
+
+@pytest.mark.parametrize("prec", ["fp32"])
+@pytest.mark.parametrize("T,H,nt,nc,d", [(2, 8, 5, 4, 64), (2, 8, 21, 15, 256), (1, 2, 36, 25, 64)])
+def test_favor_attention_fwd_bwd(prec, T, H, nt, nc, d):
+    """Fused FAVOR+ (re-associated) vs the closed-form fp64 restatement of the reference
+    (oracle.np_oracle.favor_attention_fwd_bwd, itself checked against autograd through the
+    reference formulation in tests/test_oracle_golden.py)."""
+    from b200np.engine import FavorAttentionFn
+    from oracle import np_oracle
+    M = int(d * np.log(d))
+    xq, xk, v = rnd(T, nt, H, d, seed=1), rnd(T, nc, H, d, seed=2), rnd(T, nc, H, d, seed=3)
+    if nc >= 4:
+        xk[0, 1] = xk[0, 0]  # duplicated context row -> exact tie of the global key max candidates
+    P = rnd(M, d, seed=4)
+    d_out = rnd(T, H, nt, d, seed=5)
+    to_bh = lambda t: t.permute(0, 2, 1, 3)  # [T,n,H,d] -> [T,H,n,d]
+    out_ref, (dq_ref, dk_ref, dv_ref) = np_oracle.favor_attention_fwd_bwd(to_bh(xq), to_bh(xk), to_bh(v), P, d_out)
+    q_g = xq.reshape(T * nt, H * d).float().cuda().requires_grad_()
+    k_g = xk.reshape(T * nc, H * d).float().cuda().requires_grad_()
+    v_g = v.reshape(T * nc, H * d).float().cuda().requires_grad_()
+    out = FavorAttentionFn.apply(PRECS[prec], T, H, nt, nc, q_g, k_g, v_g, P.float().cuda())
+    # out [T*nt, d*H] with index e*H + h
+    out_bh = out.view(T, nt, d, H).permute(0, 3, 1, 2)
+    assert rel(out_bh, out_ref) < 2e-5
+    out.backward(d_out.permute(0, 2, 3, 1).reshape(T * nt, d * H).float().cuda())
+    from_rows = lambda g, n: g.view(T, n, H, d).permute(0, 2, 1, 3)
+    assert rel(from_rows(v_g.grad, nc), dv_ref) < 2e-5
+    assert rel(from_rows(k_g.grad, nc), dk_ref) < 2e-4
+    assert rel(from_rows(q_g.grad, nt), dq_ref) < 2e-4

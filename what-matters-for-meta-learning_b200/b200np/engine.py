@@ -1,0 +1,479 @@
+"""Forward / backward of the neural-process families on libb200np kernels.
+
+Each segment of the model (CNN trunk, dense layer, head projections, aggregation, FAVOR+
+attention, loss) is one ``torch.autograd.Function`` whose forward AND backward are explicit
+sequences of C-ABI kernel launches on torch's current stream; torch autograd only stitches the
+segments together (views / reshapes -- no ATen compute kernels on the path).  Nothing here
+falls back to PyTorch ops: without the CUDA library or a CUDA tensor the calls raise.
+
+Reference call sites mirrored: networks/models.py:92-117,156-192 (CNN), networks/ResNet.py:58-74
+(BasicBlock), networks/ANPDistractor.py:78-135, networks/CNPDistractor.py:77-124,
+networks/CNPShapeNet1D.py:95-143, networks/ANPShapeNet1D.py:93-161,
+networks/fast_attention.py:74-99,151-156.
+"""
+import os
+
+import torch
+from torch.autograd import Function
+
+from . import dist, ops
+from .lib import ACT_NONE, ACT_RELU, ACT_TANH, PREC_FP32_SIMT, PREC_TF32, PREC_TF32X3
+
+_PREC_NAMES = {"fp32": PREC_FP32_SIMT, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
+PRECISION = _PREC_NAMES[os.environ.get("B200NP_PRECISION", "tf32x3")]
+
+
+def set_precision(name):
+    """'tf32x3' (fp32-grade 3-pass split on tcgen05, default), 'tf32' (single pass, what cuDNN's
+    default does for the reference on Ampere+), or 'fp32' (CUDA-core kernels, validation)."""
+    global PRECISION
+    PRECISION = _PREC_NAMES[name]
+
+
+def _p(t, off=0):
+    return t.data_ptr() + 4 * off
+
+
+# ================================================================================================
+# CNN trunk: stem 5x5 s2 + 4 residual stages + pooling, several image sources in one pass
+# ================================================================================================
+class TrunkFn(Function):
+    @staticmethod
+    def forward(ctx, img_agg, prec, n_src, *tensors):
+        imgs, params = tensors[:n_src], tensors[n_src:]
+        assert len(params) == 26
+        if img_agg not in ("max", "baco", "reshape"):
+            # 'mean' yields 64 features and breaks the 256-wide Linear in the reference too
+            raise NotImplementedError(f"img_agg={img_agg!r} is unusable in the reference (SURVEY.md 8a/a1)")
+        c1w, c1b = params[0], params[1]
+        Ns = [im.shape[0] for im in imgs]
+        N = sum(Ns)
+        _, H, W = imgs[0].shape[1:]
+        x0 = ops.empty((N, H // 2, W // 2, 64), imgs[0])
+        off = 0
+        for im, n in zip(imgs, Ns):
+            ops.conv_small_fwd(im, c1w, c1b, out=x0[off:off + n], relu=True)
+            off += n
+        x, acts, packs = x0, [], []
+        for l in range(4):
+            w1, b1, w2, b2, wsk, bsk = params[2 + 6 * l: 8 + 6 * l]
+            wf1, wd1 = ops.pack_conv_weight(w1)
+            wf2, wd2 = ops.pack_conv_weight(w2)
+            wfs, wds = ops.pack_conv_weight(wsk)
+            h = ops.conv_fwd(x, wf1, b1, 3, 2, ACT_RELU, prec)
+            y = ops.conv_fwd(h, wf2, b2, 3, 1, ACT_RELU, prec, skip=(x, wfs, bsk, 2))
+            acts.append((x, h, y))
+            packs.append((wd1, wd2, wds))
+            x = y
+        outs, idxs, off = [], [], 0
+        for n in Ns:
+            xs = x[off:off + n]
+            if img_agg == "reshape":
+                outs.append(ops.nhwc_to_nchw_flat(xs))
+                idxs.append(None)
+            else:
+                o, i = ops.amp2_flatten_fwd(xs)
+                outs.append(o)
+                idxs.append(i)
+            off += n
+        ctx.img_agg, ctx.prec, ctx.Ns = img_agg, prec, Ns
+        ctx.imgs, ctx.acts, ctx.packs, ctx.idxs = imgs, acts, packs, idxs
+        ctx.c1w_shape = tuple(c1w.shape)
+        ctx.pool_idx = idxs  # exposed for parity tests (bit-exact argmax)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        prec, Ns = ctx.prec, ctx.Ns
+        y_last = ctx.acts[3][2]
+        dy = torch.empty_like(y_last)
+        off = 0
+        for n, do, idx in zip(Ns, douts, ctx.idxs):
+            do = do.contiguous()
+            if ctx.img_agg == "reshape":
+                ops.nchw_flat_to_nhwc(do, y_last[off:off + n], dy[off:off + n])
+            else:
+                ops.amp2_flatten_bwd(do, idx, y_last[off:off + n], dy[off:off + n])
+            off += n
+        grads = [None] * 26
+        for l in (3, 2, 1, 0):
+            x, h, _ = ctx.acts[l]
+            wd1, wd2, wds = ctx.packs[l]
+            dw2, db2 = ops.conv_wgrad(h, dy, 3, 1, prec)
+            dws, _ = ops.conv_wgrad(x, dy, 1, 2, prec, want_db=False)
+            dh = ops.conv_dgrad(dy, wd2, h.shape, 3, 1, prec, mask_src=h)
+            dw1, db1 = ops.conv_wgrad(x, dh, 3, 2, prec)
+            dx = ops.conv_dgrad(dh, wd1, x.shape, 3, 2, prec, mask_src=x, skip=(dy, wds, 2))
+            grads[2 + 6 * l: 8 + 6 * l] = [dw1, db1, dw2, db2, dws, db2.clone()]
+            dy = dx
+        off, dw_acc, db_acc = 0, None, None
+        for im, n in zip(ctx.imgs, Ns):
+            dw, db = ops.conv_small_wgrad(im, dy[off:off + n], ctx.c1w_shape)
+            if dw_acc is None:
+                dw_acc, db_acc = dw, db
+            else:
+                ops.axpy(dw_acc, dw)
+                ops.axpy(db_acc, db)
+            off += n
+        grads[0], grads[1] = dw_acc, db_acc
+        return (None, None, None) + (None,) * len(Ns) + tuple(grads)
+
+
+class EncoderW0Fn(Function):
+    """encoder_w0 up to (and including) nn.Flatten: conv 1->32 s2, conv 32->48 s2, maxpool 2x2,
+    conv 48->64 s2, NCHW flatten (networks/CNPShapeNet1D.py:46-55).  The trailing Linear 4096->dim_w
+    is a LinearFn."""
+
+    @staticmethod
+    def forward(ctx, prec, n_src, *tensors):
+        imgs = tensors[:n_src]
+        w0, b0, w2, b2, w5, b5 = tensors[n_src:]
+        Ns = [im.shape[0] for im in imgs]
+        N = sum(Ns)
+        _, H, W = imgs[0].shape[1:]
+        x1 = ops.empty((N, H // 2, W // 2, w0.shape[0]), imgs[0])
+        off = 0
+        for im, n in zip(imgs, Ns):
+            ops.conv_small_fwd(im, w0, b0, out=x1[off:off + n], relu=True)
+            off += n
+        wf2, wd2 = ops.pack_conv_weight(w2)
+        wf5, wd5 = ops.pack_conv_weight(w5)
+        x2 = ops.conv_fwd(x1, wf2, b2, 3, 2, ACT_RELU, prec)
+        x3, pidx = ops.maxpool2x2_fwd(x2)
+        x4 = ops.conv_fwd(x3, wf5, b5, 3, 2, ACT_RELU, prec)
+        outs, off = [], 0
+        for n in Ns:
+            outs.append(ops.nhwc_to_nchw_flat(x4[off:off + n]))
+            off += n
+        ctx.prec, ctx.Ns, ctx.imgs = prec, Ns, imgs
+        ctx.saved = (x1, x2, x3, x4, pidx, wd2, wd5, tuple(w0.shape))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        prec, Ns = ctx.prec, ctx.Ns
+        x1, x2, x3, x4, pidx, wd2, wd5, w0_shape = ctx.saved
+        d4 = torch.empty_like(x4)
+        off = 0
+        for n, do in zip(Ns, douts):
+            ops.nchw_flat_to_nhwc(do.contiguous(), x4[off:off + n], d4[off:off + n])
+            off += n
+        dw5, db5 = ops.conv_wgrad(x3, d4, 3, 2, prec)
+        d3 = ops.conv_dgrad(d4, wd5, x3.shape, 3, 2, prec, mask_src=None)
+        d2 = ops.maxpool2x2_bwd(d3, pidx, x2)
+        dw2, db2 = ops.conv_wgrad(x1, d2, 3, 2, prec)
+        d1 = ops.conv_dgrad(d2, wd2, x1.shape, 3, 2, prec, mask_src=x1)
+        off, dw0, db0 = 0, None, None
+        for im, n in zip(ctx.imgs, Ns):
+            dw, db = ops.conv_small_wgrad(im, d1[off:off + n], w0_shape)
+            if dw0 is None:
+                dw0, db0 = dw, db
+            else:
+                ops.axpy(dw0, dw)
+                ops.axpy(db0, db)
+            off += n
+        return (None, None) + (None,) * len(Ns) + (dw0, db0, dw2, db2, dw5, db5)
+
+
+# ================================================================================================
+# dense layers
+# ================================================================================================
+class LinearFn(Function):
+    """y = act([x, x2] @ w^T + b): nn.Linear (+ torch.cat of two inputs, + ReLU/Tanh) in one kernel."""
+
+    @staticmethod
+    def forward(ctx, act, prec, x, x2, w, b):
+        x = x.contiguous()
+        K1 = x.shape[-1]
+        rows = x.numel() // K1
+        N, Kt = w.shape
+        y = ops.empty(tuple(x.shape[:-1]) + (N,), x)
+        if x2 is None:
+            assert Kt == K1
+            ops.gemm(_p(x), _p(w), _p(y), rows, N, K1, K1, 1, 1, Kt, N, bias=_p(b), act=act, prec=prec)
+        else:
+            x2 = x2.contiguous()
+            K2 = x2.shape[-1]
+            assert Kt == K1 + K2 and x2.numel() // K2 == rows
+            ops.gemm(_p(x), _p(w), _p(y), rows, N, K1, K1, 1, 1, Kt, N, prec=prec)
+            ops.gemm(_p(x2), _p(w, K1), _p(y), rows, N, K2, K2, 1, 1, Kt, N, bias=_p(b), beta=1.0, act=act,
+                     prec=prec)
+        ctx.act, ctx.prec, ctx.rows = act, prec, rows
+        ctx.save_for_backward(x, x2, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, x2, w, y = ctx.saved_tensors
+        act, prec, rows = ctx.act, ctx.prec, ctx.rows
+        dy = dy.contiguous()
+        dz = ops.act_bwd(dy, y, act) if act != ACT_NONE else dy
+        N, Kt = w.shape
+        K1 = x.shape[-1]
+        dx = dx2 = None
+        if ctx.needs_input_grad[2]:
+            dx = torch.empty_like(x)
+            ops.gemm(_p(dz), _p(w), _p(dx), rows, K1, N, N, 1, Kt, 1, K1, prec=prec)
+        dw = ops.empty((N, Kt), w)
+        ops.gemm(_p(dz), _p(x), _p(dw), N, K1, rows, 1, N, K1, 1, Kt, prec=prec)
+        if x2 is not None:
+            K2 = x2.shape[-1]
+            if ctx.needs_input_grad[3]:
+                dx2 = torch.empty_like(x2)
+                ops.gemm(_p(dz), _p(w, K1), _p(dx2), rows, K2, N, N, 1, Kt, 1, K2, prec=prec)
+            ops.gemm(_p(dz), _p(x2), _p(dw, K1), N, K2, rows, 1, N, K2, 1, Kt, prec=prec)
+        db = ops.colsum(dz, rows, N, N)
+        return None, None, dx, dx2, dw, db
+
+
+class HeadsLinearFn(Function):
+    """Eight per-head nn.Linear(K -> d) applied to the same rows (networks/ANPDistractor.py:83-96)
+    as one grouped GEMM; output [rows, H*d] with head h in columns [h*d, (h+1)*d)."""
+
+    @staticmethod
+    def forward(ctx, prec, x, *wb):
+        H = len(wb) // 2
+        ws, bs = wb[:H], wb[H:]
+        x = x.contiguous()
+        K = x.shape[-1]
+        rows = x.numel() // K
+        d = ws[0].shape[0]
+        y = ops.empty((rows, H * d), x)
+        ops.gemm([_p(x)] * H, [_p(w) for w in ws], [_p(y, h * d) for h in range(H)], rows, d, K, K, 1, 1, K, H * d,
+                 bias=[_p(b) for b in bs], prec=prec)
+        ctx.prec, ctx.rows, ctx.H, ctx.d = prec, rows, H, d
+        ctx.save_for_backward(x, *ws)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, *ws = ctx.saved_tensors
+        prec, rows, H, d = ctx.prec, ctx.rows, ctx.H, ctx.d
+        K = x.shape[-1]
+        dy = dy.contiguous()
+        dw = ops.empty((H, d, K), x)
+        ops.gemm([_p(dy, h * d) for h in range(H)], [_p(x)] * H, [_p(dw, h * d * K) for h in range(H)], d, K, rows,
+                 1, H * d, K, 1, K, prec=prec)
+        db = ops.colsum(dy, rows, H * d, H * d)
+        dx = None
+        if ctx.needs_input_grad[1]:
+            dx = torch.empty_like(x)
+            for h in range(H):
+                ops.gemm(_p(dy, h * d), _p(ws[h]), _p(dx), rows, K, d, H * d, 1, K, 1, K, beta=0.0 if h == 0 else 1.0,
+                         prec=prec)
+        return (None, dx) + tuple(dw[h] for h in range(H)) + tuple(db[h * d:(h + 1) * d] for h in range(H))
+
+
+class AggregateFn(Function):
+    """mean / max over the context dimension (networks/CNPDistractor.py:96-101)."""
+
+    @staticmethod
+    def forward(ctx, mode, feats):
+        feats = feats.contiguous()
+        out, idx = ops.ctx_aggregate_fwd(feats, mode)
+        ctx.mode, ctx.shape, ctx.idx = mode, feats.shape, idx
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        T, nc, D = ctx.shape
+        return None, ops.ctx_aggregate_bwd(dout.contiguous(), ctx.idx, T, nc, D, ctx.mode)
+
+
+class RepeatFn(Function):
+    """x[:, None, :].repeat(1, rep, 1) (networks/CNPDistractor.py:99)."""
+
+    @staticmethod
+    def forward(ctx, rep, x):
+        ctx.rep = rep
+        return ops.repeat_rows(x.contiguous(), rep)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return None, ops.repeat_rows_bwd(dy.contiguous(), ctx.rep)
+
+
+# ================================================================================================
+# FAVOR+ attention (networks/fast_attention.py:74-99,151-156,187-205)
+# ================================================================================================
+class FavorAttentionFn(Function):
+    """q [T*nt, H*d], k, v [T*nc, H*d] (head-major columns) -> out [T*nt, d*H] (index e*H + h)."""
+
+    @staticmethod
+    def forward(ctx, prec, T, H, nt, nc, xq, xk, v, proj):
+        xq, xk, v = xq.contiguous(), xk.contiguous(), v.contiguous()
+        M, d = proj.shape
+        ldu = (M + 3) // 4 * 4
+        Rq, Rk = T * nt * H, T * nc * H
+        c = float(d) ** -0.25
+        U = ops.empty((Rq, ldu), xq)
+        W = ops.empty((Rk, ldu), xq)
+        ops.gemm(_p(xq), _p(proj), _p(U), Rq, M, d, d, 1, 1, d, ldu, alpha=c, prec=prec)
+        ops.gemm(_p(xk), _p(proj), _p(W), Rk, M, d, d, 1, 1, d, ldu, alpha=c, prec=prec)
+        sq, mq, amq = ops.empty((Rq,), xq), ops.empty((Rq,), xq), ops.empty((Rq,), xq, torch.int32)
+        tk, mk = ops.empty((Rk,), xq), ops.empty((Rk,), xq)
+        ops.check(ops.LIB.b200np_favor_rowstats(ops._ptr(xq), ops._ptr(U), ops._ptr(sq), ops._ptr(mq), ops._ptr(amq),
+                                                Rq, d, M, ldu, ops._stream()), "favor_rowstats(q)")
+        ops.check(ops.LIB.b200np_favor_rowstats(ops._ptr(xk), ops._ptr(W), ops._ptr(tk), ops._ptr(mk), ops._ptr(None),
+                                                Rk, d, M, ldu, ops._stream()), "favor_rowstats(k)")
+        g = ops.reduce(mk, 0)
+        dist.all_reduce_max(g)  # the key stabiliser is a max over the WHOLE meta-batch (fast_attention.py:97)
+        ties = ops.zeros((1,), xq)
+        out = ops.empty((T * nt, d * H), xq)
+        A = ops.empty((T * H * nt * nc,), xq)
+        Dn = ops.empty((T * H * nt,), xq)
+        ops.check(ops.LIB.b200np_favor_attn_fwd(*(ops._ptr(t) for t in (U, W, sq, mq, tk, g, v, out, A, Dn, ties)),
+                                                T, H, nt, nc, d, M, ldu, ops._stream()), "favor_attn_fwd")
+        ctx.dims = (prec, T, H, nt, nc, d, M, ldu)
+        ctx.save_for_backward(xq, xk, v, proj, U, W, sq, mq, amq, tk, g, out, A, Dn, ties)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        xq, xk, v, proj, U, W, sq, mq, amq, tk, g, out, A, Dn, ties = ctx.saved_tensors
+        prec, T, H, nt, nc, d, M, ldu = ctx.dims
+        Rq, Rk = T * nt * H, T * nc * H
+        c = float(d) ** -0.25
+        d_out = d_out.contiguous()
+        dU, dW = ops.empty((Rq, ldu), xq), ops.empty((Rk, ldu), xq)
+        dv = torch.empty_like(v)
+        ds, dt = ops.empty((Rq,), xq), ops.empty((Rk,), xq)
+        dg_part = ops.empty((T * H,), xq)
+        ops.check(ops.LIB.b200np_favor_attn_bwd(
+            *(ops._ptr(t) for t in (d_out, U, W, sq, mq, amq, tk, g, v, out, A, Dn, dU, dW, dv, ds, dt, dg_part)),
+            T, H, nt, nc, d, M, ldu, ops._stream()), "favor_attn_bwd")
+        dg = ops.reduce(dg_part, 1)
+        tie_total = ties
+        if dist.world_size() > 1:
+            tie_total = ties.clone()
+            dist.all_reduce_sum(dg)       # d loss / d g sums over every rank's keys
+            dist.all_reduce_sum(tie_total)
+        ops.check(ops.LIB.b200np_favor_key_fixup(ops._ptr(dW), ops._ptr(W), ops._ptr(g), ops._ptr(dg),
+                                                 ops._ptr(tie_total), Rk, M, ldu, ops._stream()), "favor_key_fixup")
+        dxq, dxk = torch.empty_like(xq), torch.empty_like(xk)
+        ops.gemm(_p(dU), _p(proj), _p(dxq), Rq, d, M, ldu, 1, d, 1, d, alpha=c, row_scale=ds, addend=xq, ld_add=d,
+                 prec=prec)
+        ops.gemm(_p(dW), _p(proj), _p(dxk), Rk, d, M, ldu, 1, d, 1, d, alpha=c, row_scale=dt, addend=xk, ld_add=d,
+                 prec=prec)
+        return None, None, None, None, None, dxq, dxk, dv, None
+
+
+# ================================================================================================
+# model families
+# ================================================================================================
+def _lin(act, x, x2, layer):
+    return LinearFn.apply(act, PRECISION, x, x2, layer.weight, layer.bias)
+
+
+def _trunk_params(holder):
+    ps = [holder.conv1.weight, holder.conv1.bias]
+    for st in holder.resnet.stages():
+        ps += [st.conv1.weight, st.conv1.bias, st.conv2.weight, st.conv2.bias,
+               st.downsample[0].weight, st.downsample[0].bias]
+    return ps
+
+
+def _heads(x, heads):
+    return HeadsLinearFn.apply(PRECISION, x, *[m.linear.weight for m in heads], *[m.linear.bias for m in heads])
+
+
+def _attention(m, T, nt, nc, k_in, v_in, q_in):
+    """_multihead_attention (networks/ANPDistractor.py:78-101)."""
+    H = m.n_heads
+    k = _heads(k_in, m._W_k)
+    v = _heads(v_in, m._W_v)
+    q = _heads(q_in, m._W_q)
+    att = FavorAttentionFn.apply(PRECISION, T, H, nt, nc, q, k, v, m.attn.projection_matrix)
+    return _lin(ACT_NONE, att, None, m._W.linear)
+
+
+def _check_inputs(m, ctx_x, ctx_y, tgt_x):
+    for t, name in ((ctx_x, "context images"), (ctx_y, "context labels"), (tgt_x, "target images")):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32):
+            raise RuntimeError(f"{name}: expected a float32 CUDA tensor (the B200 path has no CPU fallback)")
+    if tgt_x.shape[0] != m.task_num:
+        raise RuntimeError(f"batch has {tgt_x.shape[0]} tasks but config.tasks_per_batch={m.task_num} "
+                           "(same constraint as networks/models.py:115)")
+
+
+def _forward_resnet_family(m, ctx_x, ctx_y, tgt_x):
+    T, nc, nt = m.task_num, ctx_x.shape[1], tgt_x.shape[1]
+    C, H, W = m.img_channels, m.img_size[0], m.img_size[1]
+    tgt_imgs = tgt_x.reshape(T * nt, C, H, W).contiguous()
+    if nc:
+        ctx_imgs = ctx_x.reshape(T * nc, C, H, W).contiguous()
+        lab = ctx_y.reshape(T * nc, -1).contiguous()
+        if hasattr(m, "transform_y"):
+            lab = _lin(ACT_NONE, lab, None, m.transform_y)
+        enc = _trunk_params(m.img_encoder)
+        if m.attention:
+            x_ctx, x_tgt = TrunkFn.apply(m.img_agg, PRECISION, 2, ctx_imgs, tgt_imgs, *enc)
+        else:
+            if m.agg_mode not in ("mean", "max", "baco"):
+                raise TypeError("agg_mode is not applicable for CNP, choose from ['mean', 'max', 'baco']")
+            (x_ctx,) = TrunkFn.apply(m.img_agg, PRECISION, 1, ctx_imgs, *enc)
+        cf = _lin(ACT_RELU, x_ctx, lab, m.task_encoder[0])
+        cf = _lin(ACT_RELU, cf, None, m.task_encoder[2])
+        cf = _lin(ACT_RELU, cf, None, m.task_encoder[4])
+        if m.attention:
+            rep = _attention(m, T, nt, nc, x_ctx, cf, x_tgt)
+            sample = _lin(ACT_NONE, rep, None, m.mu)
+        else:
+            if m.agg_mode == "baco":
+                raise NotImplementedError("agg_mode='baco' is not on the CUDA path yet (SURVEY.md 8a/a8)")
+            r = AggregateFn.apply(0 if m.agg_mode == "mean" else 1, cf.view(T, nc, -1))
+            sample = RepeatFn.apply(nt, _lin(ACT_NONE, r, None, m.mu))
+    else:
+        sample = ops.zeros((T * nt, 256), tgt_imgs)
+    (x_dec,) = TrunkFn.apply(m.img_agg, PRECISION, 1, tgt_imgs, *_trunk_params(m.decoder))
+    fc = m.decoder.fc_mu
+    h = _lin(ACT_RELU, x_dec, sample, fc[0])
+    h = _lin(ACT_RELU, h, None, fc[2])
+    out = _lin(ACT_NONE, h, None, fc[4])
+    return out.view(T, nt, -1)
+
+
+def _forward_shapenet1d_family(m, ctx_x, ctx_y, tgt_x):
+    T, nc, nt = m.task_num, ctx_x.shape[1], tgt_x.shape[1]
+    C, H, W = m.img_channels, m.img_size[0], m.img_size[1]
+    e = m.encoder_w0
+    conv_params = [e[0].weight, e[0].bias, e[2].weight, e[2].bias, e[5].weight, e[5].bias]
+    tgt_imgs = tgt_x.reshape(T * nt, C, H, W).contiguous()
+    if nc:
+        ctx_imgs = ctx_x.reshape(T * nc, C, H, W).contiguous()
+        f_ctx, f_tgt = EncoderW0Fn.apply(PRECISION, 2, ctx_imgs, tgt_imgs, *conv_params)
+        x_ctx = _lin(ACT_NONE, f_ctx, None, e[8])
+        x_qry = _lin(ACT_NONE, f_tgt, None, e[8])
+        lab = _lin(ACT_NONE, ctx_y.reshape(T * nc, -1).contiguous(), None, m.transform_y)
+        L = m.encoder_r.layers
+        rs = _lin(ACT_RELU, x_ctx, lab, L[0])
+        rs = _lin(ACT_RELU, rs, None, L[2])
+        rs = _lin(ACT_NONE, rs, None, L[4])
+        if m.attention:
+            if m.agg_mode != "attention":
+                raise TypeError("agg_mode is not applicable for CNP, choose from ['attention']")
+            r = _attention(m, T, nt, nc, x_ctx, rs, x_qry)
+            z = _lin(ACT_NONE, r, None, m.r_to_z)
+        else:
+            if m.agg_mode == "baco":
+                raise NotImplementedError("agg_mode='baco' is not on the CUDA path yet (SURVEY.md 8a/a8)")
+            if m.agg_mode not in ("mean", "max"):
+                raise TypeError("agg_mode is not applicable for CNP, choose from ['mean', 'max', 'baco']")
+            r = AggregateFn.apply(0 if m.agg_mode == "mean" else 1, rs.view(T, nc, -1))
+            z = RepeatFn.apply(nt, _lin(ACT_NONE, r, None, m.r_to_z))
+    else:
+        (f_tgt,) = EncoderW0Fn.apply(PRECISION, 1, tgt_imgs, *conv_params)
+        x_qry = _lin(ACT_NONE, f_tgt, None, e[8])
+        z = ops.zeros((T * nt, m.dim_z), tgt_imgs)
+    D = m.decoder0
+    h = _lin(ACT_RELU, x_qry, z, D[0])
+    h = _lin(ACT_RELU, h, None, D[2])
+    out = _lin(ACT_TANH, h, None, D[4])
+    return out.view(T, nt, -1)
+
+
+def forward(model, ctx_x, ctx_y, tgt_x):
+    _check_inputs(model, ctx_x, ctx_y, tgt_x)
+    if model.family == "resnet":
+        return _forward_resnet_family(model, ctx_x, ctx_y, tgt_x)
+    return _forward_shapenet1d_family(model, ctx_x, ctx_y, tgt_x)

@@ -1,0 +1,291 @@
+"""Tensor-level wrappers over the C ABI: argument checking, output allocation (torch is used for
+device memory and streams only), and the call into libb200np.so on torch's current stream."""
+import ctypes as C
+
+import torch
+
+from . import lib
+from .lib import LIB, GemmDesc, check
+
+F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _chk(t, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise lib.B200NPError(f"{name}: tensor is on {t.device}; the B200 path has no CPU fallback")
+    if t.dtype != F32 and t.dtype not in (torch.int32, torch.int8):
+        raise lib.B200NPError(f"{name}: dtype {t.dtype} unsupported")
+    if not t.is_contiguous():
+        raise lib.B200NPError(f"{name}: tensor must be contiguous")
+
+
+def empty(shape, like, dtype=F32):
+    return torch.empty(shape, device=like.device, dtype=dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# convolutions
+# ----------------------------------------------------------------------------------------------
+def conv_small_fwd(x, w, b, out=None, relu=True):
+    """x NCHW [N,Cin,H,W] -> NHWC [N,H/2,W/2,Cout] (stride 2, pad R//2)."""
+    for t, n in ((x, "x"), (w, "w"), (b, "b"), (out, "out")):
+        _chk(t, n)
+    N, Cin, H, W = x.shape
+    Cout, _, R, _ = w.shape
+    if out is None:
+        out = empty((N, H // 2, W // 2, Cout), x)
+    check(LIB.b200np_conv_small_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(out), N, Cin, H, W, Cout, R, 2, R // 2,
+                                    int(relu), _stream()), "conv_small_fwd")
+    return out
+
+
+def conv_small_wgrad(x, dy, w_shape):
+    N, Cin, H, W = x.shape
+    Cout, _, R, _ = w_shape
+    _chk(x, "x"), _chk(dy, "dy")
+    ws_bytes = LIB.b200np_conv_small_wgrad_workspace(N, Cin, H, W, Cout, R, 2, R // 2)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=x.device, dtype=F32)
+    dw = empty(tuple(w_shape), x)
+    db = empty((Cout,), x)
+    check(LIB.b200np_conv_small_wgrad(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), N, Cin, H, W, Cout, R, 2, R // 2,
+                                      _ptr(ws), ws_bytes, _stream()), "conv_small_wgrad")
+    return dw, db
+
+
+def pack_conv_weight(w, want_fwd=True, want_dgrad=True):
+    """torch [Cout,Cin,R,R] -> wf [R*R][Cout][Cin], wd [R*R][Cin][Cout]."""
+    _chk(w, "w")
+    Cout, Cin, R, _ = w.shape
+    wf = empty((R * R, Cout, Cin), w) if want_fwd else None
+    wd = empty((R * R, Cin, Cout), w) if want_dgrad else None
+    check(LIB.b200np_pack_conv_weight(_ptr(w), _ptr(wf), _ptr(wd), Cout, Cin, R, _stream()), "pack_conv_weight")
+    return wf, wd
+
+
+def conv_fwd(x, wf, bias, R, stride, act, prec, skip=None):
+    """x NHWC; skip = (xs, wsf, bias_s, stride_s) fuses a 1x1 projection of xs into the output."""
+    _chk(x, "x"), _chk(wf, "wf"), _chk(bias, "bias")
+    N, H, W, Cin = x.shape
+    Cout = wf.shape[1]
+    y = empty((N, H // stride, W // stride, Cout), x)
+    xs = wsf = bs = None
+    Cs, ss = 0, 1
+    if skip is not None:
+        xs, wsf, bs, ss = skip
+        _chk(xs, "xs"), _chk(wsf, "wsf"), _chk(bs, "bias_s")
+        Cs = xs.shape[3]
+    check(LIB.b200np_conv_fwd(_ptr(x), _ptr(wf), _ptr(bias), _ptr(y), N, H, W, Cin, Cout, R, stride, _ptr(xs),
+                              _ptr(wsf), _ptr(bs), Cs, ss, act, prec, _stream()), "conv_fwd")
+    return y
+
+
+def conv_dgrad(dy, wd, x_shape, R, stride, prec, mask_src=None, skip=None):
+    """dy NHWC [N,H/stride,W/stride,Cout] -> dx [N,H,W,Cin], gated by mask_src > 0;
+    skip = (dys, wsd, stride_s) adds the gradient through a 1x1 stride_s projection."""
+    _chk(dy, "dy"), _chk(wd, "wd"), _chk(mask_src, "mask")
+    N, H, W, Cin = x_shape
+    Cout = dy.shape[3]
+    dx = empty(tuple(x_shape), dy)
+    dys = wsd = None
+    Cs, ss = 0, 1
+    if skip is not None:
+        dys, wsd, ss = skip
+        _chk(dys, "dys"), _chk(wsd, "wsd")
+        Cs = dys.shape[3]
+    check(LIB.b200np_conv_dgrad(_ptr(dy), _ptr(wd), _ptr(dx), _ptr(mask_src), N, H, W, Cin, Cout, R, stride,
+                                _ptr(dys), _ptr(wsd), Cs, ss, prec, _stream()), "conv_dgrad")
+    return dx
+
+
+def conv_wgrad(x, dy, R, stride, prec, want_db=True):
+    _chk(x, "x"), _chk(dy, "dy")
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    ws_bytes = LIB.b200np_conv_wgrad_workspace(N, H, W, Cin, Cout, R, stride)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=x.device, dtype=F32)
+    dw = empty((Cout, Cin, R, R), x)
+    db = empty((Cout,), x) if want_db else None
+    check(LIB.b200np_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), N, H, W, Cin, Cout, R, stride, prec,
+                                _ptr(ws), ws_bytes, _stream()), "conv_wgrad")
+    return dw, db
+
+
+# ----------------------------------------------------------------------------------------------
+# pooling / flatten
+# ----------------------------------------------------------------------------------------------
+def amp2_flatten_fwd(x, out=None, idx=None):
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    out = empty((N, Cc * 4), x) if out is None else out
+    idx = empty((N, Cc * 4), x, torch.int32) if idx is None else idx
+    check(LIB.b200np_adaptive_maxpool2x2_flatten_fwd(_ptr(x), _ptr(out), _ptr(idx), N, H, W, Cc, _stream()),
+          "adaptive_maxpool2x2_flatten_fwd")
+    return out, idx
+
+
+def amp2_flatten_bwd(dout, idx, x_saved, dx):
+    _chk(dout, "dout")
+    N, H, W, Cc = x_saved.shape
+    check(LIB.b200np_adaptive_maxpool2x2_flatten_bwd(_ptr(dout), _ptr(idx), _ptr(x_saved), _ptr(dx), N, H, W, Cc,
+                                                     _stream()), "adaptive_maxpool2x2_flatten_bwd")
+    return dx
+
+
+def nhwc_to_nchw_flat(x, out=None):
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    out = empty((N, Cc * H * W), x) if out is None else out
+    check(LIB.b200np_nhwc_to_nchw_flat(_ptr(x), _ptr(out), N, H, W, Cc, _stream()), "nhwc_to_nchw_flat")
+    return out
+
+
+def nchw_flat_to_nhwc(dout, x_saved, dx, mask=True):
+    _chk(dout, "dout")
+    N, H, W, Cc = dx.shape
+    check(LIB.b200np_nchw_flat_to_nhwc(_ptr(dout), _ptr(x_saved if mask else None), _ptr(dx), N, H, W, Cc,
+                                       _stream()), "nchw_flat_to_nhwc")
+    return dx
+
+
+def maxpool2x2_fwd(x):
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    y = empty((N, H // 2, W // 2, Cc), x)
+    idx = empty((N, H // 2, W // 2, Cc), x, torch.int8)
+    check(LIB.b200np_maxpool2x2_fwd(_ptr(x), _ptr(y), _ptr(idx), N, H, W, Cc, _stream()), "maxpool2x2_fwd")
+    return y, idx
+
+
+def maxpool2x2_bwd(dy, idx, x_saved):
+    _chk(dy, "dy")
+    N, H, W, Cc = x_saved.shape
+    dx = empty((N, H, W, Cc), dy)
+    check(LIB.b200np_maxpool2x2_bwd(_ptr(dy), _ptr(idx), _ptr(x_saved), _ptr(dx), N, H, W, Cc, _stream()),
+          "maxpool2x2_bwd")
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# GEMM and friends
+# ----------------------------------------------------------------------------------------------
+def gemm(A, B, Cmat, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, bias=None, alpha=1.0, beta=0.0, act=lib.ACT_NONE,
+         row_scale=None, addend=None, ld_add=0, prec=lib.PREC_FP32_SIMT):
+    """A, B, Cmat, bias: device pointers (ints) or lists of up to 8 of them (grouped)."""
+    d = GemmDesc()
+    As = A if isinstance(A, (list, tuple)) else [A]
+    Bs = B if isinstance(B, (list, tuple)) else [B]
+    Cs = Cmat if isinstance(Cmat, (list, tuple)) else [Cmat]
+    bs = bias if isinstance(bias, (list, tuple)) else [bias] * len(As)
+    g = len(As)
+    assert len(Bs) == g and len(Cs) == g and len(bs) == g and g <= 8
+    for i in range(g):
+        d.A[i], d.B[i], d.C[i], d.bias[i] = As[i], Bs[i], Cs[i], bs[i] or 0
+    d.groups, d.M, d.N, d.K = g, M, N, K
+    d.a_rs, d.a_cs, d.b_rs, d.b_cs, d.ldc = a_rs, a_cs, b_rs, b_cs, ldc
+    d.alpha, d.beta, d.act = alpha, beta, act
+    d.row_scale = 0 if row_scale is None else row_scale.data_ptr()
+    d.addend = 0 if addend is None else addend.data_ptr()
+    d.ld_add, d.precision = ld_add, prec
+    check(LIB.b200np_gemm(C.byref(d), _stream()), "gemm")
+
+
+def act_bwd(dy, y, act):
+    _chk(dy, "dy"), _chk(y, "y")
+    dz = torch.empty_like(dy)
+    check(LIB.b200np_act_bwd(_ptr(dy), _ptr(y), _ptr(dz), dy.numel(), act, _stream()), "act_bwd")
+    return dz
+
+
+def colsum(x, rows, cols, ld, out=None):
+    _chk(x, "x")
+    out = empty((cols,), x) if out is None else out
+    ws_bytes = LIB.b200np_colsum_workspace(rows, cols)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=x.device, dtype=F32)
+    check(LIB.b200np_colsum(_ptr(x), _ptr(out), rows, cols, ld, _ptr(ws), ws_bytes, _stream()), "colsum")
+    return out
+
+
+def fill(x, value):
+    check(LIB.b200np_fill(_ptr(x), x.numel(), float(value), _stream()), "fill")
+    return x
+
+
+def zeros(shape, like):
+    return fill(empty(shape, like), 0.0)
+
+
+def axpy(y, x, a=1.0):
+    check(LIB.b200np_axpy(_ptr(y), _ptr(x), y.numel(), float(a), _stream()), "axpy")
+    return y
+
+
+def repeat_rows(x, rep):
+    rows, cols = x.shape
+    y = empty((rows * rep, cols), x)
+    check(LIB.b200np_repeat_rows(_ptr(x), _ptr(y), rows, rep, cols, _stream()), "repeat_rows")
+    return y
+
+
+def repeat_rows_bwd(dy, rep):
+    rows, cols = dy.shape[0] // rep, dy.shape[1]
+    dx = empty((rows, cols), dy)
+    check(LIB.b200np_repeat_rows_bwd(_ptr(dy), _ptr(dx), rows, rep, cols, _stream()), "repeat_rows_bwd")
+    return dx
+
+
+def scale_by_device_scalar(x, s):
+    y = torch.empty_like(x)
+    check(LIB.b200np_scale_by_device_scalar(_ptr(x), _ptr(s), _ptr(y), x.numel(), _stream()), "scale")
+    return y
+
+
+def reduce(x, op):
+    out = empty((1,), x)
+    check(LIB.b200np_reduce(_ptr(x), x.numel(), _ptr(out), op, _stream()), "reduce")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# aggregation, loss, optimizer
+# ----------------------------------------------------------------------------------------------
+def ctx_aggregate_fwd(feats, mode):
+    _chk(feats, "feats")
+    T, nc, D = feats.shape
+    out = empty((T, D), feats)
+    idx = empty((T, D), feats, torch.int32) if mode == 1 else None
+    check(LIB.b200np_ctx_aggregate_fwd(_ptr(feats), _ptr(out), _ptr(idx), T, nc, D, mode, _stream()),
+          "ctx_aggregate_fwd")
+    return out, idx
+
+
+def ctx_aggregate_bwd(dout, idx, T, nc, D, mode):
+    _chk(dout, "dout")
+    df = empty((T, nc, D), dout)
+    check(LIB.b200np_ctx_aggregate_bwd(_ptr(dout), _ptr(idx), _ptr(df), T, nc, D, mode, _stream()),
+          "ctx_aggregate_bwd")
+    return df
+
+
+def loss_fwd_bwd(mu, y, kind, want_grad=True):
+    _chk(mu, "mu"), _chk(y, "y")
+    R = mu.numel() // mu.shape[-1]
+    loss = empty((1,), mu)
+    dmu = torch.empty_like(mu) if want_grad else None
+    check(LIB.b200np_loss_fwd_bwd(_ptr(mu), _ptr(y), _ptr(loss), _ptr(dmu), R, mu.shape[-1], y.shape[-1], kind,
+                                  _stream()), "loss_fwd_bwd")
+    return loss, dmu
+
+
+def adam_step(p, g, m, v, n, lr, b1, b2, eps, wd, step, grad_scale=1.0):
+    check(LIB.b200np_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, step, grad_scale,
+                               _stream()), "adam_step")

@@ -1,0 +1,81 @@
+"""Flat parameter / gradient buffers and the fused Adam step.
+
+``flatten_module`` re-homes every parameter of a model into one contiguous fp32 buffer (each
+``nn.Parameter`` becomes a view, so ``state_dict`` / ``load_state_dict`` / ``parameters()`` keep
+working) and gives every parameter a ``.grad`` view into one flat gradient buffer.  That turns
+the optimizer step into ONE HBM-bound kernel launch and the data-parallel gradient exchange into
+ONE NCCL all-reduce.  Parameters that never receive a gradient (the dead ``resnet.fc`` layers,
+SURVEY.md 8a/a14) are placed after the live ones and skipped, exactly like torch.optim.Adam skips
+``p.grad is None``.
+"""
+import torch
+
+from . import dist, ops
+
+
+class FlatParams:
+    def __init__(self, module, dead=lambda name: ".resnet.fc." in name):
+        named = list(module.named_parameters())
+        live = [(n, p) for n, p in named if not dead(n)]
+        rest = [(n, p) for n, p in named if dead(n)]
+        dev = named[0][1].device
+        pad = lambda k: (k + 3) // 4 * 4  # keep every view 16-byte aligned
+        self.n_live = sum(pad(p.numel()) for _, p in live)
+        total = self.n_live + sum(pad(p.numel()) for _, p in rest)
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(self.n_live, device=dev, dtype=torch.float32)
+        self.live, self.views = [], {}
+        off = 0
+        for n, p in live + rest:
+            k = p.numel()
+            view = self.flat[off:off + k].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            if off < self.n_live:
+                self.live.append((n, p, off, k))
+            off += pad(k)
+
+    def attach_grads(self):
+        """Point every live parameter's .grad at its slice of the flat gradient buffer."""
+        for _, p, off, k in self.live:
+            p.grad = self.grad[off:off + k].view_as(p)
+
+    def gather_grads(self):
+        """After autograd: make sure every .grad lives in the flat buffer (copy only if autograd
+        replaced the view with its own tensor)."""
+        for _, p, off, k in self.live:
+            view = self.grad[off:off + k].view_as(p)
+            g = p.grad
+            if g is None:
+                ops.fill(view, 0.0)
+            elif g.data_ptr() != view.data_ptr():
+                view.copy_(g)
+            p.grad = view
+
+    def zero_grad(self):
+        ops.fill(self.grad, 0.0)
+        self.attach_grads()
+
+
+class FusedAdam:
+    """torch.optim.Adam semantics (train.py:52-56: lr from config, betas (0.9, 0.999), eps 1e-8,
+    optional L2 weight decay) as one kernel over the flat live-parameter segment."""
+
+    def __init__(self, flat: FlatParams, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.flat, self.lr, self.betas, self.eps, self.wd = flat, lr, betas, eps, weight_decay
+        self.m = torch.zeros_like(flat.grad)
+        self.v = torch.zeros_like(flat.grad)
+        self.t = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.zero_grad()
+
+    def step(self):
+        f = self.flat
+        f.gather_grads()
+        world = dist.world_size()
+        if world > 1:
+            dist.all_reduce_grads(f.grad)
+        self.t += 1
+        ops.adam_step(f.flat, f.grad, self.m, self.v, f.n_live, self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.wd, self.t, 1.0 / world)

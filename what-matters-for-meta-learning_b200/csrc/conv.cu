@@ -1,0 +1,188 @@
+// C ABI of the channel-dense NHWC convolutions: builds tap tables (tapconv.cuh) for forward,
+// data-gradient and weight-gradient and dispatches to the tcgen05 kernels (64-channel layers) or
+// the CUDA-core kernels (fp32 validation mode; 32/48-channel layers of encoder_w0).
+#include "tapconv.cuh"
+
+using namespace b200np;
+
+namespace {
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd,
+                                   int Cout, int Cin, int RR) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = Cout * Cin * RR;
+  if (i >= total) return;
+  // torch layout: ((co*Cin + ci)*RR + t)
+  int t = i % RR, r = i / RR;
+  int ci = r % Cin, co = r / Cin;
+  float v = w[i];
+  if (wf) wf[((long long)t * Cout + co) * Cin + ci] = v;
+  if (wd) wd[((long long)t * Cin + ci) * Cout + co] = v;
+}
+
+// dw[co][ci][t] = sum_chunks part[chunk][t][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int chunks, int ntaps,
+                                    int Cout, int Cin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // index in part order (t, co, ci): coalesced reads
+  int per = ntaps * Cout * Cin;
+  if (i >= per) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += part[(long long)c * per + i];
+  int ci = i % Cin, r = i / Cin;
+  int co = r % Cout, t = r / Cout;
+  dw[((long long)co * Cin + ci) * ntaps + t] = s;
+}
+
+int wgrad_chunks(long long M, int ntaps) {
+  long long want = ceil_div(4LL * kNumSMs, ntaps);
+  long long maxc = ceil_div(M, 64);
+  if (want > maxc) want = maxc;
+  return (int)(want < 1 ? 1 : want);
+}
+long long wgrad_pix_per_chunk(long long M, int chunks) { return ceil_div(ceil_div(M, chunks), 16) * 16; }
+
+bool use_umma(int precision, int Cin, int Cout) {
+  return precision != B200NP_PREC_FP32_SIMT && Cin == 64 && Cout == 64;
+}
+
+int run_tapconv(const TapConvArgs& a, int precision, cudaStream_t st) {
+  if (use_umma(precision, a.Cin, a.Cout)) {
+    int rc = launch_tapconv_umma(a, precision, st);
+    if (rc != B200NP_E_UNSUPPORTED) return rc;
+  }
+  return launch_tapconv_simt(a, st);
+}
+
+}  // namespace
+
+extern "C" size_t b200np_colsum_workspace(long long rows, int cols);
+extern "C" int b200np_colsum(const float* x, float* out, long long rows, int cols, long long ld, void* ws,
+                             size_t ws_bytes, void* stream);
+
+extern "C" int b200np_pack_conv_weight(const float* w, float* wf, float* wd, int Cout, int Cin, int R,
+                                       void* stream) {
+  if (!w || (!wf && !wd) || Cout <= 0 || Cin <= 0 || R <= 0) return B200NP_E_BADARG;
+  int total = Cout * Cin * R * R;
+  pack_weight_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, wf, wd, Cout, Cin, R * R);
+  return launch_status();
+}
+
+extern "C" int b200np_conv_fwd(const float* x, const float* wf, const float* bias, float* y, int N, int H, int W,
+                               int Cin, int Cout, int R, int stride, const float* xs, const float* wsf,
+                               const float* bias_s, int Cs, int stride_s, int act, int precision, void* stream) {
+  if (!x || !wf || !y || N <= 0 || H <= 0 || W <= 0) return B200NP_E_BADARG;
+  if ((R != 1 && R != 3) || (stride != 1 && stride != 2) || H % stride || W % stride) return B200NP_E_UNSUPPORTED;
+  if (xs && (!wsf || Cs != Cin || stride_s < 1)) return B200NP_E_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(wf) || !aligned16(y) || (xs && (!aligned16(xs) || !aligned16(wsf))))
+    return B200NP_E_BADARG;
+  TapConvArgs a{};
+  a.src[0] = x; a.srcH[0] = H; a.srcW[0] = W; a.in_s[0] = stride; a.w[0] = wf;
+  a.Cin = Cin; a.Cout = Cout; a.bias = bias; a.bias2 = xs ? bias_s : nullptr;
+  a.dst = y; a.mask = nullptr;
+  a.N = N; a.OH = H / stride; a.OW = W / stride;
+  a.dstH = a.OH; a.dstW = a.OW; a.dst_s = 1; a.dst_oy = 0; a.dst_ox = 0;
+  a.act = act;
+  int nt = 0;
+  const int pad = R / 2;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < R; ++s) a.taps[nt++] = Tap{0, (int8_t)(r - pad), (int8_t)(s - pad), (int8_t)(r * R + s)};
+  if (xs) {
+    a.src[1] = xs; a.srcH[1] = a.OH * stride_s; a.srcW[1] = a.OW * stride_s; a.in_s[1] = stride_s; a.w[1] = wsf;
+    a.taps[nt++] = Tap{1, 0, 0, 0};
+  }
+  a.ntaps = nt;
+  return run_tapconv(a, precision, as_stream(stream));
+}
+
+extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, const float* mask_src, int N, int H,
+                                 int W, int Cin, int Cout, int R, int stride, const float* dys, const float* wsd,
+                                 int Cs, int stride_s, int precision, void* stream) {
+  if (!dy || !wd || !dx || N <= 0 || H <= 0 || W <= 0) return B200NP_E_BADARG;
+  if ((R != 1 && R != 3) || (stride != 1 && stride != 2) || H % stride || W % stride) return B200NP_E_UNSUPPORTED;
+  if (dys && (!wsd || Cs != Cout || stride_s != stride || stride != 2)) return B200NP_E_UNSUPPORTED;
+  if (!aligned16(dy) || !aligned16(wd) || !aligned16(dx) || (mask_src && !aligned16(mask_src)) ||
+      (dys && (!aligned16(dys) || !aligned16(wsd))))
+    return B200NP_E_BADARG;
+  const int pad = R / 2;
+  const int OHc = H / stride, OWc = W / stride;  // dy geometry
+  TapConvArgs a{};
+  a.src[0] = dy; a.srcH[0] = OHc; a.srcW[0] = OWc; a.in_s[0] = 1; a.w[0] = wd;
+  a.src[1] = dys; a.srcH[1] = OHc; a.srcW[1] = OWc; a.in_s[1] = 1; a.w[1] = wsd;
+  a.Cin = Cout;  // reduction runs over the conv's output channels
+  a.Cout = Cin;  // and produces the conv's input channels
+  a.bias = a.bias2 = nullptr;
+  a.dst = dx; a.mask = mask_src;
+  a.N = N; a.dstH = H; a.dstW = W;
+  a.act = B200NP_ACT_NONE;
+  cudaStream_t st = as_stream(stream);
+  if (stride == 1) {
+    a.OH = H; a.OW = W; a.dst_s = 1; a.dst_oy = a.dst_ox = 0;
+    int nt = 0;
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < R; ++s) a.taps[nt++] = Tap{0, (int8_t)(pad - r), (int8_t)(pad - s), (int8_t)(r * R + s)};
+    a.ntaps = nt;
+    return run_tapconv(a, precision, st);
+  }
+  // stride 2: one launch per parity class of the input pixel (iy,ix) = (2*oy+py, 2*ox+px).
+  // y[o] = sum_r x[2o + r - pad] w[r]  =>  dx[i] = sum_{r : (i + pad - r) even} dy[(i + pad - r)/2] w[r]
+  a.OH = OHc; a.OW = OWc; a.dst_s = 2;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      int nt = 0;
+      for (int r = 0; r < R; ++r) {
+        if ((py + pad - r) & 1) continue;
+        for (int s = 0; s < R; ++s) {
+          if ((px + pad - s) & 1) continue;
+          a.taps[nt++] = Tap{0, (int8_t)((py + pad - r) / 2), (int8_t)((px + pad - s) / 2), (int8_t)(r * R + s)};
+        }
+      }
+      if (dys && py == 0 && px == 0) a.taps[nt++] = Tap{1, 0, 0, 0};
+      a.ntaps = nt;
+      a.dst_oy = py; a.dst_ox = px;
+      int rc = run_tapconv(a, precision, st);
+      if (rc != B200NP_OK) return rc;
+    }
+  return B200NP_OK;
+}
+
+extern "C" size_t b200np_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int stride) {
+  if (N <= 0 || stride <= 0) return 0;
+  long long M = (long long)N * (H / stride) * (W / stride);
+  int nt = R * R;
+  int chunks = wgrad_chunks(M, nt);
+  size_t part = (size_t)chunks * nt * Cout * Cin * sizeof(float);
+  return part + b200np_colsum_workspace(M, Cout);
+}
+
+extern "C" int b200np_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int Cin,
+                                 int Cout, int R, int stride, int precision, void* ws, size_t ws_bytes, void* stream) {
+  if (!x || !dy || !dw || N <= 0 || H <= 0 || W <= 0) return B200NP_E_BADARG;
+  if ((R != 1 && R != 3) || (stride != 1 && stride != 2) || H % stride || W % stride) return B200NP_E_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(ws)) return B200NP_E_BADARG;
+  if (!ws || ws_bytes < b200np_conv_wgrad_workspace(N, H, W, Cin, Cout, R, stride)) return B200NP_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  TapWgradArgs a{};
+  a.src = x; a.srcH = H; a.srcW = W; a.in_s = stride; a.Cin = Cin;
+  a.dy = dy; a.N = N; a.OH = H / stride; a.OW = W / stride; a.Cout = Cout;
+  const int pad = R / 2;
+  int nt = 0;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < R; ++s) a.taps[nt++] = Tap{0, (int8_t)(r - pad), (int8_t)(s - pad), (int8_t)(r * R + s)};
+  a.ntaps = nt;
+  const long long M = (long long)N * a.OH * a.OW;
+  a.chunks = wgrad_chunks(M, nt);
+  a.pix_per_chunk = wgrad_pix_per_chunk(M, a.chunks);
+  a.part = (float*)ws;
+  int rc = B200NP_E_UNSUPPORTED;
+  if (use_umma(precision, Cin, Cout)) rc = launch_tapwgrad_umma(a, precision, st);
+  if (rc == B200NP_E_UNSUPPORTED) rc = launch_tapwgrad_simt(a, st);
+  if (rc != B200NP_OK) return rc;
+  int per = nt * Cout * Cin;
+  wgrad_reduce_kernel<<<(per + 255) / 256, 256, 0, st>>>(a.part, dw, a.chunks, nt, Cout, Cin);
+  if (db) {
+    size_t part_bytes = (size_t)a.chunks * per * sizeof(float);
+    rc = b200np_colsum(dy, db, M, Cout, Cout, (char*)ws + part_bytes, ws_bytes - part_bytes, stream);
+    if (rc != B200NP_OK) return rc;
+  }
+  return launch_status(1);
+}

@@ -1,0 +1,375 @@
+// Elementwise / reduction kernels: HBM-bound, coalesced, vectorised where alignment allows.
+#include <math.h>
+
+#include "common.cuh"
+
+using namespace b200np;
+
+extern "C" const char* b200np_strerror(int code) {
+  switch (code) {
+    case B200NP_OK: return "ok";
+    case B200NP_E_BADARG: return "bad argument (dimension / pointer / alignment precondition)";
+    case B200NP_E_LAUNCH: return "CUDA launch failure";
+    case B200NP_E_WORKSPACE: return "workspace too small";
+    case B200NP_E_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+namespace b200np { std::atomic<long long> g_launches{0}; }
+extern "C" int b200np_version(void) { return B200NP_VERSION; }
+extern "C" long long b200np_launch_count(void) { return b200np::g_launches.load(); }
+extern "C" int b200np_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B200NP_E_LAUNCH;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return B200NP_E_LAUNCH;
+  return major == 10 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += st) x[i] = v;
+}
+extern "C" int b200np_fill(float* x, long long n, float value, void* stream) {
+  if (n <= 0) return B200NP_OK;
+  if (!x) return B200NP_E_BADARG;
+  fill_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, n, value);
+  return launch_status();
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, long long n, float a) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += st) y[i] = fmaf(a, x[i], y[i]);
+}
+extern "C" int b200np_axpy(float* y, const float* x, long long n, float a, void* stream) {
+  if (n <= 0) return B200NP_OK;
+  if (!x || !y) return B200NP_E_BADARG;
+  axpy_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(y, x, n, a);
+  return launch_status();
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                               float* __restrict__ dz, long long n, int act) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += st) {
+    float g = dy[i], o = y[i];
+    dz[i] = act == B200NP_ACT_RELU ? (o > 0.f ? g : 0.f) : act == B200NP_ACT_TANH ? g * (1.f - o * o) : g;
+  }
+}
+extern "C" int b200np_act_bwd(const float* dy, const float* y, float* dz, long long n, int act,
+                              void* stream) {
+  if (n <= 0) return B200NP_OK;
+  if (!dy || !y || !dz) return B200NP_E_BADARG;
+  act_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(dy, y, dz, n, act);
+  return launch_status();
+}
+
+__global__ void scale_dev_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                 float* __restrict__ y, long long n) {
+  float a = __ldg(s);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += st) y[i] = a * x[i];
+}
+extern "C" int b200np_scale_by_device_scalar(const float* x, const float* scale, float* y, long long n,
+                                             void* stream) {
+  if (n <= 0) return B200NP_OK;
+  if (!x || !scale || !y) return B200NP_E_BADARG;
+  scale_dev_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, scale, y, n);
+  return launch_status();
+}
+
+__global__ void repeat_rows_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows_in,
+                                   int rep, int cols) {
+  long long total = rows_in * rep * cols;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += st) {
+    long long r = i / cols;
+    int c = (int)(i - r * cols);
+    y[i] = x[(r / rep) * cols + c];
+  }
+}
+extern "C" int b200np_repeat_rows(const float* x, float* y, long long rows_in, int rep, int cols,
+                                  void* stream) {
+  long long n = rows_in * rep * cols;
+  if (n <= 0) return B200NP_OK;
+  if (!x || !y) return B200NP_E_BADARG;
+  repeat_rows_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, y, rows_in, rep, cols);
+  return launch_status();
+}
+__global__ void repeat_rows_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                                       long long rows_in, int rep, int cols) {
+  long long total = rows_in * cols;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += st) {
+    long long r = i / cols;
+    int c = (int)(i - r * cols);
+    float s = 0.f;
+    for (int k = 0; k < rep; ++k) s += dy[(r * rep + k) * cols + c];
+    dx[i] = s;
+  }
+}
+extern "C" int b200np_repeat_rows_bwd(const float* dy, float* dx, long long rows_in, int rep, int cols,
+                                      void* stream) {
+  long long n = rows_in * cols;
+  if (n <= 0) return B200NP_OK;
+  if (!dy || !dx) return B200NP_E_BADARG;
+  repeat_rows_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(dy, dx, rows_in, rep, cols);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums (bias gradients), deterministic two-stage: blocks of (32 columns x 8 row lanes)
+// reduce a contiguous row chunk into ws[chunk][col]; a second kernel folds the chunks in order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kColsumChunksMax = 592;  // 4 x 148
+static int colsum_chunks(long long rows) {
+  long long c = ceil_div(rows, 256);
+  if (c > kColsumChunksMax) c = kColsumChunksMax;
+  return (int)(c < 1 ? 1 : c);
+}
+__global__ void colsum_stage1(const float* __restrict__ x, float* __restrict__ part, long long rows,
+                              int cols, long long ld, int chunks) {
+  __shared__ float sm[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int chunk = blockIdx.y;
+  long long per = (rows + chunks - 1) / chunks;
+  long long r0 = chunk * per, r1 = r0 + per < rows ? r0 + per : rows;
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += x[r * ld + c];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    part[(long long)chunk * cols + c] = t;
+  }
+}
+__global__ void colsum_stage2(const float* __restrict__ part, float* __restrict__ out, int cols, int chunks) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += part[(long long)k * cols + c];
+  out[c] = s;
+}
+extern "C" size_t b200np_colsum_workspace(long long rows, int cols) {
+  return (size_t)colsum_chunks(rows) * (size_t)cols * sizeof(float);
+}
+extern "C" int b200np_colsum(const float* x, float* out, long long rows, int cols, long long ld, void* ws,
+                             size_t ws_bytes, void* stream) {
+  if (cols <= 0) return B200NP_OK;
+  if (!x || !out || rows < 0 || ld < cols) return B200NP_E_BADARG;
+  if (rows == 0) return b200np_fill(out, cols, 0.f, stream);
+  int chunks = colsum_chunks(rows);
+  if (!ws || ws_bytes < (size_t)chunks * cols * sizeof(float)) return B200NP_E_WORKSPACE;
+  dim3 grid((cols + 31) / 32, chunks), block(32, 8);
+  colsum_stage1<<<grid, block, 0, as_stream(stream)>>>(x, (float*)ws, rows, cols, ld, chunks);
+  colsum_stage2<<<(cols + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)ws, out, cols, chunks);
+  return launch_status(2);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void max_reduce_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, x[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    t = warp_max(t);
+    if (threadIdx.x == 0) out[0] = t;
+  }
+}
+extern "C" int b200np_max_reduce(const float* x, long long n, float* out, void* stream) {
+  if (!x || !out || n <= 0) return B200NP_E_BADARG;
+  max_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n, out);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// CNP context aggregation: feats [T,nc,D] -> out [T,D]; one thread per (task, feature), the
+// context loop strides by D so every load is coalesced across the warp.
+// ------------------------------------------------------------------------------------------------
+__global__ void ctx_agg_fwd_kernel(const float* __restrict__ f, float* __restrict__ out,
+                                   int32_t* __restrict__ idx, int T, int nc, int D, int mode) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * D) return;
+  int t = (int)(i / D), c = (int)(i - (long long)t * D);
+  const float* p = f + (long long)t * nc * D + c;
+  if (mode == 0) {
+    float s = 0.f;
+    for (int j = 0; j < nc; ++j) s += p[(long long)j * D];
+    out[i] = s / (float)nc;
+  } else {
+    float m = p[0];
+    int a = 0;
+    for (int j = 1; j < nc; ++j) {
+      float v = p[(long long)j * D];
+      if (v > m) { m = v; a = j; }  // strict '>' keeps the FIRST maximum (torch.max(dim) rule)
+    }
+    out[i] = m;
+    if (idx) idx[i] = a;
+  }
+}
+__global__ void ctx_agg_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
+                                   float* __restrict__ df, int T, int nc, int D, int mode) {
+  long long n = (long long)T * nc * D;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += st) {
+    int c = (int)(i % D);
+    long long tj = i / D;
+    int j = (int)(tj % nc);
+    long long t = tj / nc;
+    float g = dout[t * D + c];
+    df[i] = mode == 0 ? g / (float)nc : (idx[t * D + c] == j ? g : 0.f);
+  }
+}
+extern "C" int b200np_ctx_aggregate_fwd(const float* feats, float* out, int32_t* idx, int T, int nc, int D,
+                                        int mode, void* stream) {
+  if (!feats || !out || T <= 0 || nc <= 0 || D <= 0 || (mode != 0 && mode != 1)) return B200NP_E_BADARG;
+  if (mode == 1 && !idx) return B200NP_E_BADARG;
+  long long n = (long long)T * D;
+  ctx_agg_fwd_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(feats, out, idx, T, nc, D, mode);
+  return launch_status();
+}
+extern "C" int b200np_ctx_aggregate_bwd(const float* dout, const int32_t* idx, float* dfeats, int T, int nc,
+                                        int D, int mode, void* stream) {
+  if (!dout || !dfeats || T <= 0 || nc <= 0 || D <= 0 || (mode != 0 && mode != 1)) return B200NP_E_BADARG;
+  if (mode == 1 && !idx) return B200NP_E_BADARG;
+  long long n = (long long)T * nc * D;
+  ctx_agg_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(dout, idx, dfeats, T, nc, D, mode);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Losses: one block; rows are tiny ([T*nt, 2|4]).  Writes the mean loss and d loss / d mu.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
+
+__global__ void loss_kernel(const float* __restrict__ mu, const float* __restrict__ y, float* __restrict__ loss,
+                            float* __restrict__ dmu, long long R, int out, int L, int kind) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const float invR = 1.f / (float)R;
+  for (long long r = threadIdx.x; r < R; r += blockDim.x) {
+    const float* m = mu + r * out;
+    const float* t = y + r * L;
+    if (kind == 0) {  // trainer/losses.py:35-36
+      float e0 = t[0] - m[0], e1 = t[1] - m[1];
+      float nrm = sqrtf(e0 * e0 + e1 * e1);
+      acc += nrm;
+      if (dmu) {
+        dmu[r * 2 + 0] = -e0 / nrm * invR;
+        dmu[r * 2 + 1] = -e1 / nrm * invR;
+      }
+    } else if (kind == 1) {  // trainer/losses.py:50-57
+      float q[4], g[4], nrm = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nrm += m[k] * m[k];
+      nrm = sqrtf(nrm);
+      float pos = 0.f, neg = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        q[k] = m[k] / nrm;
+        pos += fabsf(t[k] - q[k]);
+        neg += fabsf(-t[k] - q[k]);
+      }
+      acc += fminf(pos, neg);
+      if (dmu) {
+        float wp = pos < neg ? 1.f : (pos > neg ? 0.f : 0.5f);  // torch.minimum splits ties evenly
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          g[k] = -(wp * sgn(t[k] - q[k]) + (1.f - wp) * sgn(-t[k] - q[k]));
+          dot += g[k] * q[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dmu[r * 4 + k] = (g[k] - q[k] * dot) / nrm * invR;
+      }
+    } else if (kind == 2) {  // trainer/losses.py:59-61
+      float e0 = t[0] - m[0], e1 = t[1] - m[1];
+      acc += e0 * e0 + e1 * e1;
+      if (dmu) {
+        dmu[r * 2 + 0] = -2.f * e0 * invR;
+        dmu[r * 2 + 1] = -2.f * e1 * invR;
+      }
+    } else {  // degree error, trainer/losses.py:63-76 (evaluation only)
+      const float r2d = 180.f / 3.14159265358979323846f;
+      float gt = t[L - 1] * r2d;
+      float a = acosf(m[0]);
+      if (m[1] < 0.f) a = -a + 2.f * 3.14159265358979323846f;
+      a *= r2d;
+      float e = fminf(fabsf(gt - a), fminf(fabsf(gt + 360.f - a), fabsf(gt - (a + 360.f))));
+      acc += e;
+    }
+  }
+  float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) loss[0] = tot * invR;
+}
+extern "C" int b200np_loss_fwd_bwd(const float* mu, const float* y, float* loss, float* dmu, long long R,
+                                   int out, int L, int kind, void* stream) {
+  if (!mu || !y || !loss || R <= 0) return B200NP_E_BADARG;
+  if (kind == 0 && (out != 2 || L < 2)) return B200NP_E_BADARG;
+  if (kind == 1 && (out != 4 || L != 4)) return B200NP_E_BADARG;
+  if (kind == 2 && (out != 2 || L < 2)) return B200NP_E_BADARG;
+  if (kind == 3 && (out != 2 || L < 1 || dmu)) return B200NP_E_BADARG;
+  if (kind < 0 || kind > 3) return B200NP_E_BADARG;
+  loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(mu, y, loss, dmu, R, out, L, kind);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused Adam on a flat segment: 16 B read + 12 B written per parameter, float4 vectorised.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float eps,
+                                         float wd, float step_size, float inv_bc2_sqrt, float gs) {
+  g *= gs;
+  if (wd != 0.f) g = fmaf(wd, p, g);
+  m = m + (g - m) * (1.f - b1);
+  v = v * b2 + (1.f - b2) * g * g;
+  float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+  p = p - step_size * (m / denom);
+}
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float b1, float b2, float eps, float wd,
+                            float step_size, float inv_bc2_sqrt, float gs, int vec) {
+  long long st = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    long long n4 = n >> 2;
+    for (long long k = i; k < n4; k += st) {
+      float4 P = reinterpret_cast<float4*>(p)[k], G = reinterpret_cast<const float4*>(g)[k];
+      float4 M = reinterpret_cast<float4*>(m)[k], V = reinterpret_cast<float4*>(v)[k];
+      adam_one(P.x, G.x, M.x, V.x, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gs);
+      adam_one(P.y, G.y, M.y, V.y, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gs);
+      adam_one(P.z, G.z, M.z, V.z, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gs);
+      adam_one(P.w, G.w, M.w, V.w, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gs);
+      reinterpret_cast<float4*>(p)[k] = P;
+      reinterpret_cast<float4*>(m)[k] = M;
+      reinterpret_cast<float4*>(v)[k] = V;
+    }
+    for (long long k = (n4 << 2) + i; k < n; k += st)
+      adam_one(p[k], g[k], m[k], v[k], b1, b2, eps, wd, step_size, inv_bc2_sqrt, gs);
+  } else {
+    for (long long k = i; k < n; k += st)
+      adam_one(p[k], g[k], m[k], v[k], b1, b2, eps, wd, step_size, inv_bc2_sqrt, gs);
+  }
+}
+extern "C" int b200np_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int step,
+                                float grad_scale, void* stream) {
+  if (n <= 0) return B200NP_OK;
+  if (!p || !g || !m || !v || step < 1) return B200NP_E_BADARG;
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  float step_size = (float)((double)lr / bc1);
+  float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  int vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
+  adam_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(
+      p, g, m, v, n, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale, vec);
+  return launch_status();
+}

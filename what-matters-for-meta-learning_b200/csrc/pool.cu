@@ -1,0 +1,163 @@
+// Pooling / flatten kernels at the tail of the CNNs.  All tensors here are tiny next to the conv
+// activations (<= N x 4096 floats); they are written for exactness (first-max tie rule) and
+// coalesced access on the NHWC side.
+#include "common.cuh"
+
+using namespace b200np;
+
+// AdaptiveMaxPool2d((2,2)) + NCHW flatten.  Thread = (image, channel): scans the four windows in
+// torch's order (rows, then columns; strict '>' keeps the first maximum), writes one float4.
+__global__ void amp2_flat_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                     int32_t* __restrict__ idx, int N, int H, int W, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * C) return;
+  int n = (int)(i / C), c = (int)(i - (long long)n * C);
+  const float* p = x + (long long)n * H * W * C + c;
+  int hh = H / 2, hw = W / 2;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    int oh = o >> 1, ow = o & 1;
+    float m = -INFINITY;
+    int a = (oh * hh) * W + ow * hw;
+    for (int h = oh * hh; h < (oh + 1) * hh; ++h)
+      for (int w = ow * hw; w < (ow + 1) * hw; ++w) {
+        float v = p[((long long)h * W + w) * C];
+        if (v > m) { m = v; a = h * W + w; }
+      }
+    out[(long long)n * C * 4 + c * 4 + o] = m;
+    idx[(long long)n * C * 4 + c * 4 + o] = a;
+  }
+}
+__global__ void amp2_flat_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
+                                     const float* __restrict__ xs, float* __restrict__ dx, int N, int H, int W,
+                                     int C) {
+  long long n_el = (long long)N * H * W * C;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n_el; i += st) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    int w = (int)(r % W);
+    r /= W;
+    int h = (int)(r % H);
+    long long n = r / H;
+    int o = (h / (H / 2)) * 2 + (w / (W / 2));
+    long long k = n * C * 4 + c * 4 + o;
+    float g = (idx[k] == h * W + w) ? dout[k] : 0.f;
+    dx[i] = (xs[i] > 0.f) ? g : 0.f;
+  }
+}
+extern "C" int b200np_adaptive_maxpool2x2_flatten_fwd(const float* x, float* out, int32_t* idx, int N, int H,
+                                                      int W, int C, void* stream) {
+  if (!x || !out || !idx || N <= 0 || C <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1)) return B200NP_E_BADARG;
+  long long n = (long long)N * C;
+  amp2_flat_fwd_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(x, out, idx, N, H, W, C);
+  return launch_status();
+}
+extern "C" int b200np_adaptive_maxpool2x2_flatten_bwd(const float* dout, const int32_t* idx, const float* x_saved,
+                                                      float* dx, int N, int H, int W, int C, void* stream) {
+  if (!dout || !idx || !x_saved || !dx || N <= 0 || C <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1))
+    return B200NP_E_BADARG;
+  long long n = (long long)N * H * W * C;
+  amp2_flat_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(dout, idx, x_saved, dx, N, H, W, C);
+  return launch_status();
+}
+
+// NHWC <-> NCHW-order flatten.
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H, int W,
+                                    int C) {
+  long long n_el = (long long)N * H * W * C;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n_el; i += st) {  // i indexes the NHWC side (coalesced reads)
+    int c = (int)(i % C);
+    long long r = i / C;
+    int hw = (int)(r % ((long long)H * W));
+    long long n = r / ((long long)H * W);
+    out[(n * C + c) * H * W + hw] = x[i];
+  }
+}
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ dout, const float* __restrict__ xs,
+                                    float* __restrict__ dx, int N, int H, int W, int C) {
+  long long n_el = (long long)N * H * W * C;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n_el; i += st) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    int hw = (int)(r % ((long long)H * W));
+    long long n = r / ((long long)H * W);
+    float g = dout[(n * C + c) * H * W + hw];
+    dx[i] = (!xs || xs[i] > 0.f) ? g : 0.f;
+  }
+}
+extern "C" int b200np_nhwc_to_nchw_flat(const float* x, float* out, int N, int H, int W, int C, void* stream) {
+  if (!x || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0) return B200NP_E_BADARG;
+  long long n = (long long)N * H * W * C;
+  nhwc_to_nchw_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, out, N, H, W, C);
+  return launch_status();
+}
+extern "C" int b200np_nchw_flat_to_nhwc(const float* dout, const float* x_saved, float* dx, int N, int H, int W,
+                                        int C, void* stream) {
+  if (!dout || !dx || N <= 0 || H <= 0 || W <= 0 || C <= 0) return B200NP_E_BADARG;
+  long long n = (long long)N * H * W * C;
+  nchw_to_nhwc_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(dout, x_saved, dx, N, H, W, C);
+  return launch_status();
+}
+
+// MaxPool2d(2,2) on NHWC; first maximum in (0,0),(0,1),(1,0),(1,1) order.
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int8_t* __restrict__ idx,
+                                    int N, int H, int W, int C) {
+  int OH = H / 2, OW = W / 2;
+  long long n_el = (long long)N * OH * OW * C;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n_el; i += st) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    int ow = (int)(r % OW);
+    r /= OW;
+    int oh = (int)(r % OH);
+    long long n = r / OH;
+    const float* p = x + ((n * H + oh * 2) * W + ow * 2) * C + c;
+    float m = p[0];
+    int a = 0;
+    float v = p[C];
+    if (v > m) { m = v; a = 1; }
+    v = p[(long long)W * C];
+    if (v > m) { m = v; a = 2; }
+    v = p[(long long)W * C + C];
+    if (v > m) { m = v; a = 3; }
+    y[i] = m;
+    idx[i] = (int8_t)a;
+  }
+}
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ dy, const int8_t* __restrict__ idx,
+                                    const float* __restrict__ xs, float* __restrict__ dx, int N, int H, int W,
+                                    int C) {
+  int OH = H / 2, OW = W / 2;
+  long long n_el = (long long)N * H * W * C;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
+  for (; i < n_el; i += st) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    int w = (int)(r % W);
+    r /= W;
+    int h = (int)(r % H);
+    long long n = r / H;
+    long long k = ((n * OH + h / 2) * OW + w / 2) * C + c;
+    float g = (idx[k] == (h & 1) * 2 + (w & 1)) ? dy[k] : 0.f;
+    dx[i] = (xs[i] > 0.f) ? g : 0.f;
+  }
+}
+extern "C" int b200np_maxpool2x2_fwd(const float* x, float* y, int8_t* idx, int N, int H, int W, int C,
+                                     void* stream) {
+  if (!x || !y || !idx || N <= 0 || C <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1)) return B200NP_E_BADARG;
+  long long n = (long long)N * (H / 2) * (W / 2) * C;
+  maxpool2_fwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, y, idx, N, H, W, C);
+  return launch_status();
+}
+extern "C" int b200np_maxpool2x2_bwd(const float* dy, const int8_t* idx, const float* x_saved, float* dx, int N,
+                                     int H, int W, int C, void* stream) {
+  if (!dy || !idx || !x_saved || !dx || N <= 0 || C <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1))
+    return B200NP_E_BADARG;
+  long long n = (long long)N * H * W * C;
+  maxpool2_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(dy, idx, x_saved, dx, N, H, W, C);
+  return launch_status();
+}

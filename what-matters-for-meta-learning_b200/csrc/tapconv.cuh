@@ -1,0 +1,64 @@
+// "Tap convolution": the one implicit-GEMM formulation behind every channel-dense conv on the path.
+//
+//   dst[pix(n,oy,ox), co] = epilogue( sum_{t < ntaps} sum_{ci < Cin}
+//                                       src_t[n, oy*in_s + dy_t, ox*in_s + dx_t, ci] * w_t[co, ci] )
+//
+// A tap names a source tensor (NHWC, zero outside its bounds), a spatial offset and a
+// [Cout x Cin] weight slab.  With the right tap table this is
+//   * forward RxR conv, any stride                       (taps = filter positions)
+//   * conv2 + 1x1 stride-2 skip projection fused         (one extra tap on a second source)
+//   * data gradient of a stride-1 conv                   (taps = mirrored filter positions)
+//   * data gradient of a stride-2 conv (+ skip gradient) (one launch per input-pixel parity class,
+//                                                         each with its dense subset of taps; the
+//                                                         destination is written with stride 2)
+// GEMM view: M = N*OH*OW pixels, N = Cout, K = ntaps*Cin.  Both operands are K-major
+// (channels contiguous), which is what the tcgen05 path wants as well.
+#pragma once
+#include "common.cuh"
+
+namespace b200np {
+
+constexpr int kMaxTaps = 12;
+
+struct Tap {
+  int8_t src;   // 0 or 1
+  int8_t dy;    // input row  = oy*in_s[src] + dy
+  int8_t dx;    // input col  = ox*in_s[src] + dx
+  int8_t slab;  // weight slab index inside w[src]
+};
+
+struct TapConvArgs {
+  const float* src[2];
+  int srcH[2], srcW[2], in_s[2];
+  const float* w[2];   // [slabs][Cout][Cin] per source
+  int Cin, Cout;
+  const float* bias;   // nullable
+  const float* bias2;  // nullable
+  float* dst;
+  const float* mask;   // nullable; same geometry as dst: result *= (mask > 0)
+  int N, OH, OW;       // pixel grid of this launch
+  int dstH, dstW, dst_s, dst_oy, dst_ox;  // dst pixel = (oy*dst_s + dst_oy, ox*dst_s + dst_ox)
+  int ntaps;
+  Tap taps[kMaxTaps];
+  int act;
+};
+
+struct TapWgradArgs {
+  const float* src;    // [N, srcH, srcW, Cin]
+  int srcH, srcW, in_s, Cin;
+  const float* dy;     // [N, OH, OW, Cout]
+  int N, OH, OW, Cout;
+  int ntaps;
+  Tap taps[kMaxTaps];  // dy/dx only
+  float* part;         // [chunks][ntaps][Cout][Cin]
+  int chunks;
+  long long pix_per_chunk;  // multiple of 16
+};
+
+int launch_tapconv_simt(const TapConvArgs& a, cudaStream_t st);
+int launch_tapwgrad_simt(const TapWgradArgs& a, cudaStream_t st);
+// tcgen05 path (tapconv_umma.cu); returns B200NP_E_UNSUPPORTED when the shape does not fit
+int launch_tapconv_umma(const TapConvArgs& a, int precision, cudaStream_t st);
+int launch_tapwgrad_umma(const TapWgradArgs& a, int precision, cudaStream_t st);
+
+}  // namespace b200np

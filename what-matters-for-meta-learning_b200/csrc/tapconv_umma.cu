@@ -1,0 +1,293 @@
+// tcgen05 / TMEM implementation of the tap convolution (tapconv.cuh) for the 64-channel layers.
+//
+// GEMM view per CTA: D[128 pixels x 64 couts] (fp32 accumulator in TMEM, 64 columns)
+//                    += sum over K-blocks (tap, 32-channel half) of A[128 x 32] * B[64 x 32]^T
+// Operands are K-major (channels contiguous) in the canonical SWIZZLE_128B shared-memory layout:
+// a row is 128 B (32 tf32), 8 rows form a 1024 B swizzle atom, 16-byte chunk c of row r sits at
+// chunk position c ^ (r & 7).  tcgen05.mma.kind::tf32 consumes K = 8 per instruction, so a K-block
+// is 4 instructions per pass.
+//
+// Precision modes
+//   TF32    one pass; the tensor core reads the top 19 bits of each fp32.
+//   TF32X3  fp32-grade: every operand is split exactly into hi = x & ~0x1fff and lo = x - hi while it
+//           is staged, and D += hi*hi + lo*hi + hi*lo (the dropped lo*lo term is < 2^-22 relative).
+//
+// The im2col gather (zero padding, stride, second source for the fused skip projection, parity
+// classes of the stride-2 data gradient) is done by the 128 threads with 16-byte loads straight
+// into the swizzled layout -- the operand split needs the values in registers anyway.  A 2-stage
+// shared-memory ring decouples the gather from the asynchronous MMAs via mbarriers
+// (tcgen05.commit); two CTAs per SM overlap one CTA's gather latency with the other's MMAs.
+#include "tapconv.cuh"
+
+namespace b200np {
+
+namespace {
+
+constexpr int kBM = 128, kBN = 64, kBK = 32;          // K-block = 32 channels = one 128 B swizzle row
+constexpr int kStages = 2;
+constexpr uint32_t kABytes = kBM * kBK * 4;           // 16 KB
+constexpr uint32_t kBBytes = kBN * kBK * 4;           //  8 KB
+constexpr uint32_t kTmemCols = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (sticky error the host sees) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate, issued by one thread.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major; 1 by convention),
+// SBO >> 4 in [32,46) = 1024 B between 8-row groups, version 1 in [46,48), layout type 2 in [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format
+// TF32 (2) at [7,10)/[10,13), both K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kIdescTf32_128x64 = (1u << 4) | (2u << 7) | (2u << 10) | ((kBN >> 3) << 17) | ((kBM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
+  return static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v, bool x3) {
+  if (x3) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi_base + off) = h;
+    *reinterpret_cast<float4*>(lo_base + off) = l;
+  } else {
+    *reinterpret_cast<float4*>(hi_base + off) = v;
+  }
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs a) {
+  constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kABytes + kBBytes);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);  // [kStages] stage free, [1] accum done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const long long M = (long long)a.N * a.OH * a.OW;
+  const long long m0 = (long long)blockIdx.x * kBM;
+
+  if (tid == 0) {
+    for (int s = 0; s <= kStages; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  // pixel gathered by this thread (row `tid` of the A tile)
+  const long long p = m0 + tid;
+  const bool pvalid = p < M;
+  int ox = 0, oy = 0, n = 0;
+  if (pvalid) {
+    ox = (int)(p % a.OW);
+    long long q = p / a.OW;
+    oy = (int)(q % a.OH);
+    n = (int)(q / a.OH);
+  }
+  const int brow = tid >> 1, bhalf = tid & 1;  // B: cout row, 64-byte half of the 128 B K-block row
+
+  const int KB = a.ntaps * 2;
+  float4 av[8], bv[4];
+  auto fetch = [&](int kb) {
+    const int t = kb >> 1, c0 = (kb & 1) * kBK;
+    const Tap tp = a.taps[t];
+    const int s = tp.src;
+    const int iy = oy * a.in_s[s] + tp.dy, ix = ox * a.in_s[s] + tp.dx;
+    const bool ok = pvalid && iy >= 0 && iy < a.srcH[s] && ix >= 0 && ix < a.srcW[s];
+    if (ok) {
+      const float* ap = a.src[s] + (((long long)n * a.srcH[s] + iy) * a.srcW[s] + ix) * 64 + c0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) av[c] = ldg4(ap + 4 * c);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* bp = a.w[s] + ((long long)tp.slab * 64 + brow) * 64 + c0 + bhalf * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bv[c] = ldg4(bp + 4 * c);
+  };
+
+  if (KB > 0) fetch(0);
+  for (int kb = 0; kb < KB; ++kb) {
+    const int s = kb % kStages;
+    const int use = kb / kStages;
+    if (use >= 1) mbar_wait(bars + s, (use - 1) & 1);  // MMAs that read this stage have retired
+    uint8_t* st = smem + s * kStageBytes;
+    uint8_t* a_hi = st;
+    uint8_t* a_lo = st + kABytes;                       // only in X3
+    uint8_t* b_hi = st + (X3 ? 2 : 1) * kABytes;
+    uint8_t* b_lo = b_hi + kBBytes;                     // only in X3
+#pragma unroll
+    for (int c = 0; c < 8; ++c) split_store(a_hi, a_lo, sw128_offset(tid, c), av[c], X3);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) split_store(b_hi, b_lo, sw128_offset(brow, bhalf * 4 + c), bv[c], X3);
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ah = make_kmajor_sw128_desc(smem_u32(a_hi)), bh = make_kmajor_sw128_desc(smem_u32(b_hi));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)  // +32 B (8 tf32) along K inside the swizzle atom = +2 in the address field
+        umma_tf32(tmem_d, ah + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb | k) != 0);
+      if (X3) {
+        const uint64_t al = make_kmajor_sw128_desc(smem_u32(a_lo)), bl = make_kmajor_sw128_desc(smem_u32(b_lo));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, al + 2 * k, bh + 2 * k, kIdescTf32_128x64, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 2 * k, bl + 2 * k, kIdescTf32_128x64, 1u);
+      }
+      umma_commit(bars + s);                       // stage reusable once these MMAs retire
+      if (kb == KB - 1) umma_commit(bars + kStages);  // accumulator complete
+    }
+    if (kb + 1 < KB) fetch(kb + 1);
+  }
+
+  // ---- epilogue: TMEM -> registers -> bias / ReLU-mask / activation -> NHWC global ----
+  if (KB > 0) {
+    mbar_wait(bars + kStages, 0);
+    tc_fence_after();
+  }
+  float acc[64];
+  if (KB > 0) {
+    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+    uint32_t r[64];
+#define B200NP_TMEM_LD32(base, col)                                                                         \
+  asm volatile(                                                                                             \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                             \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                             \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"             \
+      : "=r"(r[base + 0]), "=r"(r[base + 1]), "=r"(r[base + 2]), "=r"(r[base + 3]), "=r"(r[base + 4]),      \
+        "=r"(r[base + 5]), "=r"(r[base + 6]), "=r"(r[base + 7]), "=r"(r[base + 8]), "=r"(r[base + 9]),      \
+        "=r"(r[base + 10]), "=r"(r[base + 11]), "=r"(r[base + 12]), "=r"(r[base + 13]), "=r"(r[base + 14]), \
+        "=r"(r[base + 15]), "=r"(r[base + 16]), "=r"(r[base + 17]), "=r"(r[base + 18]), "=r"(r[base + 19]), \
+        "=r"(r[base + 20]), "=r"(r[base + 21]), "=r"(r[base + 22]), "=r"(r[base + 23]), "=r"(r[base + 24]), \
+        "=r"(r[base + 25]), "=r"(r[base + 26]), "=r"(r[base + 27]), "=r"(r[base + 28]), "=r"(r[base + 29]), \
+        "=r"(r[base + 30]), "=r"(r[base + 31])                                                              \
+      : "r"(taddr + col))
+    B200NP_TMEM_LD32(0, 0);
+    B200NP_TMEM_LD32(32, 32);
+#undef B200NP_TMEM_LD32
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = __uint_as_float(r[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+  }
+  if (pvalid) {
+    const long long off =
+        (((long long)n * a.dstH + (long long)oy * a.dst_s + a.dst_oy) * a.dstW + (long long)ox * a.dst_s + a.dst_ox) * 64;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      float4 o = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+      if (a.bias) {
+        const float4 b = ldg4(a.bias + 4 * q);
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      if (a.bias2) {
+        const float4 b = ldg4(a.bias2 + 4 * q);
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      if (a.mask) {
+        const float4 mk = ldg4(a.mask + off + 4 * q);
+        o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
+        o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+      }
+      if (a.act == B200NP_ACT_RELU) {
+        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+      }
+      *reinterpret_cast<float4*>(a.dst + off + 4 * q) = o;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <bool X3>
+int launch(const TapConvArgs& a, cudaStream_t st) {
+  constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kABytes + kBBytes);
+  const size_t smem = kStages * kStageBytes + 1024 + 64;
+  static bool configured = false;  // idempotent attribute; benign if two threads race
+  if (!configured) {
+    if (cudaFuncSetAttribute(tapconv_umma_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return B200NP_E_LAUNCH;
+    configured = true;
+  }
+  const long long M = (long long)a.N * a.OH * a.OW;
+  if (M <= 0) return B200NP_OK;
+  tapconv_umma_kernel<X3><<<(unsigned)ceil_div(M, kBM), 128, smem, st>>>(a);
+  return launch_status();
+}
+
+}  // namespace
+
+int launch_tapconv_umma(const TapConvArgs& a, int precision, cudaStream_t st) {
+  if (a.Cin != 64 || a.Cout != 64 || a.ntaps > kMaxTaps) return B200NP_E_UNSUPPORTED;
+  if (a.act != B200NP_ACT_NONE && a.act != B200NP_ACT_RELU) return B200NP_E_UNSUPPORTED;
+  return precision == B200NP_PREC_TF32 ? launch<false>(a, st) : launch<true>(a, st);
+}
+
+int launch_tapwgrad_umma(const TapWgradArgs&, int, cudaStream_t) { return B200NP_E_UNSUPPORTED; }
+
+}  // namespace b200np
