@@ -206,17 +206,20 @@ def run_b200_arm(args, rank, world, local_rank):
         b = [t.to(dev, non_blocking=True) for t in host[i % nbatch]]
         return float(step(b))
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_step(0)
-    ms_e2e = timed(e2e_step, e2e_steps)
     h2d = sum(t.numel() * 4 for t in host[0])
+    if args.profile:
+        ms_e2e = float("nan")
+    else:
+        e2e_step(0)
+        ms_e2e = timed(e2e_step, e2e_steps)
 
-    roof = dominant_kernel_roofline(args, dev) if rank == 0 else None
+    roof = dominant_kernel_roofline(args, dev) if (rank == 0 and not args.profile) else None
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
         return
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.profile:
         sample = 2
         times = cpu_port_step_time(sample, 3, 1)
         cpu = {"value": sample * len(times) / sum(times), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
@@ -297,6 +300,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("B200NP_PRECISION", "tf32x3"),
                     choices=["tf32x3", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="only the resident-input timed loop (for ncu launch lists); skips e2e / roofline / CPU legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -304,7 +309,8 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
-    args.warmup = max(args.warmup, 3)
+    if not args.profile:
+        args.warmup = max(args.warmup, 3)
     run_b200_arm(args, rank, world, local_rank)
 
 

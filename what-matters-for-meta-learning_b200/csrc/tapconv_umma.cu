@@ -27,7 +27,6 @@ constexpr int kBM = 128, kBN = 64, kBK = 32;          // K-block = 32 channels =
 constexpr int kStages = 2;
 constexpr uint32_t kABytes = kBM * kBK * 4;           // 16 KB
 constexpr uint32_t kBBytes = kBN * kBK * 4;           //  8 KB
-constexpr uint32_t kTmemCols = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -108,6 +107,53 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
   }
 }
 
+// 32 lanes x 32 columns of fp32 from TMEM into registers (warp-collective)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Accumulator blocks in TMEM.  The tensor core adds into its fp32 accumulator with truncation, which
+// biases a long K loop (measured 3.7e-6 relative at K = 640 -- 10x the CUDA-core fp32 result).  The
+// fp32-grade mode therefore spreads the hi*hi products round-robin over kAccX3 independent 64-column
+// accumulators (each sees 1/kAccX3 of the K-blocks), keeps the 2^-11-smaller cross terms in a block
+// of their own, and sums the blocks with round-to-nearest adds in the epilogue.
+constexpr int kAccX3 = 3;
+template <bool X3> struct AccCfg {
+  static constexpr int kHi = X3 ? kAccX3 : 1;
+  static constexpr int kBlocks = X3 ? kAccX3 + 1 : 1;
+  static constexpr uint32_t kCols = X3 ? 256 : 64;  // power of two >= 64 * kBlocks
+};
+// sum the accumulator blocks of one 32-column half into acc[0..32)
+template <bool X3>
+__device__ __forceinline__ void gather_acc(uint32_t taddr, int col0, int hi_used, float (&acc)[32]) {
+  uint32_t r[32];
+  if (X3) {
+    tmem_ld32(taddr + AccCfg<X3>::kHi * 64 + col0, r);  // cross terms first (smallest magnitude)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  }
+#pragma unroll
+  for (int b = 0; b < AccCfg<X3>::kHi; ++b) {
+    if (b < hi_used) {
+      tmem_ld32(taddr + b * 64 + col0, r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+    }
+  }
+}
+
 template <bool X3>
 __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs a) {
   constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kABytes + kBBytes);
@@ -126,7 +172,7 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols)
+                 "r"(AccCfg<X3>::kCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -187,15 +233,17 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
     if (tid == 0) {
       tc_fence_after();
       const uint64_t ah = make_kmajor_sw128_desc(smem_u32(a_hi)), bh = make_kmajor_sw128_desc(smem_u32(b_hi));
+      const uint32_t d_hi = tmem_d + (kb % AccCfg<X3>::kHi) * 64;
 #pragma unroll
       for (int k = 0; k < 4; ++k)  // +32 B (8 tf32) along K inside the swizzle atom = +2 in the address field
-        umma_tf32(tmem_d, ah + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb | k) != 0);
+        umma_tf32(d_hi, ah + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb >= AccCfg<X3>::kHi) | (k != 0));
       if (X3) {
         const uint64_t al = make_kmajor_sw128_desc(smem_u32(a_lo)), bl = make_kmajor_sw128_desc(smem_u32(b_lo));
+        const uint32_t d_lo = tmem_d + AccCfg<X3>::kHi * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, al + 2 * k, bh + 2 * k, kIdescTf32_128x64, 1u);
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb | k) != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 2 * k, bl + 2 * k, kIdescTf32_128x64, 1u);
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + 2 * k, bl + 2 * k, kIdescTf32_128x64, 1u);
       }
       umma_commit(bars + s);                       // stage reusable once these MMAs retire
       if (kb == KB - 1) umma_commit(bars + kStages);  // accumulator complete
@@ -208,62 +256,48 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
     mbar_wait(bars + kStages, 0);
     tc_fence_after();
   }
-  float acc[64];
-  if (KB > 0) {
-    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-    uint32_t r[64];
-#define B200NP_TMEM_LD32(base, col)                                                                         \
-  asm volatile(                                                                                             \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                             \
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                             \
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"             \
-      : "=r"(r[base + 0]), "=r"(r[base + 1]), "=r"(r[base + 2]), "=r"(r[base + 3]), "=r"(r[base + 4]),      \
-        "=r"(r[base + 5]), "=r"(r[base + 6]), "=r"(r[base + 7]), "=r"(r[base + 8]), "=r"(r[base + 9]),      \
-        "=r"(r[base + 10]), "=r"(r[base + 11]), "=r"(r[base + 12]), "=r"(r[base + 13]), "=r"(r[base + 14]), \
-        "=r"(r[base + 15]), "=r"(r[base + 16]), "=r"(r[base + 17]), "=r"(r[base + 18]), "=r"(r[base + 19]), \
-        "=r"(r[base + 20]), "=r"(r[base + 21]), "=r"(r[base + 22]), "=r"(r[base + 23]), "=r"(r[base + 24]), \
-        "=r"(r[base + 25]), "=r"(r[base + 26]), "=r"(r[base + 27]), "=r"(r[base + 28]), "=r"(r[base + 29]), \
-        "=r"(r[base + 30]), "=r"(r[base + 31])                                                              \
-      : "r"(taddr + col))
-    B200NP_TMEM_LD32(0, 0);
-    B200NP_TMEM_LD32(32, 32);
-#undef B200NP_TMEM_LD32
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+  const int hi_used = KB < AccCfg<X3>::kHi ? KB : AccCfg<X3>::kHi;
+  const long long off = pvalid ? (((long long)n * a.dstH + (long long)oy * a.dst_s + a.dst_oy) * a.dstW +
+                                  (long long)ox * a.dst_s + a.dst_ox) * 64
+                               : 0;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = __uint_as_float(r[j]);
-  } else {
+  for (int half = 0; half < 2; ++half) {
+    float acc[32];
+    if (KB > 0) {
+      gather_acc<X3>(taddr, half * 32, hi_used, acc);  // warp-collective: every lane takes part
+    } else {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-  }
-  if (pvalid) {
-    const long long off =
-        (((long long)n * a.dstH + (long long)oy * a.dst_s + a.dst_oy) * a.dstW + (long long)ox * a.dst_s + a.dst_ox) * 64;
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    }
+    if (!pvalid) continue;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
+    for (int q = 0; q < 8; ++q) {
+      const int c = half * 32 + 4 * q;
       float4 o = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
       if (a.bias) {
-        const float4 b = ldg4(a.bias + 4 * q);
+        const float4 b = ldg4(a.bias + c);
         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
       }
       if (a.bias2) {
-        const float4 b = ldg4(a.bias2 + 4 * q);
+        const float4 b = ldg4(a.bias2 + c);
         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
       }
       if (a.mask) {
-        const float4 mk = ldg4(a.mask + off + 4 * q);
+        const float4 mk = ldg4(a.mask + off + c);
         o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
         o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
       }
       if (a.act == B200NP_ACT_RELU) {
         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
       }
-      *reinterpret_cast<float4*>(a.dst + off + 4 * q) = o;
+      *reinterpret_cast<float4*>(a.dst + off + c) = o;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(AccCfg<X3>::kCols) : "memory");
   }
 }
 
@@ -284,6 +318,196 @@ int launch(const TapConvArgs& a, cudaStream_t st) {
   return launch_status();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05.  Per CTA: one pair of taps (t0, t0+1) over one chunk of pixels.
+//   D[128 x 64] : row m = tap_local*64 + ci, column = co
+//   D += sum over pixels p of  X_tap[gather(p)][ci] * dY[p][co]
+// i.e. A = [X_t0^T ; X_t1^T] (M = 128) and B = dY^T (N = 64), contraction over PIXELS.  Both operands
+// are contiguous along their M/N index (channels) and strided along K (pixels): "MN-major" in UMMA
+// terms.  Canonical SWIZZLE_128B MN-major layout: an atom is 8 pixels x 32 channels (8 rows of 128 B,
+// 16-byte chunk c of pixel-row r at chunk position c ^ (r & 7)); atoms of the four pixel-groups of a
+// 32-pixel K-block are SBO = 1024 B apart, the 32-channel blocks LBO = 4096 B apart.  One
+// tcgen05.mma (K = 8) consumes one pixel-group; its descriptor start advances by 1024 B per k-step.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgK = 32;                             // pixels per K-block
+constexpr uint32_t kWgABytes = 128 * kWgK * 4;        // 16 KB : 4 channel blocks x 4 pixel groups x 1 KB
+constexpr uint32_t kWgBBytes = 64 * kWgK * 4;         //  8 KB : 2 channel blocks x 4 pixel groups x 1 KB
+constexpr uint32_t kIdescTf32_128x64_MN = kIdescTf32_128x64 | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(4096 >> 4) << 16;  // LBO: next 32-channel block
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;  // SBO: next group of 8 pixels
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t mn_offset(int cblock, int k, int chunk) {
+  return static_cast<uint32_t>(cblock * 4096 + (k >> 3) * 1024 + (k & 7) * 128 + ((chunk ^ (k & 7)) << 4));
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArgs a) {
+  constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kWgABytes + kWgBBytes);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x, pair = blockIdx.y;
+  const long long M = (long long)a.N * a.OH * a.OW;
+  const long long p_begin = (long long)chunk * a.pix_per_chunk;
+  long long p_end = p_begin + a.pix_per_chunk;
+  if (p_end > M) p_end = M;
+
+  if (tid == 0) {
+    for (int s = 0; s <= kStages; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(AccCfg<X3>::kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  // A gather role: (tap_local, pixel k, channel half) -> 128 contiguous bytes
+  const int a_tl = tid >> 6, a_k = (tid >> 1) & 31, a_half = tid & 1;
+  const int a_tap = pair * 2 + a_tl;
+  const bool a_tap_ok = a_tap < a.ntaps;
+  const Tap tp = a.taps[a_tap_ok ? a_tap : 0];
+  // B gather role: (pixel k, channel half, 64-byte sub-half)
+  const int b_k = tid >> 2, b_half = (tid >> 1) & 1, b_sub = tid & 1;
+
+  const long long KB = p_begin < p_end ? ((p_end - p_begin + kWgK - 1) / kWgK) : 0;
+  float4 av[8], bv[4];
+  auto fetch = [&](long long kb) {
+    const long long p0 = p_begin + kb * kWgK;
+    {
+      const long long p = p0 + a_k;
+      bool ok = a_tap_ok && p < p_end;
+      const float* ap = nullptr;
+      if (ok) {
+        const int ox = (int)(p % a.OW);
+        const long long q = p / a.OW;
+        const int oy = (int)(q % a.OH);
+        const long long n = q / a.OH;
+        const int iy = oy * a.in_s + tp.dy, ix = ox * a.in_s + tp.dx;
+        ok = iy >= 0 && iy < a.srcH && ix >= 0 && ix < a.srcW;
+        ap = a.src + ((n * a.srcH + iy) * a.srcW + ix) * 64 + a_half * 32;
+      }
+      if (ok) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) av[c] = ldg4(ap + 4 * c);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    {
+      const long long p = p0 + b_k;
+      if (p < p_end) {
+        const float* bp = a.dy + p * 64 + b_half * 32 + b_sub * 16;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bv[c] = ldg4(bp + 4 * c);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+
+  if (KB > 0) fetch(0);
+  for (long long kb = 0; kb < KB; ++kb) {
+    const int s = (int)(kb % kStages);
+    const long long use = kb / kStages;
+    if (use >= 1) mbar_wait(bars + s, (uint32_t)((use - 1) & 1));
+    uint8_t* st = smem + s * kStageBytes;
+    uint8_t* a_hi = st;
+    uint8_t* a_lo = st + kWgABytes;
+    uint8_t* b_hi = st + (X3 ? 2 : 1) * kWgABytes;
+    uint8_t* b_lo = b_hi + kWgBBytes;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) split_store(a_hi, a_lo, mn_offset(a_tl * 2 + a_half, a_k, c), av[c], X3);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) split_store(b_hi, b_lo, mn_offset(b_half, b_k, b_sub * 4 + c), bv[c], X3);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ah = make_mnmajor_sw128_desc(smem_u32(a_hi)), bh = make_mnmajor_sw128_desc(smem_u32(b_hi));
+      const uint32_t d_hi = tmem_d + (uint32_t)(kb % AccCfg<X3>::kHi) * 64;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)  // next group of 8 pixels: +1024 B = +64 in the address field
+        umma_tf32(d_hi, ah + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, (kb >= AccCfg<X3>::kHi) | (k != 0));
+      if (X3) {
+        const uint64_t al = make_mnmajor_sw128_desc(smem_u32(a_lo)), bl = make_mnmajor_sw128_desc(smem_u32(b_lo));
+        const uint32_t d_lo = tmem_d + AccCfg<X3>::kHi * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, (kb | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + 64 * k, bl + 64 * k, kIdescTf32_128x64_MN, 1u);
+      }
+      umma_commit(bars + s);
+      if (kb == KB - 1) umma_commit(bars + kStages);
+    }
+    if (kb + 1 < KB) fetch(kb + 1);
+  }
+
+  // epilogue: thread (warp w, lane l) holds row m = 32w + l = tap_local*64 + ci, 64 couts
+  const int tl = warp >> 1, ci = (warp & 1) * 32 + lane;
+  const int tap = pair * 2 + tl;
+  if (KB > 0) {
+    mbar_wait(bars + kStages, 0);
+    tc_fence_after();
+  }
+  {
+    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+    const int hi_used = KB < AccCfg<X3>::kHi ? (int)KB : AccCfg<X3>::kHi;
+    float* po = a.part + ((long long)chunk * a.ntaps + (tap < a.ntaps ? tap : 0)) * 64 * 64 + ci;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float acc[32];
+      if (KB > 0) {
+        gather_acc<X3>(taddr, half * 32, hi_used, acc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      }
+      if (tap < a.ntaps) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) po[(half * 32 + j) * 64] = acc[j];  // lanes = consecutive ci: coalesced
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(AccCfg<X3>::kCols) : "memory");
+  }
+}
+
+template <bool X3>
+int launch_wgrad(const TapWgradArgs& a, cudaStream_t st) {
+  constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kWgABytes + kWgBBytes);
+  const size_t smem = kStages * kStageBytes + 1024 + 64;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tapwgrad_umma_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return B200NP_E_LAUNCH;
+    configured = true;
+  }
+  dim3 grid(a.chunks, (a.ntaps + 1) / 2);
+  tapwgrad_umma_kernel<X3><<<grid, 128, smem, st>>>(a);
+  return launch_status();
+}
+
 }  // namespace
 
 int launch_tapconv_umma(const TapConvArgs& a, int precision, cudaStream_t st) {
@@ -292,6 +516,10 @@ int launch_tapconv_umma(const TapConvArgs& a, int precision, cudaStream_t st) {
   return precision == B200NP_PREC_TF32 ? launch<false>(a, st) : launch<true>(a, st);
 }
 
-int launch_tapwgrad_umma(const TapWgradArgs&, int, cudaStream_t) { return B200NP_E_UNSUPPORTED; }
+int launch_tapwgrad_umma(const TapWgradArgs& a, int precision, cudaStream_t st) {
+  if (a.Cin != 64 || a.Cout != 64 || a.ntaps > kMaxTaps || a.ntaps < 1 || a.pix_per_chunk % kWgK != 0)
+    return B200NP_E_UNSUPPORTED;
+  return precision == B200NP_PREC_TF32 ? launch_wgrad<false>(a, st) : launch_wgrad<true>(a, st);
+}
 
 }  // namespace b200np
