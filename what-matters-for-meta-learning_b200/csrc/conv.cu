@@ -27,7 +27,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   int per = ntaps * Cout * Cin;
   if (i >= per) return;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c) s += part[(long long)c * per + i];
+#pragma unroll 8
+  for (int c = 0; c < chunks; ++c) s += part[(long long)c * per + i];  // independent loads: 8 in flight
   int ci = i % Cin, r = i / Cin;
   int co = r % Cout, t = r / Cout;
   dw[((long long)co * Cin + ci) * ntaps + t] = s;
@@ -39,7 +40,7 @@ int wgrad_chunks(long long M, int ntaps) {
   if (want > maxc) want = maxc;
   return (int)(want < 1 ? 1 : want);
 }
-long long wgrad_pix_per_chunk(long long M, int chunks) { return ceil_div(ceil_div(M, chunks), 16) * 16; }
+long long wgrad_pix_per_chunk(long long M, int chunks) { return ceil_div(ceil_div(M, chunks), 32) * 32; }
 
 bool use_umma(int precision, int Cin, int Cout) {
   return precision != B200NP_PREC_FP32_SIMT && Cin == 64 && Cout == 64;

@@ -324,10 +324,12 @@ int launch(const TapConvArgs& a, cudaStream_t st) {
 //   D += sum over pixels p of  X_tap[gather(p)][ci] * dY[p][co]
 // i.e. A = [X_t0^T ; X_t1^T] (M = 128) and B = dY^T (N = 64), contraction over PIXELS.  Both operands
 // are contiguous along their M/N index (channels) and strided along K (pixels): "MN-major" in UMMA
-// terms.  Canonical SWIZZLE_128B MN-major layout: an atom is 8 pixels x 32 channels (8 rows of 128 B,
-// 16-byte chunk c of pixel-row r at chunk position c ^ (r & 7)); atoms of the four pixel-groups of a
-// 32-pixel K-block are SBO = 1024 B apart, the 32-channel blocks LBO = 4096 B apart.  One
-// tcgen05.mma (K = 8) consumes one pixel-group; its descriptor start advances by 1024 B per k-step.
+// terms.  For 32-bit operands the only MN-major shared-memory layout the tensor core accepts is
+// SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom): an atom is 4 pixels x 32 channels (4 rows of
+// 128 B) and the swizzle permutes 32-BYTE units -- unit j of pixel-row r sits at unit position
+// j ^ (r & 3).  Atoms of successive 4-pixel groups are SBO = 512 B apart, the 32-channel blocks
+// LBO = 4096 B apart (one 32-pixel K-block).  One tcgen05.mma (K = 8) consumes two pixel groups; its
+// descriptor start advances by 1024 B per k-step.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgK = 32;                             // pixels per K-block
 constexpr uint32_t kWgABytes = 128 * kWgK * 4;        // 16 KB : 4 channel blocks x 4 pixel groups x 1 KB
@@ -338,13 +340,15 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(4096 >> 4) << 16;  // LBO: next 32-channel block
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;  // SBO: next group of 8 pixels
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;   // SBO: next group of 4 pixels
+  d |= static_cast<uint64_t>(1) << 46;          // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(1) << 61;          // layout type 1 = SWIZZLE_128B_BASE32B
   return d;
 }
+// byte offset of 16-byte chunk `chunk` (0..7) of pixel-row k (0..31) in channel block `cblock`
 __device__ __forceinline__ uint32_t mn_offset(int cblock, int k, int chunk) {
-  return static_cast<uint32_t>(cblock * 4096 + (k >> 3) * 1024 + (k & 7) * 128 + ((chunk ^ (k & 7)) << 4));
+  return static_cast<uint32_t>(cblock * 4096 + (k >> 2) * 512 + (k & 3) * 128 + (((chunk >> 1) ^ (k & 3)) << 5) +
+                               ((chunk & 1) << 4));
 }
 
 template <bool X3>
