@@ -57,6 +57,38 @@ def conv_diag():
     P(f"conv2+skip fwd  cpu-fp32   rel-L2 vs fp64: {rel(y32, ref):.3e}")
 
 
+def convops_diag():
+    """dgrad / wgrad of one residual stage at a realistic size, every precision mode vs fp64."""
+    from b200np import ops
+    g = torch.Generator().manual_seed(3)
+    N, H = 8, 32
+    x = torch.rand(N, 64, 2 * H, 2 * H, generator=g, dtype=torch.float64).requires_grad_()
+    w1 = (torch.randn(64, 64, 3, 3, generator=g, dtype=torch.float64) * 0.04).requires_grad_()
+    w2 = (torch.randn(64, 64, 3, 3, generator=g, dtype=torch.float64) * 0.04).requires_grad_()
+    ws = (torch.randn(64, 64, 1, 1, generator=g, dtype=torch.float64) * 0.1).requires_grad_()
+    h = F.relu(F.conv2d(x, w1, None, stride=2, padding=1) - 0.3)
+    y = F.relu(F.conv2d(h, w2, None, padding=1) + F.conv2d(x, ws, None, stride=2) - 0.3)
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    dz = (gy * (y > 0)).detach()
+    hh = h.detach().requires_grad_()
+    F.conv2d(hh, w2.detach(), None, padding=1).backward(dz)
+    dh_ref = hh.grad * (h > 0)
+    nh = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().float().cuda()
+    xg, hg, dzg = nh(x), nh(h), nh(dz)
+    _, wd1 = ops.pack_conv_weight(w1.detach().float().cuda())
+    _, wd2 = ops.pack_conv_weight(w2.detach().float().cuda())
+    _, wds = ops.pack_conv_weight(ws.detach().float().cuda())
+    for name, prec in (("fp32-simt", 0), ("tf32x3", 1), ("tf32", 2)):
+        dw2, _ = ops.conv_wgrad(hg, dzg, 3, 1, prec)
+        dws, _ = ops.conv_wgrad(xg, dzg, 1, 2, prec, want_db=False)
+        dh = ops.conv_dgrad(dzg, wd2, hg.shape, 3, 1, prec, mask_src=hg)
+        dw1, _ = ops.conv_wgrad(xg, nh(dh_ref), 3, 2, prec)
+        dx = ops.conv_dgrad(nh(dh_ref), wd1, xg.shape, 3, 2, prec, mask_src=xg, skip=(dzg, wds, 2))
+        P(f"stage bwd {name:10s} dgrad_s1 {rel(dh.permute(0, 3, 1, 2), dh_ref):.2e} dgrad_s2+skip {rel(dx.permute(0, 3, 1, 2), x.grad):.2e} "
+          f"wgrad3x3s1 {rel(dw2, w2.grad):.2e} wgrad3x3s2 {rel(dw1, w1.grad):.2e} wgrad1x1s2 {rel(dws, ws.grad):.2e}")
+
+
 def model_diag(case):
     from b200np import engine
     from trainer.losses import LossFunc
@@ -102,6 +134,9 @@ def model_diag(case):
         nonq = [v for k, v in errs.items() if "_W_q" not in k]
         wq = [v for k, v in errs.items() if "_W_q" in k]
         worst_k = max((k for k in errs if "_W_q" not in k), key=lambda k: errs[k])
+        if name == "b200np tf32x3":
+            for k in sorted(errs, key=lambda k: -errs[k])[:14]:
+                P(f"      x3 {errs[k]:.2e}  {k}")
         P(f"{name:22s} mu {rel(mu, mu64):.2e} loss {abs(loss - l64) / abs(l64):.2e} | grads: global {rel(flat, flat64):.2e} "
           f"median {np.median(nonq):.2e} worst {max(nonq):.2e} ({worst_k})" + (f" | _W_q worst {max(wq):.2e}" if wq else ""))
 
@@ -137,7 +172,7 @@ def favor_diag():
 if __name__ == "__main__":
     torch.manual_seed(0)
     conv_diag()
-    favor_diag()
+    convops_diag()
     for c in sys.argv[1:] or ["cnp_distractor_max", "anp_distractor"]:
         model_diag(c)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
