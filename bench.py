@@ -264,9 +264,9 @@ def dominant_kernel_roofline(args, dev):
     w2 = (torch.randn(64, 64, 3, 3, generator=g) * 0.04).to(dev)
     ws = (torch.randn(64, 64, 1, 1, generator=g) * 0.1).to(dev)
     b = torch.zeros(64, device=dev)
-    wf2, _ = ops.pack_conv_weight(w2)
-    wfs, _ = ops.pack_conv_weight(ws)
-    run = lambda: ops.conv_fwd(h, wf2, b, 3, 1, 1, prec, skip=(x, wfs, b, 2))
+    wf2 = ops.pack_conv_weight(w2)
+    wfs = ops.pack_conv_weight(ws)
+    run = lambda: ops.conv_fwd(h, wf2, b, 1, 1, prec, skip=(x, wfs, b, 2))
     for _ in range(3):
         run()
     torch.cuda.synchronize()

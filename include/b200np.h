@@ -71,10 +71,13 @@ int b200np_conv_small_wgrad(const float* x, const float* dy, float* dw, float* d
  * 1x1 projection (:200-204), encoder_w0's 2nd/3rd convs (networks/CNPShapeNet1D.py:49-53) and
  * their autograd backward.
  *
- * Packed weights (made by b200np_pack_conv_weight from torch [Cout,Cin,R,R]):
- *   wf [R*R][Cout][Cin]  -- forward / wgrad order
- *   wd [R*R][Cin][Cout]  -- data-gradient order
+ * Packed weights (made by b200np_pack_conv_weight from torch [Cout,Cin,R,R]) are opaque buffers of
+ * b200np_packed_weight_floats(Cout,Cin,R) floats each:
+ *   wf: [R*R][Cout][Cin] forward order,  wd: [R*R][Cin][Cout] data-gradient order,
+ *   followed (64x64 layers) by the tensor-core image of the same slabs: tf32 hi/lo split,
+ *   pre-swizzled 8 KB tiles that the tcgen05 kernels fetch with one bulk copy per K-block.
  * ------------------------------------------------------------------------------------------ */
+size_t b200np_packed_weight_floats(int Cout, int Cin, int R);
 int b200np_pack_conv_weight(const float* w, float* wf, float* wd, int Cout, int Cin, int R,
                             void* stream);
 

@@ -58,7 +58,7 @@ def test_conv_small_fwd_and_wgrad(cin, r, cout, hw):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
-@pytest.mark.parametrize("cin,cout,hw,n", [(64, 64, 16, 3), (64, 64, 4, 5), (64, 64, 2, 70), (32, 48, 16, 2), (48, 64, 8, 2)])
+@pytest.mark.parametrize("cin,cout,hw,n", [(64, 64, 16, 3), (64, 64, 4, 5), (64, 64, 2, 70), (64, 64, 64, 2), (64, 64, 32, 3), (32, 48, 16, 2), (48, 64, 8, 2)])
 def test_conv_block_ops(prec, cin, cout, hw, n):
     """3x3 s2 / 3x3 s1 / fused skip projection: forward, data gradient (with ReLU mask), weight grad."""
     ops = _ops()
@@ -72,8 +72,8 @@ def test_conv_block_ops(prec, cin, cout, hw, n):
     pre1 = F.conv2d(x, w1, b1, stride=2, padding=1)
     h = F.relu(pre1)
     xg = nhwc(x.detach())
-    wf1, wd1 = ops.pack_conv_weight(w1.detach().float().cuda())
-    hg = ops.conv_fwd(xg, wf1, b1.detach().float().cuda(), 3, 2, 1, P)
+    p1 = ops.pack_conv_weight(w1.detach().float().cuda())
+    hg = ops.conv_fwd(xg, p1, b1.detach().float().cuda(), 2, 1, P)
     assert rel(from_nhwc(hg), h) < tol
     if hw < 4:
         return
@@ -82,11 +82,11 @@ def test_conv_block_ops(prec, cin, cout, hw, n):
         w2, b2 = rnd(cout, cout, 3, 3, seed=4, scale=0.05).requires_grad_(), rnd(cout, seed=5, scale=0.1).requires_grad_()
         ws, bs = rnd(cout, cin, 1, 1, seed=6, scale=0.1).requires_grad_(), rnd(cout, seed=7, scale=0.1).requires_grad_()
         y = F.relu(F.conv2d(h, w2, b2, padding=1) + F.conv2d(x, ws, bs, stride=2))
-        wf2, wd2 = ops.pack_conv_weight(w2.detach().float().cuda())
-        wfs, wds = ops.pack_conv_weight(ws.detach().float().cuda())
+        p2 = ops.pack_conv_weight(w2.detach().float().cuda())
+        ps = ops.pack_conv_weight(ws.detach().float().cuda())
         hgx = nhwc(h.detach())
-        yg = ops.conv_fwd(hgx, wf2, b2.detach().float().cuda(), 3, 1, 1, P,
-                          skip=(xg, wfs, bs.detach().float().cuda(), 2))
+        yg = ops.conv_fwd(hgx, p2, b2.detach().float().cuda(), 1, 1, P,
+                          skip=(xg, ps, bs.detach().float().cuda(), 2))
         assert rel(from_nhwc(yg), y) < tol
         gy = rnd(*y.shape, seed=8)
         y.backward(gy)
@@ -95,7 +95,7 @@ def test_conv_block_ops(prec, cin, cout, hw, n):
         dw2, db2 = ops.conv_wgrad(hgx, dzg, 3, 1, P)
         dws, _ = ops.conv_wgrad(xg, dzg, 1, 2, P, want_db=False)
         assert rel(dw2, w2.grad) < tol and rel(db2, b2.grad) < 1e-5 and rel(dws, ws.grad) < tol
-        dh = ops.conv_dgrad(dzg, wd2, hgx.shape, 3, 1, P, mask_src=hgx)
+        dh = ops.conv_dgrad(dzg, p2, hgx.shape, 1, P, mask_src=hgx)
         # reference dh: gradient at conv1's pre-activation
         hh = h.detach().requires_grad_()
         F.conv2d(hh, w2.detach(), None, padding=1).backward(dz)
@@ -103,7 +103,7 @@ def test_conv_block_ops(prec, cin, cout, hw, n):
         assert rel(from_nhwc(dh), dh_ref) < tol
         dw1, db1 = ops.conv_wgrad(xg, dh, 3, 2, P)
         assert rel(dw1, w1.grad) < tol and rel(db1, b1.grad) < max(tol, 2e-5)
-        dx = ops.conv_dgrad(dh, wd1, xg.shape, 3, 2, P, mask_src=xg, skip=(dzg, wds, 2))
+        dx = ops.conv_dgrad(dh, p1, xg.shape, 2, P, mask_src=xg, skip=(dzg, ps, 2))
         assert rel(from_nhwc(dx), x.grad * (x > 0)) < tol
     else:
         gy = rnd(*h.shape, seed=8)
@@ -111,7 +111,7 @@ def test_conv_block_ops(prec, cin, cout, hw, n):
         dz = nhwc((gy * (h > 0)).detach())
         dw1, db1 = ops.conv_wgrad(xg, dz, 3, 2, P)
         assert rel(dw1, w1.grad) < tol and rel(db1, b1.grad) < max(tol, 2e-5)
-        dx = ops.conv_dgrad(dz, wd1, xg.shape, 3, 2, P, mask_src=None)
+        dx = ops.conv_dgrad(dz, p1, xg.shape, 2, P, mask_src=None)
         assert rel(from_nhwc(dx), x.grad) < tol
 
 

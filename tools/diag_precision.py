@@ -42,11 +42,11 @@ def conv_diag():
     b = torch.randn(64, generator=g, dtype=torch.float64) * 0.1
     ref = F.relu(F.conv2d(h, w2, b, padding=1) + F.conv2d(x, ws, b, stride=2))
     nh = lambda t: t.permute(0, 2, 3, 1).contiguous().float().cuda()
-    wf2, _ = ops.pack_conv_weight(w2.float().cuda())
-    wfs, _ = ops.pack_conv_weight(ws.float().cuda())
+    wf2 = ops.pack_conv_weight(w2.float().cuda())
+    wfs = ops.pack_conv_weight(ws.float().cuda())
     bg = b.float().cuda()
     for name, prec in (("fp32-simt", 0), ("tf32x3", 1), ("tf32", 2)):
-        y = ops.conv_fwd(nh(h), wf2, bg, 3, 1, 1, prec, skip=(nh(x), wfs, bg, 2))
+        y = ops.conv_fwd(nh(h), wf2, bg, 1, 1, prec, skip=(nh(x), wfs, bg, 2))
         P(f"conv2+skip fwd  {name:10s} rel-L2 vs fp64: {rel(y.permute(0, 3, 1, 2), ref):.3e}")
     for tf in (False, True):
         torch.backends.cudnn.allow_tf32 = tf
@@ -76,15 +76,15 @@ def convops_diag():
     dh_ref = hh.grad * (h > 0)
     nh = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().float().cuda()
     xg, hg, dzg = nh(x), nh(h), nh(dz)
-    _, wd1 = ops.pack_conv_weight(w1.detach().float().cuda())
-    _, wd2 = ops.pack_conv_weight(w2.detach().float().cuda())
-    _, wds = ops.pack_conv_weight(ws.detach().float().cuda())
+    wd1 = ops.pack_conv_weight(w1.detach().float().cuda())
+    wd2 = ops.pack_conv_weight(w2.detach().float().cuda())
+    wds = ops.pack_conv_weight(ws.detach().float().cuda())
     for name, prec in (("fp32-simt", 0), ("tf32x3", 1), ("tf32", 2)):
         dw2, _ = ops.conv_wgrad(hg, dzg, 3, 1, prec)
         dws, _ = ops.conv_wgrad(xg, dzg, 1, 2, prec, want_db=False)
-        dh = ops.conv_dgrad(dzg, wd2, hg.shape, 3, 1, prec, mask_src=hg)
+        dh = ops.conv_dgrad(dzg, wd2, hg.shape, 1, prec, mask_src=hg)
         dw1, _ = ops.conv_wgrad(xg, nh(dh_ref), 3, 2, prec)
-        dx = ops.conv_dgrad(nh(dh_ref), wd1, xg.shape, 3, 2, prec, mask_src=xg, skip=(dzg, wds, 2))
+        dx = ops.conv_dgrad(nh(dh_ref), wd1, xg.shape, 2, prec, mask_src=xg, skip=(dzg, wds, 2))
         P(f"stage bwd {name:10s} dgrad_s1 {rel(dh.permute(0, 3, 1, 2), dh_ref):.2e} dgrad_s2+skip {rel(dx.permute(0, 3, 1, 2), x.grad):.2e} "
           f"wgrad3x3s1 {rel(dw2, w2.grad):.2e} wgrad3x3s2 {rel(dw1, w1.grad):.2e} wgrad1x1s2 {rel(dws, ws.grad):.2e}")
 

@@ -57,13 +57,11 @@ class TrunkFn(Function):
         x, acts, packs = x0, [], []
         for l in range(4):
             w1, b1, w2, b2, wsk, bsk = params[2 + 6 * l: 8 + 6 * l]
-            wf1, wd1 = ops.pack_conv_weight(w1)
-            wf2, wd2 = ops.pack_conv_weight(w2)
-            wfs, wds = ops.pack_conv_weight(wsk)
-            h = ops.conv_fwd(x, wf1, b1, 3, 2, ACT_RELU, prec)
-            y = ops.conv_fwd(h, wf2, b2, 3, 1, ACT_RELU, prec, skip=(x, wfs, bsk, 2))
+            p1, p2, ps = ops.pack_conv_weight(w1), ops.pack_conv_weight(w2), ops.pack_conv_weight(wsk)
+            h = ops.conv_fwd(x, p1, b1, 2, ACT_RELU, prec)
+            y = ops.conv_fwd(h, p2, b2, 1, ACT_RELU, prec, skip=(x, ps, bsk, 2))
             acts.append((x, h, y))
-            packs.append((wd1, wd2, wds))
+            packs.append((p1, p2, ps))
             x = y
         outs, idxs, off = [], [], 0
         for n in Ns:
@@ -98,12 +96,12 @@ class TrunkFn(Function):
         grads = [None] * 26
         for l in (3, 2, 1, 0):
             x, h, _ = ctx.acts[l]
-            wd1, wd2, wds = ctx.packs[l]
+            p1, p2, ps = ctx.packs[l]
             dw2, db2 = ops.conv_wgrad(h, dy, 3, 1, prec)
             dws, _ = ops.conv_wgrad(x, dy, 1, 2, prec, want_db=False)
-            dh = ops.conv_dgrad(dy, wd2, h.shape, 3, 1, prec, mask_src=h)
+            dh = ops.conv_dgrad(dy, p2, h.shape, 1, prec, mask_src=h)
             dw1, db1 = ops.conv_wgrad(x, dh, 3, 2, prec)
-            dx = ops.conv_dgrad(dh, wd1, x.shape, 3, 2, prec, mask_src=x, skip=(dy, wds, 2))
+            dx = ops.conv_dgrad(dh, p1, x.shape, 2, prec, mask_src=x, skip=(dy, ps, 2))
             grads[2 + 6 * l: 8 + 6 * l] = [dw1, db1, dw2, db2, dws, db2.clone()]
             dy = dx
         off, dw_acc, db_acc = 0, None, None
@@ -136,11 +134,10 @@ class EncoderW0Fn(Function):
         for im, n in zip(imgs, Ns):
             ops.conv_small_fwd(im, w0, b0, out=x1[off:off + n], relu=True)
             off += n
-        wf2, wd2 = ops.pack_conv_weight(w2)
-        wf5, wd5 = ops.pack_conv_weight(w5)
-        x2 = ops.conv_fwd(x1, wf2, b2, 3, 2, ACT_RELU, prec)
+        wd2, wd5 = ops.pack_conv_weight(w2), ops.pack_conv_weight(w5)
+        x2 = ops.conv_fwd(x1, wd2, b2, 2, ACT_RELU, prec)
         x3, pidx = ops.maxpool2x2_fwd(x2)
-        x4 = ops.conv_fwd(x3, wf5, b5, 3, 2, ACT_RELU, prec)
+        x4 = ops.conv_fwd(x3, wd5, b5, 2, ACT_RELU, prec)
         outs, off = [], 0
         for n in Ns:
             outs.append(ops.nhwc_to_nchw_flat(x4[off:off + n]))
@@ -159,10 +156,10 @@ class EncoderW0Fn(Function):
             ops.nchw_flat_to_nhwc(do.contiguous(), x4[off:off + n], d4[off:off + n])
             off += n
         dw5, db5 = ops.conv_wgrad(x3, d4, 3, 2, prec)
-        d3 = ops.conv_dgrad(d4, wd5, x3.shape, 3, 2, prec, mask_src=None)
+        d3 = ops.conv_dgrad(d4, wd5, x3.shape, 2, prec, mask_src=None)
         d2 = ops.maxpool2x2_bwd(d3, pidx, x2)
         dw2, db2 = ops.conv_wgrad(x1, d2, 3, 2, prec)
-        d1 = ops.conv_dgrad(d2, wd2, x1.shape, 3, 2, prec, mask_src=x1)
+        d1 = ops.conv_dgrad(d2, wd2, x1.shape, 2, prec, mask_src=x1)
         off, dw0, db0 = 0, None, None
         for im, n in zip(ctx.imgs, Ns):
             dw, db = ops.conv_small_wgrad(im, d1[off:off + n], w0_shape)

@@ -62,47 +62,58 @@ def conv_small_wgrad(x, dy, w_shape):
     return dw, db
 
 
+class PackedConvWeight:
+    """Opaque packed copies of one conv weight (include/b200np.h): `f` forward order, `d` data-gradient
+    order, each followed by its tensor-core image for 64x64 layers."""
+    __slots__ = ("f", "d", "Cout", "Cin", "R")
+
+    def __init__(self, f, d, Cout, Cin, R):
+        self.f, self.d, self.Cout, self.Cin, self.R = f, d, Cout, Cin, R
+
+
 def pack_conv_weight(w, want_fwd=True, want_dgrad=True):
-    """torch [Cout,Cin,R,R] -> wf [R*R][Cout][Cin], wd [R*R][Cin][Cout]."""
+    """torch [Cout,Cin,R,R] -> PackedConvWeight."""
     _chk(w, "w")
     Cout, Cin, R, _ = w.shape
-    wf = empty((R * R, Cout, Cin), w) if want_fwd else None
-    wd = empty((R * R, Cin, Cout), w) if want_dgrad else None
+    n = LIB.b200np_packed_weight_floats(Cout, Cin, R)
+    wf = empty((n,), w) if want_fwd else None
+    wd = empty((n,), w) if want_dgrad else None
     check(LIB.b200np_pack_conv_weight(_ptr(w), _ptr(wf), _ptr(wd), Cout, Cin, R, _stream()), "pack_conv_weight")
-    return wf, wd
+    return PackedConvWeight(wf, wd, Cout, Cin, R)
 
 
-def conv_fwd(x, wf, bias, R, stride, act, prec, skip=None):
-    """x NHWC; skip = (xs, wsf, bias_s, stride_s) fuses a 1x1 projection of xs into the output."""
-    _chk(x, "x"), _chk(wf, "wf"), _chk(bias, "bias")
+def conv_fwd(x, pw, bias, stride, act, prec, skip=None):
+    """x NHWC, pw PackedConvWeight; skip = (xs, pws, bias_s, stride_s) fuses a 1x1 projection of xs."""
+    _chk(x, "x"), _chk(pw.f, "wf"), _chk(bias, "bias")
     N, H, W, Cin = x.shape
-    Cout = wf.shape[1]
-    y = empty((N, H // stride, W // stride, Cout), x)
+    assert Cin == pw.Cin
+    y = empty((N, H // stride, W // stride, pw.Cout), x)
     xs = wsf = bs = None
     Cs, ss = 0, 1
     if skip is not None:
-        xs, wsf, bs, ss = skip
-        _chk(xs, "xs"), _chk(wsf, "wsf"), _chk(bs, "bias_s")
-        Cs = xs.shape[3]
-    check(LIB.b200np_conv_fwd(_ptr(x), _ptr(wf), _ptr(bias), _ptr(y), N, H, W, Cin, Cout, R, stride, _ptr(xs),
-                              _ptr(wsf), _ptr(bs), Cs, ss, act, prec, _stream()), "conv_fwd")
+        xs, pws, bs, ss = skip
+        _chk(xs, "xs"), _chk(pws.f, "wsf"), _chk(bs, "bias_s")
+        wsf, Cs = pws.f, xs.shape[3]
+    check(LIB.b200np_conv_fwd(_ptr(x), _ptr(pw.f), _ptr(bias), _ptr(y), N, H, W, Cin, pw.Cout, pw.R, stride,
+                              _ptr(xs), _ptr(wsf), _ptr(bs), Cs, ss, act, prec, _stream()), "conv_fwd")
     return y
 
 
-def conv_dgrad(dy, wd, x_shape, R, stride, prec, mask_src=None, skip=None):
+def conv_dgrad(dy, pw, x_shape, stride, prec, mask_src=None, skip=None):
     """dy NHWC [N,H/stride,W/stride,Cout] -> dx [N,H,W,Cin], gated by mask_src > 0;
-    skip = (dys, wsd, stride_s) adds the gradient through a 1x1 stride_s projection."""
-    _chk(dy, "dy"), _chk(wd, "wd"), _chk(mask_src, "mask")
+    skip = (dys, pws, stride_s) adds the gradient through a 1x1 stride_s projection."""
+    _chk(dy, "dy"), _chk(pw.d, "wd"), _chk(mask_src, "mask")
     N, H, W, Cin = x_shape
     Cout = dy.shape[3]
+    assert Cin == pw.Cin and Cout == pw.Cout
     dx = empty(tuple(x_shape), dy)
     dys = wsd = None
     Cs, ss = 0, 1
     if skip is not None:
-        dys, wsd, ss = skip
-        _chk(dys, "dys"), _chk(wsd, "wsd")
-        Cs = dys.shape[3]
-    check(LIB.b200np_conv_dgrad(_ptr(dy), _ptr(wd), _ptr(dx), _ptr(mask_src), N, H, W, Cin, Cout, R, stride,
+        dys, pws, ss = skip
+        _chk(dys, "dys"), _chk(pws.d, "wsd")
+        wsd, Cs = pws.d, dys.shape[3]
+    check(LIB.b200np_conv_dgrad(_ptr(dy), _ptr(pw.d), _ptr(dx), _ptr(mask_src), N, H, W, Cin, Cout, pw.R, stride,
                                 _ptr(dys), _ptr(wsd), Cs, ss, prec, _stream()), "conv_dgrad")
     return dx
 

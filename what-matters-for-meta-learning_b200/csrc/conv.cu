@@ -2,13 +2,27 @@
 // data-gradient and weight-gradient and dispatches to the tcgen05 kernels (64-channel layers) or
 // the CUDA-core kernels (fp32 validation mode; 32/48-channel layers of encoder_w0).
 #include "tapconv.cuh"
+#include "umma.cuh"
 
 using namespace b200np;
 
 namespace {
 
+// Packed weight buffers (opaque to callers; size = b200np_packed_weight_floats):
+//   [0, RR*Cout*Cin)            K-major slabs   wf: [t][co][ci]    wd: [t][ci][co]
+//   64x64 layers only, after that: the tensor-core image of the same slabs, split into tf32 hi / lo and
+//   laid out as ready-to-copy SWIZZLE_128B tiles  [half][t][hi 8 KB | lo 8 KB]  (row = output channel of
+//   the GEMM, 32 reduction channels per row) -- one cp.async.bulk per K-block in tapconv_halo.cu.
+__device__ __forceinline__ void put_umma(float* img, int RR, int t, int row, int k, float v) {
+  const int half = k >> 5, c = (k & 31) >> 2, e = k & 3;
+  const float hi = umma::to_tf32(v), lo = umma::to_tf32(v - hi);
+  const long long tile = ((long long)half * RR + t) * 4096;          // floats per [hi|lo] K-block
+  const int off = ((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4)) / 4 + e;
+  img[tile + off] = hi;
+  img[tile + 2048 + off] = lo;
+}
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd,
-                                   int Cout, int Cin, int RR) {
+                                   int Cout, int Cin, int RR, int umma_img) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int total = Cout * Cin * RR;
   if (i >= total) return;
@@ -18,6 +32,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   float v = w[i];
   if (wf) wf[((long long)t * Cout + co) * Cin + ci] = v;
   if (wd) wd[((long long)t * Cin + ci) * Cout + co] = v;
+  if (umma_img) {
+    if (wf) put_umma(wf + total, RR, t, co, ci, v);
+    if (wd) put_umma(wd + total, RR, t, ci, co, v);
+  }
 }
 
 // dw[co][ci][t] = sum_chunks part[chunk][t][co][ci]
@@ -46,9 +64,13 @@ bool use_umma(int precision, int Cin, int Cout) {
   return precision != B200NP_PREC_FP32_SIMT && Cin == 64 && Cout == 64;
 }
 
-int run_tapconv(const TapConvArgs& a, int precision, cudaStream_t st) {
+// bp0 / bp1: tensor-core images of the packed weights of source 0 / 1 (nullptr when absent)
+int run_tapconv(const TapConvArgs& a, int precision, cudaStream_t st, const float* bp0 = nullptr, int ns0 = 0,
+                const float* bp1 = nullptr, int ns1 = 0) {
   if (use_umma(precision, a.Cin, a.Cout)) {
-    int rc = launch_tapconv_umma(a, precision, st);
+    int rc = launch_tapconv_halo(a, bp0, ns0, bp1, ns1, precision, st);
+    if (rc != B200NP_E_UNSUPPORTED) return rc;
+    rc = launch_tapconv_umma(a, precision, st);
     if (rc != B200NP_E_UNSUPPORTED) return rc;
   }
   return launch_tapconv_simt(a, st);
@@ -64,8 +86,14 @@ extern "C" int b200np_pack_conv_weight(const float* w, float* wf, float* wd, int
                                        void* stream) {
   if (!w || (!wf && !wd) || Cout <= 0 || Cin <= 0 || R <= 0) return B200NP_E_BADARG;
   int total = Cout * Cin * R * R;
-  pack_weight_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, wf, wd, Cout, Cin, R * R);
+  pack_weight_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, wf, wd, Cout, Cin, R * R,
+                                                                        Cout == 64 && Cin == 64);
   return launch_status();
+}
+
+extern "C" size_t b200np_packed_weight_floats(int Cout, int Cin, int R) {
+  size_t base = (size_t)Cout * Cin * R * R;
+  return (Cout == 64 && Cin == 64) ? 3 * base : base;
 }
 
 extern "C" int b200np_conv_fwd(const float* x, const float* wf, const float* bias, float* y, int N, int H, int W,
@@ -92,7 +120,9 @@ extern "C" int b200np_conv_fwd(const float* x, const float* wf, const float* bia
     a.taps[nt++] = Tap{1, 0, 0, 0};
   }
   a.ntaps = nt;
-  return run_tapconv(a, precision, as_stream(stream));
+  const bool img = Cin == 64 && Cout == 64;
+  return run_tapconv(a, precision, as_stream(stream), img ? wf + (size_t)R * R * 4096 : nullptr, R * R,
+                     (img && xs) ? wsf + 4096 : nullptr, 1);
 }
 
 extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, const float* mask_src, int N, int H,
@@ -116,13 +146,14 @@ extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, co
   a.N = N; a.dstH = H; a.dstW = W;
   a.act = B200NP_ACT_NONE;
   cudaStream_t st = as_stream(stream);
+  const bool img = Cin == 64 && Cout == 64;
   if (stride == 1) {
     a.OH = H; a.OW = W; a.dst_s = 1; a.dst_oy = a.dst_ox = 0;
     int nt = 0;
     for (int r = 0; r < R; ++r)
       for (int s = 0; s < R; ++s) a.taps[nt++] = Tap{0, (int8_t)(pad - r), (int8_t)(pad - s), (int8_t)(r * R + s)};
     a.ntaps = nt;
-    return run_tapconv(a, precision, st);
+    return run_tapconv(a, precision, st, img ? wd + (size_t)R * R * 4096 : nullptr, R * R);
   }
   // stride 2: one launch per parity class of the input pixel (iy,ix) = (2*oy+py, 2*ox+px).
   // y[o] = sum_r x[2o + r - pad] w[r]  =>  dx[i] = sum_{r : (i + pad - r) even} dy[(i + pad - r)/2] w[r]
@@ -140,7 +171,8 @@ extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, co
       if (dys && py == 0 && px == 0) a.taps[nt++] = Tap{1, 0, 0, 0};
       a.ntaps = nt;
       a.dst_oy = py; a.dst_ox = px;
-      int rc = run_tapconv(a, precision, st);
+      int rc = run_tapconv(a, precision, st, img ? wd + (size_t)R * R * 4096 : nullptr, R * R,
+                           (img && dys) ? wsd + 4096 : nullptr, 1);
       if (rc != B200NP_OK) return rc;
     }
   return B200NP_OK;

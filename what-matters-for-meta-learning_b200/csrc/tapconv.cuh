@@ -60,5 +60,8 @@ int launch_tapwgrad_simt(const TapWgradArgs& a, cudaStream_t st);
 // tcgen05 path (tapconv_umma.cu); returns B200NP_E_UNSUPPORTED when the shape does not fit
 int launch_tapconv_umma(const TapConvArgs& a, int precision, cudaStream_t st);
 int launch_tapwgrad_umma(const TapWgradArgs& a, int precision, cudaStream_t st);
+// halo-tile tcgen05 path for unit-input-stride stencils (tapconv_halo.cu); bp = tensor-core weight images
+int launch_tapconv_halo(const TapConvArgs& a, const float* bp0, int nslabs0, const float* bp1, int nslabs1,
+                        int precision, cudaStream_t st);
 
 }  // namespace b200np

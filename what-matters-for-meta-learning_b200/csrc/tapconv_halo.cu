@@ -1,0 +1,359 @@
+// Halo-tile tcgen05 implementation of the tap convolution for unit-input-stride stencils
+// (forward 3x3 s1 [+ fused 1x1 s2 skip projection], data gradient of a 3x3 s1 conv, and the four
+// parity classes of a stride-2 data gradient [+ skip gradient]).
+//
+// Why: the gather kernel (tapconv_umma.cu) re-reads and re-splits every input pixel once per tap
+// (9x) and is bound by the latency of those loads (ncu: long_scoreboard, tensor pipe 14 %).  Here an
+// output tile is 16 rows x 8 pixels of one image; its input HALO ((16+dy_span) x (8+dx_span) pixels) is
+// loaded, split into tf32 hi/lo and stored in shared memory ONCE per 32-channel half, in the K-major
+// SWIZZLE_128B layout with one 128-byte "slot" per halo pixel.  A tap is then nothing but a
+// descriptor: start = slot(dy,dx), 8 consecutive slots = 8 consecutive output pixels, stride between
+// the 16 row groups (SBO) = halo pitch * 128 B.  (The tensor core applies the 128B swizzle to absolute
+// shared-memory address bits, so start addresses at any 128-byte slot and any SBO are legal as long as
+// the data is stored with the same absolute-address swizzle -- verified on B200 by tools/probe.)
+//
+// Weights arrive pre-split (hi/lo) and pre-swizzled from b200np_pack_conv_weight, one 16 KB K-block
+// (tap, channel half) per cp.async.bulk into a 3-deep ring.
+//
+// Persistent, warp-specialised CTA (one per SM), tiles round-robin:
+//   warps 0-3  halo producers (gather + split + store), 2 stages of one channel half each
+//   warp  4    weight producer (one lane issues bulk copies); also owns the TMEM allocation
+//   warp  5    MMA issuer (one lane)
+//   warps 6-9  epilogue (TMEM -> registers -> bias / ReLU mask / activation -> NHWC global)
+// Two accumulator sets in TMEM (2 x 256 columns in the fp32-grade mode) let the epilogue of tile i
+// overlap the MMAs of tile i+1.
+#include "tapconv.cuh"
+#include "umma.cuh"
+
+namespace b200np {
+
+using namespace umma;
+
+namespace {
+
+constexpr int kTileRows = 16, kTileCols = 8;
+constexpr int kMaxHaloSlots = 184;                       // 18 x 10 = 180, rounded up to a multiple of 8
+constexpr uint32_t kHaloBytes = kMaxHaloSlots * 128;     // 23,552 B (multiple of 1024)
+constexpr uint32_t kSkipBytes = 128 * 128;               // 16 KB
+constexpr int kAStages = 2, kBStages = 3;
+constexpr uint32_t kBSlotBytes = 2 * kBBytes;            // hi + lo = 16 KB
+constexpr int kProducerThreads = 128, kThreads = 320;
+constexpr int kMaxTasks = (kMaxHaloSlots + 128) * 8 / kProducerThreads + 1;  // chunk tasks per producer thread
+
+struct HaloArgs {
+  TapConvArgs t;
+  const float* bp[2];   // pre-split, pre-swizzled weights per source: [half][slab][hi 8 KB | lo 8 KB]
+  int nslabs[2];
+  int dy_min, dx_min, HR, HC;   // halo geometry (src 0)
+  int has_skip;                 // one extra tap on src 1 at offset (0,0)
+  int tiles_x, tiles_total;
+};
+
+template <bool X3>
+struct Smem {
+  static constexpr uint32_t kStage = (X3 ? 2u : 1u) * (kHaloBytes + kSkipBytes);
+  static constexpr uint32_t kBSlot = X3 ? kBSlotBytes : kBBytes;
+  static constexpr uint32_t kBOff = kAStages * kStage;
+  static constexpr uint32_t kBarOff = kBOff + kBStages * kBSlot;
+  static constexpr uint32_t kTotal = kBarOff + 256 + 1024;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct Ring {
+  int idx = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++idx == n) { idx = 0; phase ^= 1; }
+  }
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArgs h) {
+  using S = Smem<X3>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* a_full = bars;                  // [kAStages] producers -> MMA            (count 128)
+  uint64_t* a_empty = bars + 2;             // [kAStages] MMA commit -> producers     (count 1)
+  uint64_t* b_full = bars + 4;              // [kBStages] bulk copy tx -> MMA         (count 1 + tx)
+  uint64_t* b_empty = bars + 7;             // [kBStages] MMA commit -> weight warp   (count 1)
+  uint64_t* acc_full = bars + 10;           // [2] MMA commit -> epilogue             (count 1)
+  uint64_t* acc_empty = bars + 12;          // [2] epilogue -> MMA                    (count 128)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const TapConvArgs& a = h.t;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t kAccCols = AccCfg<X3>::kCols;      // columns per accumulator set
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
+
+  if (tid == 0) {
+    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full + s, kProducerThreads); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < kBStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int hslots = h.HR * h.HC;
+  const int ntaps = a.ntaps;
+
+  if (warp < 4) {
+    // ===================== halo producers =====================
+    Ring st;
+    const int total = (hslots + (h.has_skip ? 128 : 0)) * 8;   // 16-byte chunk tasks per stage
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
+      const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
+      const int r0 = rb * kTileRows;
+      const int n = r0 / a.OH, oy0 = r0 - n * a.OH, ox0 = xt * kTileCols;
+      for (int half = 0; half < 2; ++half) {
+        float4 v[kMaxTasks];
+#pragma unroll
+        for (int i = 0; i < kMaxTasks; ++i) {
+          const int j = tid + i * kProducerThreads;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < total) {
+            const int slot = j >> 3, c = j & 7;
+            const float* p = nullptr;
+            if (slot < hslots) {
+              const int hy = slot / h.HC, hx = slot - hy * h.HC;
+              const int iy = oy0 + h.dy_min + hy, ix = ox0 + h.dx_min + hx;
+              if (iy >= 0 && iy < a.srcH[0] && ix >= 0 && ix < a.srcW[0])
+                p = a.src[0] + (((long long)n * a.srcH[0] + iy) * a.srcW[0] + ix) * 64 + half * 32 + c * 4;
+            } else {
+              const int m = slot - hslots;               // output pixel (row group m>>3, column m&7)
+              const int iy = (oy0 + (m >> 3)) * a.in_s[1], ix = (ox0 + (m & 7)) * a.in_s[1];
+              p = a.src[1] + (((long long)n * a.srcH[1] + iy) * a.srcW[1] + ix) * 64 + half * 32 + c * 4;
+            }
+            if (p) v[i] = ldg4(p);
+          }
+        }
+        mbar_wait(a_empty + st.idx, st.phase ^ 1);
+        uint8_t* stage = smem + st.idx * S::kStage;
+        uint8_t* halo_hi = stage;
+        uint8_t* halo_lo = stage + kHaloBytes;
+        uint8_t* skip_hi = stage + (X3 ? 2 : 1) * kHaloBytes;
+        uint8_t* skip_lo = skip_hi + kSkipBytes;
+#pragma unroll
+        for (int i = 0; i < kMaxTasks; ++i) {
+          const int j = tid + i * kProducerThreads;
+          if (j < total) {
+            const int slot = j >> 3, c = j & 7;
+            if (slot < hslots) {
+              // stage bases are 1024-aligned, so the absolute-address swizzle phase of a slot is slot & 7
+              split_store(halo_hi, halo_lo, (uint32_t)(slot * 128 + ((c ^ (slot & 7)) << 4)), v[i], X3);
+            } else {
+              split_store(skip_hi, skip_lo, sw128_offset(slot - hslots, c), v[i], X3);
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(a_full + st.idx);
+        st.advance(kAStages);
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      Ring bs;
+      for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
+        for (int half = 0; half < 2; ++half) {
+          for (int t = 0; t < ntaps; ++t) {
+            const Tap tp = a.taps[t];
+            const float* src = h.bp[tp.src] + ((long long)half * h.nslabs[tp.src] + tp.slab) * (kBSlotBytes / 4);
+            mbar_wait(b_empty + bs.idx, bs.phase ^ 1);
+            mbar_expect_tx(b_full + bs.idx, S::kBSlot);
+            bulk_g2s(smem + S::kBOff + bs.idx * S::kBSlot, src, S::kBSlot, b_full + bs.idx);
+            bs.advance(kBStages);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      Ring st, bs;
+      int acc_set = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t sbo_halo = (uint32_t)h.HC * 128u;
+      for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
+        mbar_wait(acc_empty + acc_set, acc_phase ^ 1);   // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc_set * kAccCols;
+        int kb = 0;                                      // K-block counter of this tile (hi accumulator rotation)
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(a_full + st.idx, st.phase);
+          tc_fence_after();
+          uint8_t* stage = smem + st.idx * S::kStage;
+          const uint32_t halo_hi = smem_u32(stage), halo_lo = halo_hi + kHaloBytes;
+          const uint32_t skip_hi = halo_hi + (X3 ? 2 : 1) * kHaloBytes, skip_lo = skip_hi + kSkipBytes;
+          for (int t = 0; t < ntaps; ++t, ++kb) {
+            const Tap tp = a.taps[t];
+            mbar_wait(b_full + bs.idx, bs.phase);
+            tc_fence_after();
+            uint32_t ah_addr, al_addr, sbo;
+            if (tp.src == 0) {
+              const uint32_t off = (uint32_t)((tp.dy - h.dy_min) * h.HC + (tp.dx - h.dx_min)) * 128u;
+              ah_addr = halo_hi + off; al_addr = halo_lo + off; sbo = sbo_halo;
+            } else {
+              ah_addr = skip_hi; al_addr = skip_lo; sbo = 1024u;
+            }
+            const uint32_t b_addr = smem_u32(smem + S::kBOff + bs.idx * S::kBSlot);
+            // descriptors: same bit layout as make_kmajor_sw128_desc, with a per-operand SBO
+            const uint64_t hi_bits = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
+                                     (static_cast<uint64_t>(1) << 16);
+            const uint64_t ah = hi_bits | ((uint64_t)(sbo >> 4) << 32) | ((ah_addr & 0x3FFFFu) >> 4);
+            const uint64_t al = hi_bits | ((uint64_t)(sbo >> 4) << 32) | ((al_addr & 0x3FFFFu) >> 4);
+            const uint64_t bh = make_kmajor_sw128_desc(b_addr), bl = make_kmajor_sw128_desc(b_addr + kBBytes);
+            const uint32_t d_hi = d0 + (kb % AccCfg<X3>::kHi) * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(d_hi, ah + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb >= AccCfg<X3>::kHi) | (k != 0));
+            if (X3) {
+              const uint32_t d_lo = d0 + AccCfg<X3>::kHi * 64;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb | k) != 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + 2 * k, bl + 2 * k, kIdescTf32_128x64, 1u);
+            }
+            umma_commit(b_empty + bs.idx);
+            bs.advance(kBStages);
+          }
+          umma_commit(a_empty + st.idx);
+          st.advance(kAStages);
+        }
+        umma_commit(acc_full + acc_set);
+        if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;                         // accumulator row = output pixel of the tile
+    int acc_set = 0;
+    uint32_t acc_phase = 0;
+    const int kb_total = 2 * ntaps;
+    const int hi_used = kb_total < AccCfg<X3>::kHi ? kb_total : AccCfg<X3>::kHi;
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
+      const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
+      const int r0 = rb * kTileRows;
+      const int n = r0 / a.OH, oy = r0 - n * a.OH + (m >> 3), ox = xt * kTileCols + (m & 7);
+      const long long off =
+          (((long long)n * a.dstH + (long long)oy * a.dst_s + a.dst_oy) * a.dstW + (long long)ox * a.dst_s + a.dst_ox) * 64;
+      mbar_wait(acc_full + acc_set, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc_set * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float acc[32];
+        gather_acc<X3>(taddr, hf * 32, hi_used, acc);
+        if (hf == 1) {                                   // all TMEM reads of this set are done
+          tc_fence_before();
+          mbar_arrive(acc_empty + acc_set);
+        }
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {
+          const int c = hf * 32 + 4 * qq;
+          float4 o = make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
+          if (a.bias) {
+            const float4 b = ldg4(a.bias + c);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (a.bias2) {
+            const float4 b = ldg4(a.bias2 + c);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (a.mask) {
+            const float4 mk = ldg4(a.mask + off + c);
+            o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
+            o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+          }
+          if (a.act == B200NP_ACT_RELU) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+          }
+          *reinterpret_cast<float4*>(a.dst + off + c) = o;
+        }
+      }
+      if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <bool X3>
+int launch_halo(const HaloArgs& h, cudaStream_t st) {
+  const size_t smem = Smem<X3>::kTotal;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tapconv_halo_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return B200NP_E_LAUNCH;
+    configured = true;
+  }
+  int grid = h.tiles_total < kNumSMs ? h.tiles_total : kNumSMs;
+  tapconv_halo_kernel<X3><<<grid, kThreads, smem, st>>>(h);
+  return launch_status();
+}
+
+}  // namespace
+
+// Eligibility + geometry.  `bp0` / `bp1`: pre-split weights of source 0 / 1 (see b200np_pack_conv_weight).
+int launch_tapconv_halo(const TapConvArgs& a, const float* bp0, int nslabs0, const float* bp1, int nslabs1,
+                        int precision, cudaStream_t st) {
+  if (a.Cin != 64 || a.Cout != 64 || a.ntaps < 1 || a.ntaps > kMaxTaps || !bp0) return B200NP_E_UNSUPPORTED;
+  if (a.act != B200NP_ACT_NONE && a.act != B200NP_ACT_RELU) return B200NP_E_UNSUPPORTED;
+  if (a.OH % kTileRows != 0 || a.OW % kTileCols != 0 || a.in_s[0] != 1) return B200NP_E_UNSUPPORTED;
+  HaloArgs h{};
+  h.t = a;
+  h.bp[0] = bp0; h.bp[1] = bp1; h.nslabs[0] = nslabs0; h.nslabs[1] = nslabs1;
+  int dy_min = 127, dy_max = -127, dx_min = 127, dx_max = -127, n0 = 0, n1 = 0;
+  for (int t = 0; t < a.ntaps; ++t) {
+    const Tap& tp = a.taps[t];
+    if (tp.src == 0) {
+      ++n0;
+      dy_min = tp.dy < dy_min ? tp.dy : dy_min; dy_max = tp.dy > dy_max ? tp.dy : dy_max;
+      dx_min = tp.dx < dx_min ? tp.dx : dx_min; dx_max = tp.dx > dx_max ? tp.dx : dx_max;
+    } else {
+      ++n1;
+      if (tp.dy != 0 || tp.dx != 0 || !bp1) return B200NP_E_UNSUPPORTED;
+    }
+  }
+  if (n0 < 1 || n1 > 1) return B200NP_E_UNSUPPORTED;
+  h.dy_min = dy_min; h.dx_min = dx_min;
+  h.HR = kTileRows + dy_max - dy_min; h.HC = kTileCols + dx_max - dx_min;
+  if (h.HR * h.HC > kMaxHaloSlots) return B200NP_E_UNSUPPORTED;
+  h.has_skip = n1;
+  h.tiles_x = a.OW / kTileCols;
+  const long long tiles = (long long)a.N * a.OH / kTileRows * h.tiles_x;
+  if (tiles <= 0) return B200NP_OK;
+  if (tiles > 0x7fffffff) return B200NP_E_UNSUPPORTED;
+  h.tiles_total = (int)tiles;
+  return precision == B200NP_PREC_TF32 ? launch_halo<false>(h, st) : launch_halo<true>(h, st);
+}
+
+}  // namespace b200np

@@ -18,141 +18,14 @@
 // shared-memory ring decouples the gather from the asynchronous MMAs via mbarriers
 // (tcgen05.commit); two CTAs per SM overlap one CTA's gather latency with the other's MMAs.
 #include "tapconv.cuh"
+#include "umma.cuh"
 
 namespace b200np {
 
 namespace {
 
-constexpr int kBM = 128, kBN = 64, kBK = 32;          // K-block = 32 channels = one 128 B swizzle row
-constexpr int kStages = 2;
-constexpr uint32_t kABytes = kBM * kBK * 4;           // 16 KB
-constexpr uint32_t kBBytes = kBN * kBK * 4;           //  8 KB
+using namespace umma;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug traps (sticky error the host sees) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate, issued by one thread.
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start address >> 4 in [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major; 1 by convention),
-// SBO >> 4 in [32,46) = 1024 B between 8-row groups, version 1 in [46,48), layout type 2 in [61,64).
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format
-// TF32 (2) at [7,10)/[10,13), both K-major, N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t kIdescTf32_128x64 = (1u << 4) | (2u << 7) | (2u << 10) | ((kBN >> 3) << 17) | ((kBM >> 4) << 24);
-
-__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
-  return static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
-}
-// fp32 -> tf32 with round-to-nearest (the tensor core itself truncates: measured 2.3x the error of
-// cuDNN's RN path).  The result has its low 13 mantissa bits clear, so hardware truncation is a no-op.
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-// X3: hi = rn_tf32(x), lo = rn_tf32(x - hi) (x - hi is exact in fp32); single pass: rn_tf32(x).
-__device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v, bool x3) {
-  float4 h;
-  h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-  *reinterpret_cast<float4*>(hi_base + off) = h;
-  if (x3) {
-    float4 l;
-    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-    *reinterpret_cast<float4*>(lo_base + off) = l;
-  }
-}
-
-// 32 lanes x 32 columns of fp32 from TMEM into registers (warp-collective)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Accumulator blocks in TMEM.  The tensor core adds into its fp32 accumulator with truncation, which
-// biases a long K loop (measured 3.7e-6 relative at K = 640 -- 10x the CUDA-core fp32 result).  The
-// fp32-grade mode therefore spreads the hi*hi products round-robin over kAccX3 independent 64-column
-// accumulators (each sees 1/kAccX3 of the K-blocks), keeps the 2^-11-smaller cross terms in a block
-// of their own, and sums the blocks with round-to-nearest adds in the epilogue.
-constexpr int kAccX3 = 3;
-template <bool X3> struct AccCfg {
-  static constexpr int kHi = X3 ? kAccX3 : 1;
-  static constexpr int kBlocks = X3 ? kAccX3 + 1 : 1;
-  static constexpr uint32_t kCols = X3 ? 256 : 64;  // power of two >= 64 * kBlocks
-};
-// sum the accumulator blocks of one 32-column half into acc[0..32)
-template <bool X3>
-__device__ __forceinline__ void gather_acc(uint32_t taddr, int col0, int hi_used, float (&acc)[32]) {
-  uint32_t r[32];
-  if (X3) {
-    tmem_ld32(taddr + AccCfg<X3>::kHi * 64 + col0, r);  // cross terms first (smallest magnitude)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-  }
-#pragma unroll
-  for (int b = 0; b < AccCfg<X3>::kHi; ++b) {
-    if (b < hi_used) {
-      tmem_ld32(taddr + b * 64 + col0, r);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
-    }
-  }
-}
 
 template <bool X3>
 __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs a) {
