@@ -1,184 +1,228 @@
-// Small-Cin direct convolution (the 5x5 stride-2 stem with 1 or 3 input channels, and the
-// 3x3 stride-2 first conv of encoder_w0).  K = Cin*R*R is 9..75: far too thin for a tensor-core
-// tile and 12-32 FLOP/B, so these run on CUDA cores and are bound by the NHWC output stream
-// (forward) / the dY read (wgrad).  Input is NCHW exactly as the datasets deliver it.
+// Small-Cin direct convolution: the 5x5 stride-2 stem with 1 or 3 input channels and the 3x3 stride-2
+// first conv of encoder_w0.  K = Cin*R*R is 9..75 -- far too thin for a tensor-core tile and 12-32
+// FLOP/B -- so these run on CUDA cores and are bound by the NHWC output stream (forward: 1 MB per
+// 128x128 image) or the dY read (weight gradient).  Input is NCHW exactly as the datasets deliver it.
+//
+// Both kernels stage the input patch of an (8|4) x 32 output tile in shared memory and give each
+// thread 4 output channels, so that 16 consecutive lanes cover the 64 channels (256 contiguous
+// bytes) of one NHWC pixel: every global access of a warp is a full 128-byte line.
 #include "common.cuh"
 
 using namespace b200np;
 
 namespace {
 
-constexpr int kTile = 16;  // 16x16 output pixels per CTA
+constexpr int kTW = 32;  // output tile width
 
 // ---------------------------------------------------------------------------------------------
 // forward: y[n,oy,ox,:] = act(b + sum_{ci,r,s} w[:,ci,r,s] * x[n,ci,oy*2+r-pad,ox*2+s-pad])
+// thread = (channel group cg = 4 couts, pixel lane pl); weights of its 4 couts live in registers.
 // ---------------------------------------------------------------------------------------------
-template <int CIN, int R>
+template <int CIN, int R, int TH>
 __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __restrict__ x,
                                                             const float* __restrict__ w,
                                                             const float* __restrict__ bias,
                                                             float* __restrict__ y, int H, int W, int Cout,
-                                                            int stride, int pad, int relu) {
-  constexpr int KK = CIN * R * R;
-  constexpr int PH = (kTile - 1) * 2 + R;  // patch extent for stride 2 (stride 1 needs less)
-  constexpr int PW = PH + 1;               // +1: odd row pitch
-  extern __shared__ float smem[];
-  float* patch = smem;                     // [CIN][PH][PW]
-  float* ws = smem + ((CIN * PH * PW + 3) & ~3);  // [KK][Cout], 16 B aligned
-  const int OH = H / stride, OW = W / stride;
-  const int n = blockIdx.z;
-  const int oy0 = blockIdx.y * kTile, ox0 = blockIdx.x * kTile;
+                                                            int pad, int relu) {
+  constexpr int RR = R * R;
+  constexpr int PH = (TH - 1) * 2 + R, PW = (kTW - 1) * 2 + R;
+  constexpr int PWp = PW | 1;  // odd pitch
+  constexpr int MAXP = (TH * kTW * 16) / 256;  // pixels per thread when Cout = 64 (half of them for Cout = 32)
+  __shared__ float patch[CIN][PH][PWp];
+  const int OH = H / 2, OW = W / 2;
+  const int n = blockIdx.z, oy0 = blockIdx.y * TH, ox0 = blockIdx.x * kTW;
   const int tid = threadIdx.x;
+  const int cgs = Cout / 4;               // 16 (Cout 64) or 8 (Cout 32) channel groups
+  const int cg = tid % cgs, pl = tid / cgs, npl = 256 / cgs;
 
-  for (int i = tid; i < KK * Cout; i += 256) {  // transpose weights to [k][co]
-    int co = i / KK, k = i - co * KK;
-    ws[k * Cout + co] = __ldg(w + i);
-  }
-  const int iy0 = oy0 * stride - pad, ix0 = ox0 * stride - pad;
-  const int ph = (kTile - 1) * stride + R;
-  for (int i = tid; i < CIN * ph * ph; i += 256) {
-    int ci = i / (ph * ph), rem = i - ci * ph * ph;
-    int py = rem / ph, px = rem - py * ph;
-    int iy = iy0 + py, ix = ix0 + px;
+  const int iy0 = oy0 * 2 - pad, ix0 = ox0 * 2 - pad;
+  for (int i = tid; i < CIN * PH * PW; i += 256) {
+    const int ci = i / (PH * PW), rem = i - ci * PH * PW;
+    const int py = rem / PW, px = rem - py * PW;
+    const int iy = iy0 + py, ix = ix0 + px;
     float v = 0.f;
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((long long)(n * CIN + ci) * H + iy) * W + ix);
-    patch[(ci * PH + py) * PW + px] = v;
+    patch[ci][py][px] = v;
   }
+  const float4 b4 = ldg4(bias + cg * 4);
   __syncthreads();
 
-  const int ty = tid / kTile, tx = tid % kTile;
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  if (oy >= OH || ox >= OW) return;
-  float* yo = y + ((long long)(n * OH + oy) * OW + ox) * Cout;
-  for (int c0 = 0; c0 < Cout; c0 += 16) {
-    float acc[16];
+  float acc[MAXP][4];
+  const int ppt = TH * kTW / npl;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = __ldg(bias + c0 + j);
+  for (int i = 0; i < MAXP; ++i) { acc[i][0] = b4.x; acc[i][1] = b4.y; acc[i][2] = b4.z; acc[i][3] = b4.w; }
+
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci)
+  for (int ci = 0; ci < CIN; ++ci) {
+    float wr[RR][4];  // this thread's 4 output channels, one input channel: registers
 #pragma unroll
-      for (int r = 0; r < R; ++r)
+    for (int k = 0; k < RR; ++k)
 #pragma unroll
-        for (int s = 0; s < R; ++s) {
-          float v = patch[(ci * PH + ty * stride + r) * PW + tx * stride + s];
-          const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * R + r) * R + s) * Cout + c0);
+      for (int e = 0; e < 4; ++e) wr[k][e] = __ldg(w + ((long long)(cg * 4 + e) * CIN + ci) * RR + k);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 wv = wp[q];
-            acc[q * 4 + 0] = fmaf(v, wv.x, acc[q * 4 + 0]);
-            acc[q * 4 + 1] = fmaf(v, wv.y, acc[q * 4 + 1]);
-            acc[q * 4 + 2] = fmaf(v, wv.z, acc[q * 4 + 2]);
-            acc[q * 4 + 3] = fmaf(v, wv.w, acc[q * 4 + 3]);
+    for (int i = 0; i < MAXP; ++i) {
+      if (i < ppt) {
+        const int p = pl + i * npl;       // pixel index inside the tile
+        const int ty = p / kTW, tx = p - ty * kTW;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int s = 0; s < R; ++s) {
+            const float v = patch[ci][ty * 2 + r][tx * 2 + s];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][e] = fmaf(v, wr[r * R + s][e], acc[i][e]);
           }
-        }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 o = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-      if (relu) {
-        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
       }
-      reinterpret_cast<float4*>(yo + c0)[q] = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    if (i < ppt) {
+      const int p = pl + i * npl;
+      const int ty = p / kTW, tx = p - ty * kTW;
+      const int oy = oy0 + ty, ox = ox0 + tx;
+      if (oy < OH && ox < OW) {
+        float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(y + ((long long)(n * OH + oy) * OW + ox) * Cout + cg * 4) = o;
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// wgrad: dw[co,k] = sum_pixels dy[pix,co] * patch[pix,k];  db[co] = sum dy[pix,co]
-// Stage 1: each CTA walks tiles of 64 output pixels, keeps a [Cout][KKp] partial in registers
-// (thread = one co x a strided set of 4-wide k groups), writes it to ws.  Stage 2 folds CTAs.
+// weight gradient: dw[co,k] = sum_pixels dy[pix,co] * patch[pix,k];  db[co] = sum dy[pix,co]
+// (db rides along as the extra "tap" k = KK whose patch value is 1).
+// Persistent CTAs walk 4 x 32 output tiles; thread = (4 couts, 4 taps, pixel lane) keeps a 4x4
+// partial in registers across all its tiles; stage 2 folds lanes and CTAs deterministically.
 // ---------------------------------------------------------------------------------------------
-constexpr int kWgPix = 64;
+constexpr int kWgTH = 4;
 template <int CIN, int R>
-__global__ void __launch_bounds__(256) conv_small_wgrad_stage1(const float* __restrict__ x,
+__global__ void __launch_bounds__(320) conv_small_wgrad_stage1(const float* __restrict__ x,
                                                               const float* __restrict__ dy,
                                                               float* __restrict__ part, int N, int H, int W,
-                                                              int Cout, int stride, int pad, long long tiles) {
-  constexpr int KK = CIN * R * R;
-  constexpr int KKp = (KK + 15) / 16 * 16;
-  constexpr int NJ = KKp / 16;  // float4 groups per thread
+                                                              int Cout, int pad, int KG, int nlanes,
+                                                              long long tiles) {
+  constexpr int RR = R * R, KK = CIN * RR;
+  constexpr int PH = (kWgTH - 1) * 2 + R, PW = (kTW - 1) * 2 + R;
+  constexpr int PWp = PW | 1;
   extern __shared__ float smem[];
-  float* dys = smem;                       // [64][Cout]
-  float* ps = smem + kWgPix * Cout;        // [64][KKp]
-  const int OH = H / stride, OW = W / stride;
-  const long long npix = (long long)N * OH * OW;
+  float* patch = smem;                                  // [CIN][PH][PWp] (+1 float holding 1.0f for db)
+  float* dys = smem + ((CIN * PH * PWp + 1 + 3) & ~3);   // [128][Cout]
+  const int OH = H / 2, OW = W / 2;
+  const int tiles_x = (OW + kTW - 1) / kTW, tiles_y = (OH + kWgTH - 1) / kWgTH;
   const int tid = threadIdx.x;
-  const int kg_count = 256 / Cout;         // k-groups per pixel row handled in parallel (4 or 8)
-  const int co = tid % Cout, kg = tid / Cout;
-  float acc[NJ][4];
-  float accb = 0.f;
+  const int cgs = Cout / 4;
+  const int lane_threads = cgs * KG;
+  const int lane_id = tid / lane_threads, lt = tid - lane_id * lane_threads;
+  const bool active = lane_id < nlanes;
+  const int cg = lt % cgs, kg = lt / cgs;
+  // patch offsets of this thread's 4 taps (relative to the pixel's patch origin); tap KK -> the 1.0f slot
+  const int one_slot = CIN * PH * PWp;
+  int koff[4];
+  bool kvar[4];
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  for (int e = 0; e < 4; ++e) {
+    const int k = kg * 4 + e;
+    kvar[e] = k < KK;
+    if (k < KK) {
+      const int ci = k / RR, rs = k - ci * RR;
+      koff[e] = (ci * PH + rs / R) * PWp + rs % R;
+    } else {
+      koff[e] = one_slot;  // k == KK reads the constant 1 (bias gradient); k > KK is dropped in stage 2
+    }
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+  if (tid == 0) patch[one_slot] = 1.0f;
 
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const long long p0 = tile * kWgPix;
+    const int xt = (int)(tile % tiles_x);
+    const long long q = tile / tiles_x;
+    const int yt = (int)(q % tiles_y), n = (int)(q / tiles_y);
+    const int oy0 = yt * kWgTH, ox0 = xt * kTW;
+    const int iy0 = oy0 * 2 - pad, ix0 = ox0 * 2 - pad;
     __syncthreads();
-    for (int i = tid; i < kWgPix * Cout; i += 256) {
-      long long p = p0 + i / Cout;
-      dys[i] = p < npix ? __ldg(dy + p0 * Cout + i) : 0.f;
-    }
-    for (int i = tid; i < kWgPix * KKp; i += 256) {
-      int pl = i / KKp, k = i - pl * KKp;
-      long long p = p0 + pl;
+    for (int i = tid; i < CIN * PH * PW; i += blockDim.x) {
+      const int ci = i / (PH * PW), rem = i - ci * PH * PW;
+      const int py = rem / PW, px = rem - py * PW;
+      const int iy = iy0 + py, ix = ix0 + px;
       float v = 0.f;
-      if (p < npix && k < KK) {
-        int ox = (int)(p % OW);
-        long long q = p / OW;
-        int oy = (int)(q % OH);
-        int n = (int)(q / OH);
-        int ci = k / (R * R), rs = k - ci * R * R;
-        int r = rs / R, s = rs - r * R;
-        int iy = oy * stride + r - pad, ix = ox * stride + s - pad;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((long long)(n * CIN + ci) * H + iy) * W + ix);
-      }
-      ps[i] = v;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((long long)(n * CIN + ci) * H + iy) * W + ix);
+      patch[(ci * PH + py) * PWp + px] = v;
+    }
+    const int c4 = Cout / 4;
+    for (int i = tid; i < kWgTH * kTW * c4; i += blockDim.x) {
+      const int p = i / c4, c = i - p * c4;
+      const int ty = p / kTW, tx = p - ty * kTW;
+      const int oy = oy0 + ty, ox = ox0 + tx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (oy < OH && ox < OW) v = ldg4(dy + ((long long)(n * OH + oy) * OW + ox) * Cout + c * 4);
+      reinterpret_cast<float4*>(dys)[i] = v;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int pl = 0; pl < kWgPix; ++pl) {
-      float g = dys[pl * Cout + co];
-      if (kg == 0) accb += g;
+    if (active) {
+      for (int p = lane_id; p < kWgTH * kTW; p += nlanes) {
+        const int ty = p / kTW, tx = p - ty * kTW;
+        const float4 g = reinterpret_cast<const float4*>(dys)[p * c4 + cg];
+        const int base = (ty * 2) * PWp + tx * 2;
+        float pv[4];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        int kq = kg + j * kg_count;  // 4-wide group index
-        if (kq * 4 < KKp) {
-          float4 pv = *reinterpret_cast<const float4*>(ps + pl * KKp + kq * 4);
-          acc[j][0] = fmaf(g, pv.x, acc[j][0]);
-          acc[j][1] = fmaf(g, pv.y, acc[j][1]);
-          acc[j][2] = fmaf(g, pv.z, acc[j][2]);
-          acc[j][3] = fmaf(g, pv.w, acc[j][3]);
+        for (int e = 0; e < 4; ++e) pv[e] = patch[kvar[e] ? base + koff[e] : koff[e]];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[0][e] = fmaf(g.x, pv[e], acc[0][e]);
+          acc[1][e] = fmaf(g.y, pv[e], acc[1][e]);
+          acc[2][e] = fmaf(g.z, pv[e], acc[2][e]);
+          acc[3][e] = fmaf(g.w, pv[e], acc[3][e]);
         }
       }
     }
   }
-  float* po = part + (long long)blockIdx.x * Cout * (KKp + 1);
+  // partial layout: [cta][lane][co][KG*4]
+  if (active) {
+    float* po = part + (((long long)blockIdx.x * nlanes + lane_id) * Cout) * (KG * 4);
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    int kq = kg + j * kg_count;
-    if (kq * 4 < KKp) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) po[co * (KKp + 1) + kq * 4 + e] = acc[j][e];
-    }
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(po + (long long)(cg * 4 + i) * (KG * 4) + kg * 4) =
+          make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
-  if (kg == 0) po[co * (KKp + 1) + KKp] = accb;
 }
 
 __global__ void conv_small_wgrad_stage2(const float* __restrict__ part, float* __restrict__ dw,
-                                        float* __restrict__ db, int Cout, int KK, int KKp, int blocks) {
+                                        float* __restrict__ db, int Cout, int KK, int KGp, int nparts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int total = Cout * (KK + 1);
   if (i >= total) return;
   int co = i / (KK + 1), k = i - co * (KK + 1);
-  int kp = k < KK ? k : KKp;
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += part[(long long)b * Cout * (KKp + 1) + co * (KKp + 1) + kp];
+#pragma unroll 8
+  for (int b = 0; b < nparts; ++b) s += part[((long long)b * Cout + co) * KGp + k];
   if (k < KK) dw[co * KK + k] = s;
   else if (db) db[co] = s;
 }
 
-int wgrad_blocks(long long tiles) {
-  long long b = 2LL * kNumSMs;
-  return (int)(tiles < b ? tiles : b);
+struct WgCfg { int KG, nlanes, threads, blocks; long long tiles; size_t smem, ws; };
+WgCfg wg_cfg(int N, int Cin, int H, int W, int Cout, int R) {
+  WgCfg c;
+  const int KK = Cin * R * R;
+  c.KG = (KK + 1 + 3) / 4;
+  const int lane_threads = (Cout / 4) * c.KG;
+  c.nlanes = 256 / lane_threads < 1 ? 1 : 256 / lane_threads;
+  c.threads = ((c.nlanes * lane_threads + 31) / 32) * 32;
+  const int OH = H / 2, OW = W / 2;
+  c.tiles = (long long)N * ((OH + kWgTH - 1) / kWgTH) * ((OW + kTW - 1) / kTW);
+  long long b = 4LL * kNumSMs;
+  c.blocks = (int)(c.tiles < b ? c.tiles : b);
+  const int PH = (kWgTH - 1) * 2 + R, PW = (kTW - 1) * 2 + R, PWp = PW | 1;
+  c.smem = (size_t)(((Cin * PH * PWp + 1 + 3) & ~3) + kWgTH * kTW * Cout) * sizeof(float);
+  c.ws = (size_t)c.blocks * c.nlanes * Cout * c.KG * 4 * sizeof(float);
+  return c;
 }
+
 bool supported(int Cin, int R, int Cout, int stride, int pad, int H, int W) {
   bool combo = (Cin == 1 && R == 5) || (Cin == 3 && R == 5) || (Cin == 1 && R == 3);
   return combo && (Cout == 32 || Cout == 64) && stride == 2 && pad == R / 2 && H % 2 == 0 && W % 2 == 0 &&
@@ -191,29 +235,27 @@ extern "C" int b200np_conv_small_fwd(const float* x, const float* w, const float
                                      int H, int W, int Cout, int R, int stride, int pad, int relu, void* stream) {
   if (!x || !w || !bias || !y || N <= 0) return B200NP_E_BADARG;
   if (!supported(Cin, R, Cout, stride, pad, H, W)) return B200NP_E_UNSUPPORTED;
-  if (!aligned16(y)) return B200NP_E_BADARG;
-  int OH = H / stride, OW = W / stride;
-  dim3 grid((OW + kTile - 1) / kTile, (OH + kTile - 1) / kTile, N);
-  int PH = (kTile - 1) * 2 + R;
-  size_t smem = (size_t)(((Cin * PH * (PH + 1) + 3) & ~3) + Cin * R * R * Cout) * sizeof(float);
+  if (!aligned16(y) || !aligned16(bias)) return B200NP_E_BADARG;
+  const int OH = H / 2, OW = W / 2;
   cudaStream_t st = as_stream(stream);
-#define LAUNCH(CI, RR)                                                                              \
-  conv_small_fwd_kernel<CI, RR><<<grid, 256, smem, st>>>(x, w, bias, y, H, W, Cout, stride, pad, relu)
-  if (Cin == 1 && R == 5) LAUNCH(1, 5);
-  else if (Cin == 3 && R == 5) LAUNCH(3, 5);
-  else LAUNCH(1, 3);
-#undef LAUNCH
+  if (Cin == 1 && R == 5) {
+    dim3 grid((OW + kTW - 1) / kTW, (OH + 7) / 8, N);
+    conv_small_fwd_kernel<1, 5, 8><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, Cout, pad, relu);
+  } else if (Cin == 3 && R == 5) {
+    dim3 grid((OW + kTW - 1) / kTW, (OH + 3) / 4, N);
+    conv_small_fwd_kernel<3, 5, 4><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, Cout, pad, relu);
+  } else {
+    dim3 grid((OW + kTW - 1) / kTW, (OH + 7) / 8, N);
+    conv_small_fwd_kernel<1, 3, 8><<<grid, 256, 0, st>>>(x, w, bias, y, H, W, Cout, pad, relu);
+  }
   return launch_status();
 }
 
 extern "C" size_t b200np_conv_small_wgrad_workspace(int N, int Cin, int H, int W, int Cout, int R, int stride,
                                                     int pad) {
   (void)pad;
-  if (N <= 0 || stride <= 0) return 0;
-  long long npix = (long long)N * (H / stride) * (W / stride);
-  long long tiles = ceil_div(npix, kWgPix);
-  int KKp = (Cin * R * R + 15) / 16 * 16;
-  return (size_t)wgrad_blocks(tiles) * Cout * (KKp + 1) * sizeof(float);
+  if (N <= 0 || stride != 2) return 0;
+  return wg_cfg(N, Cin, H, W, Cout, R).ws;
 }
 
 extern "C" int b200np_conv_small_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int Cin, int H,
@@ -221,21 +263,26 @@ extern "C" int b200np_conv_small_wgrad(const float* x, const float* dy, float* d
                                        void* stream) {
   if (!x || !dy || !dw || N <= 0) return B200NP_E_BADARG;
   if (!supported(Cin, R, Cout, stride, pad, H, W)) return B200NP_E_UNSUPPORTED;
-  if (!ws || ws_bytes < b200np_conv_small_wgrad_workspace(N, Cin, H, W, Cout, R, stride, pad))
-    return B200NP_E_WORKSPACE;
-  long long npix = (long long)N * (H / stride) * (W / stride);
-  long long tiles = ceil_div(npix, kWgPix);
-  int blocks = wgrad_blocks(tiles);
-  int KK = Cin * R * R, KKp = (KK + 15) / 16 * 16;
-  size_t smem = (size_t)(kWgPix * Cout + kWgPix * KKp) * sizeof(float);
+  if (!aligned16(dy) || !aligned16(ws)) return B200NP_E_BADARG;
+  const WgCfg c = wg_cfg(N, Cin, H, W, Cout, R);
+  if (!ws || ws_bytes < c.ws) return B200NP_E_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-#define LAUNCH(CI, RR)                                                                             \
-  conv_small_wgrad_stage1<CI, RR><<<blocks, 256, smem, st>>>(x, dy, (float*)ws, N, H, W, Cout, stride, pad, tiles)
+#define LAUNCH(CI, RR)                                                                                          \
+  do {                                                                                                          \
+    if (c.smem > 48 * 1024 &&                                                                                   \
+        cudaFuncSetAttribute(conv_small_wgrad_stage1<CI, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                             (int)c.smem) != cudaSuccess)                                                       \
+      return B200NP_E_LAUNCH;                                                                                   \
+    conv_small_wgrad_stage1<CI, RR><<<c.blocks, c.threads, c.smem, st>>>(x, dy, (float*)ws, N, H, W, Cout, pad, \
+                                                                         c.KG, c.nlanes, c.tiles);              \
+  } while (0)
   if (Cin == 1 && R == 5) LAUNCH(1, 5);
   else if (Cin == 3 && R == 5) LAUNCH(3, 5);
   else LAUNCH(1, 3);
 #undef LAUNCH
-  int total = Cout * (KK + 1);
-  conv_small_wgrad_stage2<<<(total + 127) / 128, 128, 0, st>>>((const float*)ws, dw, db, Cout, KK, KKp, blocks);
+  const int KK = Cin * R * R;
+  const int total = Cout * (KK + 1);
+  conv_small_wgrad_stage2<<<(total + 127) / 128, 128, 0, st>>>((const float*)ws, dw, db, Cout, KK, c.KG * 4,
+                                                               c.blocks * c.nlanes);
   return launch_status(2);
 }

@@ -67,8 +67,9 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
   const int brow = tid >> 1, bhalf = tid & 1;  // B: cout row, 64-byte half of the 128 B K-block row
 
   const int KB = a.ntaps * 2;
-  float4 av[8], bv[4];
-  auto fetch = [&](int kb) {
+  // two register buffers: the loads of K-block kb+2 are in flight while kb+1 is staged and kb runs
+  float4 av0[8], bv0[4], av1[8], bv1[4];
+  auto fetch = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
     const int t = kb >> 1, c0 = (kb & 1) * kBK;
     const Tap tp = a.taps[t];
     const int s = tp.src;
@@ -87,8 +88,9 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
     for (int c = 0; c < 4; ++c) bv[c] = ldg4(bp + 4 * c);
   };
 
-  if (KB > 0) fetch(0);
-  for (int kb = 0; kb < KB; ++kb) {
+  if (KB > 0) fetch(0, av0, bv0);
+  if (KB > 1) fetch(1, av1, bv1);
+  auto step = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
     const int s = kb % kStages;
     const int use = kb / kStages;
     if (use >= 1) mbar_wait(bars + s, (use - 1) & 1);  // MMAs that read this stage have retired
@@ -121,7 +123,11 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
       umma_commit(bars + s);                       // stage reusable once these MMAs retire
       if (kb == KB - 1) umma_commit(bars + kStages);  // accumulator complete
     }
-    if (kb + 1 < KB) fetch(kb + 1);
+    if (kb + 2 < KB) fetch(kb + 2, av, bv);
+  };
+  for (int kb = 0; kb < KB; kb += 2) {
+    step(kb, av0, bv0);
+    if (kb + 1 < KB) step(kb + 1, av1, bv1);
   }
 
   // ---- epilogue: TMEM -> registers -> bias / ReLU-mask / activation -> NHWC global ----
@@ -262,8 +268,8 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
   const int b_k = tid >> 2, b_half = (tid >> 1) & 1, b_sub = tid & 1;
 
   const long long KB = p_begin < p_end ? ((p_end - p_begin + kWgK - 1) / kWgK) : 0;
-  float4 av[8], bv[4];
-  auto fetch = [&](long long kb) {
+  float4 av0[8], bv0[4], av1[8], bv1[4];
+  auto fetch = [&](long long kb, float4 (&av)[8], float4 (&bv)[4]) {
     const long long p0 = p_begin + kb * kWgK;
     {
       const long long p = p0 + a_k;
@@ -299,8 +305,9 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
     }
   };
 
-  if (KB > 0) fetch(0);
-  for (long long kb = 0; kb < KB; ++kb) {
+  if (KB > 0) fetch(0, av0, bv0);
+  if (KB > 1) fetch(1, av1, bv1);
+  auto step = [&](long long kb, float4 (&av)[8], float4 (&bv)[4]) {
     const int s = (int)(kb % kStages);
     const long long use = kb / kStages;
     if (use >= 1) mbar_wait(bars + s, (uint32_t)((use - 1) & 1));
@@ -333,7 +340,11 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
       umma_commit(bars + s);
       if (kb == KB - 1) umma_commit(bars + kStages);
     }
-    if (kb + 1 < KB) fetch(kb + 1);
+    if (kb + 2 < KB) fetch(kb + 2, av, bv);
+  };
+  for (long long kb = 0; kb < KB; kb += 2) {
+    step(kb, av0, bv0);
+    if (kb + 1 < KB) step(kb + 1, av1, bv1);
   }
 
   // epilogue: thread (warp w, lane l) holds row m = 32w + l = tap_local*64 + ci, 64 couts
