@@ -52,8 +52,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   dw[((long long)co * Cin + ci) * ntaps + t] = s;
 }
 
+// Pixel chunks per weight gradient.  The tcgen05 kernel runs one CTA per (tap pair, chunk), two CTAs
+// per SM: size the grid to two full waves (a ragged second wave doubled the run time).  The CUDA-core
+// kernel runs one CTA per (tap, chunk).
 int wgrad_chunks(long long M, int ntaps) {
-  long long want = ceil_div(4LL * kNumSMs, ntaps);
+  const int pairs = (ntaps + 1) / 2;
+  long long want = (4LL * kNumSMs) / pairs;
   long long maxc = ceil_div(M, 64);
   if (want > maxc) want = maxc;
   return (int)(want < 1 ? 1 : want);

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = blockIdx.x, pair = blockIdx.y;
+  const int chunk = blockIdx.y, pair = blockIdx.x;
   const long long M = (long long)a.N * a.OH * a.OW;
   const long long p_begin = (long long)chunk * a.pix_per_chunk;
   long long p_end = p_begin + a.pix_per_chunk;
@@ -391,7 +391,7 @@ int launch_wgrad(const TapWgradArgs& a, cudaStream_t st) {
       return B200NP_E_LAUNCH;
     configured = true;
   }
-  dim3 grid(a.chunks, (a.ntaps + 1) / 2);
+  dim3 grid((a.ntaps + 1) / 2, a.chunks);  // pair fastest: the CTAs that share a pixel chunk run together and share it in L2
   tapwgrad_umma_kernel<X3><<<grid, 128, smem, st>>>(a);
   return launch_status();
 }
