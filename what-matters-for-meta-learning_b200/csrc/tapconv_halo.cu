@@ -35,7 +35,7 @@ constexpr int kTileRows = 16, kTileCols = 8;
 constexpr int kMaxHaloSlots = 184;                       // 18 x 10 = 180, rounded up to a multiple of 8
 constexpr uint32_t kHaloBytes = kMaxHaloSlots * 128;     // 23,552 B (multiple of 1024)
 constexpr uint32_t kSkipBytes = 128 * 128;               // 16 KB
-constexpr int kAStages = 2, kBStages = 3;
+constexpr int kAStages = 2, kMaxBStages = 10;
 constexpr uint32_t kBSlotBytes = 2 * kBBytes;            // hi + lo = 16 KB
 constexpr int kProducerThreads = 128, kThreads = 320;
 constexpr int kMaxTasks = (kMaxHaloSlots + 128) * 8 / kProducerThreads + 1;  // chunk tasks per producer thread
@@ -47,16 +47,15 @@ struct HaloArgs {
   int dy_min, dx_min, HR, HC;   // halo geometry (src 0)
   int has_skip;                 // one extra tap on src 1 at offset (0,0)
   int tiles_x, tiles_total;
+  // shared-memory plan (bytes from the 1024-aligned base), sized per launch: the weight ring takes
+  // whatever the two halo stages leave -- its depth is what hides the L2 latency of the bulk copies
+  uint32_t halo_bytes, stage_bytes, b_off, bar_off;
+  int nb;                       // weight ring depth
 };
 
+constexpr uint32_t kSmemBudget = 227 * 1024;
 template <bool X3>
-struct Smem {
-  static constexpr uint32_t kStage = (X3 ? 2u : 1u) * (kHaloBytes + kSkipBytes);
-  static constexpr uint32_t kBSlot = X3 ? kBSlotBytes : kBBytes;
-  static constexpr uint32_t kBOff = kAStages * kStage;
-  static constexpr uint32_t kBarOff = kBOff + kBStages * kBSlot;
-  static constexpr uint32_t kTotal = kBarOff + 256 + 1024;
-};
+constexpr uint32_t b_slot_bytes() { return X3 ? kBSlotBytes : kBBytes; }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -81,17 +80,18 @@ struct Ring {
 
 template <bool X3>
 __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArgs h) {
-  using S = Smem<X3>;
+  constexpr uint32_t kBSlot = b_slot_bytes<X3>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + h.bar_off);
   uint64_t* a_full = bars;                  // [kAStages] producers -> MMA            (count 128)
   uint64_t* a_empty = bars + 2;             // [kAStages] MMA commit -> producers     (count 1)
-  uint64_t* b_full = bars + 4;              // [kBStages] bulk copy tx -> MMA         (count 1 + tx)
-  uint64_t* b_empty = bars + 7;             // [kBStages] MMA commit -> weight warp   (count 1)
-  uint64_t* acc_full = bars + 10;           // [2] MMA commit -> epilogue             (count 1)
-  uint64_t* acc_empty = bars + 12;          // [2] epilogue -> MMA                    (count 128)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* acc_full = bars + 4;            // [2] MMA commit -> epilogue             (count 1)
+  uint64_t* acc_empty = bars + 6;           // [2] epilogue -> MMA                    (count 128)
+  uint64_t* b_full = bars + 8;              // [nb] bulk copy tx -> MMA               (count 1 + tx)
+  uint64_t* b_empty = b_full + kMaxBStages; // [nb] MMA commit -> weight warp         (count 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMaxBStages);
+  const int nb = h.nb;
 
   const TapConvArgs& a = h.t;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
 
   if (tid == 0) {
     for (int s = 0; s < kAStages; ++s) { mbar_init(a_full + s, kProducerThreads); mbar_init(a_empty + s, 1); }
-    for (int s = 0; s < kBStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < nb; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -149,10 +149,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           }
         }
         mbar_wait(a_empty + st.idx, st.phase ^ 1);
-        uint8_t* stage = smem + st.idx * S::kStage;
+        uint8_t* stage = smem + st.idx * h.stage_bytes;
         uint8_t* halo_hi = stage;
-        uint8_t* halo_lo = stage + kHaloBytes;
-        uint8_t* skip_hi = stage + (X3 ? 2 : 1) * kHaloBytes;
+        uint8_t* halo_lo = stage + h.halo_bytes;
+        uint8_t* skip_hi = stage + (X3 ? 2 : 1) * h.halo_bytes;
         uint8_t* skip_lo = skip_hi + kSkipBytes;
 #pragma unroll
         for (int i = 0; i < kMaxTasks; ++i) {
@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             const Tap tp = a.taps[t];
             const float* src = h.bp[tp.src] + ((long long)half * h.nslabs[tp.src] + tp.slab) * (kBSlotBytes / 4);
             mbar_wait(b_empty + bs.idx, bs.phase ^ 1);
-            mbar_expect_tx(b_full + bs.idx, S::kBSlot);
-            bulk_g2s(smem + S::kBOff + bs.idx * S::kBSlot, src, S::kBSlot, b_full + bs.idx);
-            bs.advance(kBStages);
+            mbar_expect_tx(b_full + bs.idx, kBSlot);
+            bulk_g2s(smem + h.b_off + bs.idx * kBSlot, src, kBSlot, b_full + bs.idx);
+            bs.advance(nb);
           }
         }
       }
@@ -204,9 +204,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
         for (int half = 0; half < 2; ++half) {
           mbar_wait(a_full + st.idx, st.phase);
           tc_fence_after();
-          uint8_t* stage = smem + st.idx * S::kStage;
-          const uint32_t halo_hi = smem_u32(stage), halo_lo = halo_hi + kHaloBytes;
-          const uint32_t skip_hi = halo_hi + (X3 ? 2 : 1) * kHaloBytes, skip_lo = skip_hi + kSkipBytes;
+          uint8_t* stage = smem + st.idx * h.stage_bytes;
+          const uint32_t halo_hi = smem_u32(stage), halo_lo = halo_hi + h.halo_bytes;
+          const uint32_t skip_hi = halo_hi + (X3 ? 2 : 1) * h.halo_bytes, skip_lo = skip_hi + kSkipBytes;
           for (int t = 0; t < ntaps; ++t, ++kb) {
             const Tap tp = a.taps[t];
             mbar_wait(b_full + bs.idx, bs.phase);
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             } else {
               ah_addr = skip_hi; al_addr = skip_lo; sbo = 1024u;
             }
-            const uint32_t b_addr = smem_u32(smem + S::kBOff + bs.idx * S::kBSlot);
+            const uint32_t b_addr = smem_u32(smem + h.b_off + bs.idx * kBSlot);
             // descriptors: same bit layout as make_kmajor_sw128_desc, with a per-operand SBO
             const uint64_t hi_bits = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
                                      (static_cast<uint64_t>(1) << 16);
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
               for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + 2 * k, bl + 2 * k, kIdescTf32_128x64, 1u);
             }
             umma_commit(b_empty + bs.idx);
-            bs.advance(kBStages);
+            bs.advance(nb);
           }
           umma_commit(a_empty + st.idx);
           st.advance(kAStages);
@@ -306,14 +306,25 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
 }
 
 template <bool X3>
-int launch_halo(const HaloArgs& h, cudaStream_t st) {
-  const size_t smem = Smem<X3>::kTotal;
-  static bool configured = false;
-  if (!configured) {
+int launch_halo(HaloArgs& h, cudaStream_t st) {
+  // plan shared memory: two halo stages (+ skip tiles when fused), then as deep a weight ring as fits
+  const uint32_t planes = X3 ? 2u : 1u;
+  h.halo_bytes = ((uint32_t)(h.HR * h.HC) * 128u + 1023u) & ~1023u;
+  h.stage_bytes = planes * (h.halo_bytes + (h.has_skip ? kSkipBytes : 0u));
+  h.b_off = kAStages * h.stage_bytes;
+  const uint32_t tail = 1024 /*alignment slack*/ + 256 /*barriers*/;
+  int nb = (int)((kSmemBudget - tail - h.b_off) / b_slot_bytes<X3>());
+  if (nb > kMaxBStages) nb = kMaxBStages;
+  if (nb < 2) return B200NP_E_UNSUPPORTED;
+  h.nb = nb;
+  h.bar_off = h.b_off + nb * b_slot_bytes<X3>();
+  const size_t smem = h.bar_off + tail;
+  static size_t configured = 0;
+  if (smem > configured) {
     if (cudaFuncSetAttribute(tapconv_halo_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
       return B200NP_E_LAUNCH;
-    configured = true;
+    configured = smem;
   }
   int grid = h.tiles_total < kNumSMs ? h.tiles_total : kNumSMs;
   tapconv_halo_kernel<X3><<<grid, kThreads, smem, st>>>(h);
