@@ -120,33 +120,39 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
 
   if (warp < 4) {
     // ===================== halo producers =====================
+    // Thread = fixed 16-byte chunk c of slots s0, s0+16, s0+32, ...  The (row, column) of those slots
+    // advances by a constant (16 / HC, 16 % HC) step, so no division appears in the per-tile loop (with
+    // one producer warp per scheduler, address arithmetic was the producers' critical path).
     Ring st;
-    const int total = (hslots + (h.has_skip ? 128 : 0)) * 8;   // 16-byte chunk tasks per stage
+    const int c = tid & 7, s0 = tid >> 3;
+    const int step_y = 16 / h.HC, step_x = 16 - step_y * h.HC;
+    const int hy0 = s0 / h.HC, hx0 = s0 - hy0 * h.HC;
+    const int nslots = hslots + (h.has_skip ? 128 : 0);
+    const long long row_pitch = (long long)a.srcW[0] * 64;
     for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
       const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
       const int r0 = rb * kTileRows;
       const int n = r0 / a.OH, oy0 = r0 - n * a.OH, ox0 = xt * kTileCols;
+      const int iy_base = oy0 + h.dy_min, ix_base = ox0 + h.dx_min;
       for (int half = 0; half < 2; ++half) {
+        const float* base0 = a.src[0] + ((long long)n * a.srcH[0] * a.srcW[0]) * 64 + half * 32 + c * 4;
         float4 v[kMaxTasks];
+        int slot = s0, hy = hy0, hx = hx0;
 #pragma unroll
         for (int i = 0; i < kMaxTasks; ++i) {
-          const int j = tid + i * kProducerThreads;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < total) {
-            const int slot = j >> 3, c = j & 7;
-            const float* p = nullptr;
-            if (slot < hslots) {
-              const int hy = slot / h.HC, hx = slot - hy * h.HC;
-              const int iy = oy0 + h.dy_min + hy, ix = ox0 + h.dx_min + hx;
-              if (iy >= 0 && iy < a.srcH[0] && ix >= 0 && ix < a.srcW[0])
-                p = a.src[0] + (((long long)n * a.srcH[0] + iy) * a.srcW[0] + ix) * 64 + half * 32 + c * 4;
-            } else {
-              const int m = slot - hslots;               // output pixel (row group m>>3, column m&7)
-              const int iy = (oy0 + (m >> 3)) * a.in_s[1], ix = (ox0 + (m & 7)) * a.in_s[1];
-              p = a.src[1] + (((long long)n * a.srcH[1] + iy) * a.srcW[1] + ix) * 64 + half * 32 + c * 4;
-            }
-            if (p) v[i] = ldg4(p);
+          if (slot < hslots) {
+            const int iy = iy_base + hy, ix = ix_base + hx;
+            if (iy >= 0 && iy < a.srcH[0] && ix >= 0 && ix < a.srcW[0]) v[i] = ldg4(base0 + iy * row_pitch + ix * 64);
+          } else if (slot < nslots) {
+            const int m = slot - hslots;                 // output pixel (row group m>>3, column m&7)
+            const int iy = (oy0 + (m >> 3)) * a.in_s[1], ix = (ox0 + (m & 7)) * a.in_s[1];
+            v[i] = ldg4(a.src[1] + (((long long)n * a.srcH[1] + iy) * a.srcW[1] + ix) * 64 + half * 32 + c * 4);
           }
+          slot += 16;
+          hy += step_y;
+          hx += step_x;
+          if (hx >= h.HC) { hx -= h.HC; ++hy; }
         }
         mbar_wait(a_empty + st.idx, st.phase ^ 1);
         uint8_t* stage = smem + st.idx * h.stage_bytes;
@@ -154,18 +160,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
         uint8_t* halo_lo = stage + h.halo_bytes;
         uint8_t* skip_hi = stage + (X3 ? 2 : 1) * h.halo_bytes;
         uint8_t* skip_lo = skip_hi + kSkipBytes;
+        slot = s0;
 #pragma unroll
         for (int i = 0; i < kMaxTasks; ++i) {
-          const int j = tid + i * kProducerThreads;
-          if (j < total) {
-            const int slot = j >> 3, c = j & 7;
-            if (slot < hslots) {
-              // stage bases are 1024-aligned, so the absolute-address swizzle phase of a slot is slot & 7
-              split_store(halo_hi, halo_lo, (uint32_t)(slot * 128 + ((c ^ (slot & 7)) << 4)), v[i], X3);
-            } else {
-              split_store(skip_hi, skip_lo, sw128_offset(slot - hslots, c), v[i], X3);
-            }
+          if (slot < hslots) {
+            // stage bases are 1024-aligned, so the absolute-address swizzle phase of a slot is slot & 7
+            split_store(halo_hi, halo_lo, (uint32_t)(slot * 128 + ((c ^ (slot & 7)) << 4)), v[i], X3);
+          } else if (slot < nslots) {
+            split_store(skip_hi, skip_lo, sw128_offset(slot - hslots, c), v[i], X3);
           }
+          slot += 16;
         }
         fence_proxy_async();
         mbar_arrive(a_full + st.idx);
