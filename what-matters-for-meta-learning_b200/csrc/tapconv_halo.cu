@@ -16,10 +16,12 @@
 // (tap, channel half) per cp.async.bulk into a 3-deep ring.
 //
 // Persistent, warp-specialised CTA (one per SM), tiles round-robin:
-//   warps 0-3  halo producers (gather + split + store), 2 stages of one channel half each
-//   warp  4    weight producer (one lane issues bulk copies); also owns the TMEM allocation
-//   warp  5    MMA issuer (one lane)
-//   warps 6-9  epilogue (TMEM -> registers -> bias / ReLU mask / activation -> NHWC global)
+//   warps 0-7   halo producers (gather + split + store), 2 stages of one channel half each; eight warps
+//               because the producers are instruction-issue bound (ncu: 1 warp per scheduler stalled on
+//               fixed-latency dependencies), not memory bound
+//   warp  8     weight producer (one lane issues bulk copies); also owns the TMEM allocation
+//   warp  9     MMA issuer (one lane)
+//   warps 10-13 epilogue (TMEM -> registers -> bias / ReLU mask / activation -> NHWC global)
 // Two accumulator sets in TMEM (2 x 256 columns in the fp32-grade mode) let the epilogue of tile i
 // overlap the MMAs of tile i+1.
 #include "tapconv.cuh"
@@ -37,8 +39,11 @@ constexpr uint32_t kHaloBytes = kMaxHaloSlots * 128;     // 23,552 B (multiple o
 constexpr uint32_t kSkipBytes = 128 * 128;               // 16 KB
 constexpr int kAStages = 2, kMaxBStages = 10;
 constexpr uint32_t kBSlotBytes = 2 * kBBytes;            // hi + lo = 16 KB
-constexpr int kProducerThreads = 128, kThreads = 320;
-constexpr int kMaxTasks = (kMaxHaloSlots + 128) * 8 / kProducerThreads + 1;  // chunk tasks per producer thread
+constexpr int kProducerWarps = 8, kProducerThreads = 32 * kProducerWarps;
+constexpr int kWeightWarp = kProducerWarps, kMmaWarp = kProducerWarps + 1, kEpiWarp0 = kProducerWarps + 2;
+constexpr int kThreads = 32 * (kProducerWarps + 2 + 4);
+constexpr int kSlotsPerPass = kProducerThreads / 8;                       // slots covered by one pass of the producers
+constexpr int kMaxTasks = (kMaxHaloSlots + 128 + kSlotsPerPass - 1) / kSlotsPerPass;  // chunk tasks per producer thread
 
 struct HaloArgs {
   TapConvArgs t;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kWeightWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(kTmemCols)
                  : "memory");
@@ -118,17 +123,22 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
   const int hslots = h.HR * h.HC;
   const int ntaps = a.ntaps;
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ===================== halo producers =====================
     // Thread = fixed 16-byte chunk c of slots s0, s0+16, s0+32, ...  The (row, column) of those slots
     // advances by a constant (16 / HC, 16 % HC) step, so no division appears in the per-tile loop (with
     // one producer warp per scheduler, address arithmetic was the producers' critical path).
+    // Slot space of a stage plane: [0, hslots) halo pixels, [hpad, hpad + 128) the skip tile (hpad = hslots
+    // rounded up to 8, so the skip tile starts 1024-aligned and the plain K-major layout "row m at m*128,
+    // chunk c at c ^ (m & 7)" coincides with the halo's absolute-address swizzle: ONE store formula).
     Ring st;
     const int c = tid & 7, s0 = tid >> 3;
-    const int step_y = 16 / h.HC, step_x = 16 - step_y * h.HC;
+    const int step_y = kSlotsPerPass / h.HC, step_x = kSlotsPerPass - step_y * h.HC;
     const int hy0 = s0 / h.HC, hx0 = s0 - hy0 * h.HC;
-    const int nslots = hslots + (h.has_skip ? 128 : 0);
+    const int hpad = (hslots + 7) & ~7;
+    const int nslots = h.has_skip ? hpad + 128 : hslots;
     const long long row_pitch = (long long)a.srcW[0] * 64;
+    const uint32_t plane = h.halo_bytes + (h.has_skip ? kSkipBytes : 0u);
     for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
       const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
       const int r0 = rb * kTileRows;
@@ -136,6 +146,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       const int iy_base = oy0 + h.dy_min, ix_base = ox0 + h.dx_min;
       for (int half = 0; half < 2; ++half) {
         const float* base0 = a.src[0] + ((long long)n * a.srcH[0] * a.srcW[0]) * 64 + half * 32 + c * 4;
+        const float* base1 = h.has_skip ? a.src[1] + ((long long)n * a.srcH[1] * a.srcW[1]) * 64 + half * 32 + c * 4
+                                        : nullptr;
         float4 v[kMaxTasks];
         int slot = s0, hy = hy0, hx = hx0;
 #pragma unroll
@@ -144,39 +156,31 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           if (slot < hslots) {
             const int iy = iy_base + hy, ix = ix_base + hx;
             if (iy >= 0 && iy < a.srcH[0] && ix >= 0 && ix < a.srcW[0]) v[i] = ldg4(base0 + iy * row_pitch + ix * 64);
-          } else if (slot < nslots) {
-            const int m = slot - hslots;                 // output pixel (row group m>>3, column m&7)
+          } else if (slot >= hpad && slot < nslots) {
+            const int m = slot - hpad;                   // output pixel (row group m>>3, column m&7)
             const int iy = (oy0 + (m >> 3)) * a.in_s[1], ix = (ox0 + (m & 7)) * a.in_s[1];
-            v[i] = ldg4(a.src[1] + (((long long)n * a.srcH[1] + iy) * a.srcW[1] + ix) * 64 + half * 32 + c * 4);
+            v[i] = ldg4(base1 + ((long long)iy * a.srcW[1] + ix) * 64);
           }
-          slot += 16;
+          slot += kSlotsPerPass;
           hy += step_y;
           hx += step_x;
           if (hx >= h.HC) { hx -= h.HC; ++hy; }
         }
         mbar_wait(a_empty + st.idx, st.phase ^ 1);
-        uint8_t* stage = smem + st.idx * h.stage_bytes;
-        uint8_t* halo_hi = stage;
-        uint8_t* halo_lo = stage + h.halo_bytes;
-        uint8_t* skip_hi = stage + (X3 ? 2 : 1) * h.halo_bytes;
-        uint8_t* skip_lo = skip_hi + kSkipBytes;
+        uint8_t* plane_hi = smem + st.idx * h.stage_bytes;
+        uint8_t* plane_lo = plane_hi + plane;
         slot = s0;
 #pragma unroll
         for (int i = 0; i < kMaxTasks; ++i) {
-          if (slot < hslots) {
-            // stage bases are 1024-aligned, so the absolute-address swizzle phase of a slot is slot & 7
-            split_store(halo_hi, halo_lo, (uint32_t)(slot * 128 + ((c ^ (slot & 7)) << 4)), v[i], X3);
-          } else if (slot < nslots) {
-            split_store(skip_hi, skip_lo, sw128_offset(slot - hslots, c), v[i], X3);
-          }
-          slot += 16;
+          if (slot < nslots) split_store(plane_hi, plane_lo, (uint32_t)(slot * 128 + ((c ^ (slot & 7)) << 4)), v[i], X3);
+          slot += kSlotsPerPass;
         }
         fence_proxy_async();
         mbar_arrive(a_full + st.idx);
         st.advance(kAStages);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kWeightWarp) {
     // ===================== weight producer =====================
     if (lane == 0) {
       Ring bs;
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       Ring st, bs;
@@ -209,8 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           mbar_wait(a_full + st.idx, st.phase);
           tc_fence_after();
           uint8_t* stage = smem + st.idx * h.stage_bytes;
-          const uint32_t halo_hi = smem_u32(stage), halo_lo = halo_hi + h.halo_bytes;
-          const uint32_t skip_hi = halo_hi + (X3 ? 2 : 1) * h.halo_bytes, skip_lo = skip_hi + kSkipBytes;
+          const uint32_t plane = h.halo_bytes + (h.has_skip ? kSkipBytes : 0u);
+          const uint32_t halo_hi = smem_u32(stage), halo_lo = halo_hi + plane;
+          const uint32_t skip_hi = halo_hi + h.halo_bytes, skip_lo = skip_hi + plane;
           for (int t = 0; t < ntaps; ++t, ++kb) {
             const Tap tp = a.taps[t];
             mbar_wait(b_full + bs.idx, bs.phase);
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access (warp id % 4)
     const int m = q * 32 + lane;                         // accumulator row = output pixel of the tile
     int acc_set = 0;
     uint32_t acc_phase = 0;
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kWeightWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
