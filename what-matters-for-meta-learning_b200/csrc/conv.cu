@@ -38,20 +38,6 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
-// dw[co][ci][t] = sum_chunks part[chunk][t][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int chunks, int ntaps,
-                                    int Cout, int Cin) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // index in part order (t, co, ci): coalesced reads
-  int per = ntaps * Cout * Cin;
-  if (i >= per) return;
-  float s = 0.f;
-#pragma unroll 8
-  for (int c = 0; c < chunks; ++c) s += part[(long long)c * per + i];  // independent loads: 8 in flight
-  int ci = i % Cin, r = i / Cin;
-  int co = r % Cout, t = r / Cout;
-  dw[((long long)co * Cin + ci) * ntaps + t] = s;
-}
-
 // Pixel chunks per weight gradient.  The tcgen05 kernel runs one CTA per (tap pair, chunk), two CTAs
 // per SM: size the grid to two full waves (a ragged second wave doubled the run time).  The CUDA-core
 // kernel runs one CTA per (tap, chunk).
@@ -215,11 +201,12 @@ extern "C" int b200np_conv_wgrad(const float* x, const float* dy, float* dw, flo
   if (rc == B200NP_E_UNSUPPORTED) rc = launch_tapwgrad_simt(a, st);
   if (rc != B200NP_OK) return rc;
   int per = nt * Cout * Cin;
-  wgrad_reduce_kernel<<<(per + 255) / 256, 256, 0, st>>>(a.part, dw, a.chunks, nt, Cout, Cin);
+  rc = launch_reduce_partials(a.part, dw, a.chunks, per, ReduceMap{1, nt, Cout, Cin, nullptr}, st);
+  if (rc != B200NP_OK) return rc;
   if (db) {
     size_t part_bytes = (size_t)a.chunks * per * sizeof(float);
     rc = b200np_colsum(dy, db, M, Cout, Cout, (char*)ws + part_bytes, ws_bytes - part_bytes, stream);
     if (rc != B200NP_OK) return rc;
   }
-  return launch_status(1);
+  return B200NP_OK;
 }

@@ -16,7 +16,10 @@ constexpr int kTW = 32;  // output tile width
 
 // ---------------------------------------------------------------------------------------------
 // forward: y[n,oy,ox,:] = act(b + sum_{ci,r,s} w[:,ci,r,s] * x[n,ci,oy*2+r-pad,ox*2+s-pad])
-// thread = (channel group cg = 4 couts, pixel lane pl); weights of its 4 couts live in registers.
+// thread = (channel group cg = 4 couts, pixel-pair lane); the weights of its 4 couts live in registers.
+// A thread owns PAIRS of horizontally adjacent output pixels: their stride-2 patches overlap, so one
+// patch row of both pixels is two aligned 16-byte shared-memory loads feeding 2*R*4 FMAs
+// (the first version loaded one float per 4 FMAs and was shared-memory-issue bound).
 // ---------------------------------------------------------------------------------------------
 template <int CIN, int R, int TH>
 __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __restrict__ x,
@@ -26,9 +29,10 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __rest
                                                             int pad, int relu) {
   constexpr int RR = R * R;
   constexpr int PH = (TH - 1) * 2 + R, PW = (kTW - 1) * 2 + R;
-  constexpr int PWp = PW | 1;  // odd pitch
-  constexpr int MAXP = (TH * kTW * 16) / 256;  // pixels per thread when Cout = 64 (half of them for Cout = 32)
-  __shared__ float patch[CIN][PH][PWp];
+  constexpr int PWp = (PW + 1 + 3) & ~3;       // pitch multiple of 4 floats (+1: the pair window reads 8)
+  constexpr int NPAIR = TH * kTW / 2;          // pixel pairs per tile
+  constexpr int MAXP = (NPAIR * 16) / 256;     // pairs per thread when Cout = 64 (half of them for Cout = 32)
+  __shared__ __align__(16) float patch[CIN][PH][PWp];
   const int OH = H / 2, OW = W / 2;
   const int n = blockIdx.z, oy0 = blockIdx.y * TH, ox0 = blockIdx.x * kTW;
   const int tid = threadIdx.x;
@@ -36,21 +40,23 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __rest
   const int cg = tid % cgs, pl = tid / cgs, npl = 256 / cgs;
 
   const int iy0 = oy0 * 2 - pad, ix0 = ox0 * 2 - pad;
-  for (int i = tid; i < CIN * PH * PW; i += 256) {
-    const int ci = i / (PH * PW), rem = i - ci * PH * PW;
-    const int py = rem / PW, px = rem - py * PW;
+  for (int i = tid; i < CIN * PH * PWp; i += 256) {
+    const int ci = i / (PH * PWp), rem = i - ci * PH * PWp;
+    const int py = rem / PWp, px = rem - py * PWp;
     const int iy = iy0 + py, ix = ix0 + px;
     float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((long long)(n * CIN + ci) * H + iy) * W + ix);
+    if (px < PW && iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((long long)(n * CIN + ci) * H + iy) * W + ix);
     patch[ci][py][px] = v;
   }
   const float4 b4 = ldg4(bias + cg * 4);
   __syncthreads();
 
-  float acc[MAXP][4];
-  const int ppt = TH * kTW / npl;
+  float acc[MAXP][2][4];
+  const int ppt = NPAIR / npl;
 #pragma unroll
-  for (int i = 0; i < MAXP; ++i) { acc[i][0] = b4.x; acc[i][1] = b4.y; acc[i][2] = b4.z; acc[i][3] = b4.w; }
+  for (int i = 0; i < MAXP; ++i)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { acc[i][q][0] = b4.x; acc[i][q][1] = b4.y; acc[i][q][2] = b4.z; acc[i][q][3] = b4.w; }
 
 #pragma unroll
   for (int ci = 0; ci < CIN; ++ci) {
@@ -62,16 +68,21 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __rest
 #pragma unroll
     for (int i = 0; i < MAXP; ++i) {
       if (i < ppt) {
-        const int p = pl + i * npl;       // pixel index inside the tile
-        const int ty = p / kTW, tx = p - ty * kTW;
+        const int p = pl + i * npl;       // pair index inside the tile: row p / 16, pixels 2*(p%16), +1
+        const int ty = p / (kTW / 2), tp = p - ty * (kTW / 2);
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < R; ++r) {
+          const float4* row = reinterpret_cast<const float4*>(&patch[ci][ty * 2 + r][tp * 4]);
+          const float4 v0 = row[0], v1 = row[1];
+          const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-          for (int s = 0; s < R; ++s) {
-            const float v = patch[ci][ty * 2 + r][tx * 2 + s];
+          for (int s = 0; s < R; ++s)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[i][e] = fmaf(v, wr[r * R + s][e], acc[i][e]);
-          }
+            for (int e = 0; e < 4; ++e) {
+              acc[i][0][e] = fmaf(v[s], wr[r * R + s][e], acc[i][0][e]);
+              acc[i][1][e] = fmaf(v[2 + s], wr[r * R + s][e], acc[i][1][e]);
+            }
+        }
       }
     }
   }
@@ -79,12 +90,16 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __rest
   for (int i = 0; i < MAXP; ++i) {
     if (i < ppt) {
       const int p = pl + i * npl;
-      const int ty = p / kTW, tx = p - ty * kTW;
-      const int oy = oy0 + ty, ox = ox0 + tx;
-      if (oy < OH && ox < OW) {
-        float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        *reinterpret_cast<float4*>(y + ((long long)(n * OH + oy) * OW + ox) * Cout + cg * 4) = o;
+      const int ty = p / (kTW / 2), tp = p - ty * (kTW / 2);
+      const int oy = oy0 + ty;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int ox = ox0 + tp * 2 + q;
+        if (oy < OH && ox < OW) {
+          float4 o = make_float4(acc[i][q][0], acc[i][q][1], acc[i][q][2], acc[i][q][3]);
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          *reinterpret_cast<float4*>(y + ((long long)(n * OH + oy) * OW + ox) * Cout + cg * 4) = o;
+        }
       }
     }
   }
@@ -192,19 +207,6 @@ __global__ void __launch_bounds__(320) conv_small_wgrad_stage1(const float* __re
   }
 }
 
-__global__ void conv_small_wgrad_stage2(const float* __restrict__ part, float* __restrict__ dw,
-                                        float* __restrict__ db, int Cout, int KK, int KGp, int nparts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int total = Cout * (KK + 1);
-  if (i >= total) return;
-  int co = i / (KK + 1), k = i - co * (KK + 1);
-  float s = 0.f;
-#pragma unroll 8
-  for (int b = 0; b < nparts; ++b) s += part[((long long)b * Cout + co) * KGp + k];
-  if (k < KK) dw[co * KK + k] = s;
-  else if (db) db[co] = s;
-}
-
 struct WgCfg { int KG, nlanes, threads, blocks; long long tiles; size_t smem, ws; };
 WgCfg wg_cfg(int N, int Cin, int H, int W, int Cout, int R) {
   WgCfg c;
@@ -215,7 +217,7 @@ WgCfg wg_cfg(int N, int Cin, int H, int W, int Cout, int R) {
   c.threads = ((c.nlanes * lane_threads + 31) / 32) * 32;
   const int OH = H / 2, OW = W / 2;
   c.tiles = (long long)N * ((OH + kWgTH - 1) / kWgTH) * ((OW + kTW - 1) / kTW);
-  long long b = 4LL * kNumSMs;
+  long long b = 2LL * kNumSMs;
   c.blocks = (int)(c.tiles < b ? c.tiles : b);
   const int PH = (kWgTH - 1) * 2 + R, PW = (kTW - 1) * 2 + R, PWp = PW | 1;
   c.smem = (size_t)(((Cin * PH * PWp + 1 + 3) & ~3) + kWgTH * kTW * Cout) * sizeof(float);
@@ -281,8 +283,8 @@ extern "C" int b200np_conv_small_wgrad(const float* x, const float* dy, float* d
   else LAUNCH(1, 3);
 #undef LAUNCH
   const int KK = Cin * R * R;
-  const int total = Cout * (KK + 1);
-  conv_small_wgrad_stage2<<<(total + 127) / 128, 128, 0, st>>>((const float*)ws, dw, db, Cout, KK, c.KG * 4,
-                                                               c.blocks * c.nlanes);
-  return launch_status(2);
+  int rc = launch_status(1);
+  if (rc != B200NP_OK) return rc;
+  return launch_reduce_partials((const float*)ws, dw, c.blocks * c.nlanes, Cout * c.KG * 4,
+                                ReduceMap{2, KK, c.KG * 4, 0, db}, st);
 }

@@ -119,6 +119,46 @@ extern "C" int b200np_repeat_rows_bwd(const float* dy, float* dx, long long rows
 }
 
 // ------------------------------------------------------------------------------------------------
+// Partial-sum reducer shared by the split-K weight gradients and the column sums.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                              int nparts, int n, b200np::ReduceMap map) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (j < n) {
+#pragma unroll 4
+    for (int p = ty; p < nparts; p += 8) s += part[(long long)p * n + j];
+  }
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][tx];
+    if (map.kind == 0) {
+      out[j] = t;
+    } else if (map.kind == 1) {
+      const int ci = j % map.c, r = j / map.c;
+      const int co = r % map.b, tp = r / map.b;
+      out[((long long)co * map.c + ci) * map.a + tp] = t;
+    } else {
+      const int co = j / map.b, k = j - co * map.b;
+      if (k < map.a) out[co * map.a + k] = t;
+      else if (k == map.a && map.out2) map.out2[co] = t;
+    }
+  }
+}
+namespace b200np {
+int launch_reduce_partials(const float* part, float* out, int nparts, int n, ReduceMap map, cudaStream_t st) {
+  if (n <= 0) return B200NP_OK;
+  reduce_partials_kernel<<<(n + 31) / 32, 256, 0, st>>>(part, out, nparts, n, map);
+  return launch_status();
+}
+}  // namespace b200np
+
+// ------------------------------------------------------------------------------------------------
 // Column sums (bias gradients), deterministic two-stage: blocks of (32 columns x 8 row lanes)
 // reduce a contiguous row chunk into ws[chunk][col]; a second kernel folds the chunks in order.
 // ------------------------------------------------------------------------------------------------
@@ -147,13 +187,6 @@ __global__ void colsum_stage1(const float* __restrict__ x, float* __restrict__ p
     part[(long long)chunk * cols + c] = t;
   }
 }
-__global__ void colsum_stage2(const float* __restrict__ part, float* __restrict__ out, int cols, int chunks) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += part[(long long)k * cols + c];
-  out[c] = s;
-}
 extern "C" size_t b200np_colsum_workspace(long long rows, int cols) {
   return (size_t)colsum_chunks(rows) * (size_t)cols * sizeof(float);
 }
@@ -166,8 +199,9 @@ extern "C" int b200np_colsum(const float* x, float* out, long long rows, int col
   if (!ws || ws_bytes < (size_t)chunks * cols * sizeof(float)) return B200NP_E_WORKSPACE;
   dim3 grid((cols + 31) / 32, chunks), block(32, 8);
   colsum_stage1<<<grid, block, 0, as_stream(stream)>>>(x, (float*)ws, rows, cols, ld, chunks);
-  colsum_stage2<<<(cols + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)ws, out, cols, chunks);
-  return launch_status(2);
+  int rc = launch_reduce_partials((const float*)ws, out, chunks, cols, ReduceMap{0, 0, 0, 0, nullptr}, as_stream(stream));
+  if (rc != B200NP_OK) return rc;
+  return launch_status(1);
 }
 
 // ------------------------------------------------------------------------------------------------
