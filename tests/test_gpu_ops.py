@@ -151,34 +151,41 @@ def test_pools_and_flatten():
     assert rel(from_nhwc(d3), x3.grad * (x3 > 0)) < 1e-6
 
 
-@pytest.mark.parametrize("M,N,K", [(420, 256, 272), (37, 2, 256), (300, 100, 80), (1000, 1419, 256), (5, 16, 2)])
-def test_gemm_forward_roles(M, N, K):
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("M,N,K", [(420, 256, 272), (37, 2, 256), (300, 100, 80), (1000, 1419, 256), (5, 16, 2),
+                                   (3360, 256, 1419)])
+def test_gemm_forward_roles(M, N, K, prec):
+    """All three autograd roles of a dense layer (K-major / MN-major operand combinations), K and N tails,
+    the fused epilogue -- on the CUDA-core kernel (fp32) and the tcgen05 kernel (tf32x3 / tf32)."""
     ops = _ops()
+    P = PRECS[prec]
+    t6 = {"fp32": 2e-6, "tf32x3": 4e-6, "tf32": 3e-3}[prec]
     x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.1), rnd(N, seed=3)
     xg, wg, bg = x.float().cuda(), w.float().cuda(), b.float().cuda()
     y = torch.empty(M, N, device="cuda")
-    ops.gemm(xg.data_ptr(), wg.data_ptr(), y.data_ptr(), M, N, K, K, 1, 1, K, N, bias=bg.data_ptr(), act=1)
-    assert rel(y, F.relu(F.linear(x, w, b))) < 2e-6
+    ops.gemm(xg.data_ptr(), wg.data_ptr(), y.data_ptr(), M, N, K, K, 1, 1, K, N, bias=bg.data_ptr(), act=1, prec=P)
+    assert rel(y, F.relu(F.linear(x, w, b))) < t6
     dz = rnd(M, N, seed=4)
     dzg = dz.float().cuda()
     dx = torch.empty(M, K, device="cuda")
-    ops.gemm(dzg.data_ptr(), wg.data_ptr(), dx.data_ptr(), M, K, N, N, 1, K, 1, K)
-    assert rel(dx, dz @ w) < 2e-6
+    ops.gemm(dzg.data_ptr(), wg.data_ptr(), dx.data_ptr(), M, K, N, N, 1, K, 1, K, prec=P)
+    assert rel(dx, dz @ w) < t6
     dw = torch.empty(N, K, device="cuda")
-    ops.gemm(dzg.data_ptr(), xg.data_ptr(), dw.data_ptr(), N, K, M, 1, N, K, 1, K)
-    assert rel(dw, dz.t() @ x) < 2e-6
+    ops.gemm(dzg.data_ptr(), xg.data_ptr(), dw.data_ptr(), N, K, M, 1, N, K, 1, K, prec=P)
+    assert rel(dw, dz.t() @ x) < t6
     db = ops.colsum(dzg, M, N, N)
     assert rel(db, dz.sum(0)) < 2e-6
     # beta / tanh / row_scale*addend epilogue
     add, rs = rnd(M, N, seed=5), rnd(M, seed=6)
     y2 = y.clone()
     ops.gemm(xg.data_ptr(), wg.data_ptr(), y2.data_ptr(), M, N, K, K, 1, 1, K, N, alpha=0.5, beta=1.0, act=2,
-             row_scale=rs.float().cuda(), addend=add.float().cuda(), ld_add=N)
+             row_scale=rs.float().cuda(), addend=add.float().cuda(), ld_add=N, prec=P)
     ref2 = torch.tanh(0.5 * (x @ w.t()) + F.relu(F.linear(x, w, b)) + rs[:, None] * add)
-    assert rel(y2, ref2) < 5e-6
+    assert rel(y2, ref2) < 3 * t6
 
 
-def test_gemm_grouped_heads():
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_gemm_grouped_heads(prec):
     ops = _ops()
     rows, K, d, H = 45, 256, 256, 8
     x = rnd(rows, K, seed=1)
@@ -189,9 +196,9 @@ def test_gemm_grouped_heads():
     bg = [b.float().cuda() for b in bs]
     y = torch.empty(rows, H * d, device="cuda")
     ops.gemm([xg.data_ptr()] * H, [w.data_ptr() for w in wg], [y.data_ptr() + 4 * h * d for h in range(H)],
-             rows, d, K, K, 1, 1, K, H * d, bias=[b.data_ptr() for b in bg])
+             rows, d, K, K, 1, 1, K, H * d, bias=[b.data_ptr() for b in bg], prec=PRECS[prec])
     ref = torch.cat([F.linear(x, w, b) for w, b in zip(ws, bs)], dim=1)
-    assert rel(y, ref) < 2e-6
+    assert rel(y, ref) < 4e-6
 
 
 def test_elementwise_and_reductions():
@@ -265,7 +272,7 @@ def test_adam_matches_torch():
     assert rel(p, p_ref) < 1e-6
 
 
-@pytest.mark.parametrize("prec", ["fp32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("T,H,nt,nc,d", [(2, 8, 5, 4, 64), (2, 8, 21, 15, 256), (1, 2, 36, 25, 64)])
 def test_favor_attention_fwd_bwd(prec, T, H, nt, nc, d):
     """Fused FAVOR+ (re-associated) vs the closed-form fp64 restatement of the reference

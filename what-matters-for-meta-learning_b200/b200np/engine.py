@@ -298,6 +298,8 @@ class FavorAttentionFn(Function):
 
     @staticmethod
     def forward(ctx, prec, T, H, nt, nc, xq, xk, v, proj):
+        if prec == PREC_TF32:
+            prec = PREC_TF32X3  # the feature pre-activations go through exp(): always fp32-grade
         xq, xk, v = xq.contiguous(), xk.contiguous(), v.contiguous()
         M, d = proj.shape
         ldu = (M + 3) // 4 * 4

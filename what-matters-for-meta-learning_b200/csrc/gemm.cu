@@ -8,6 +8,10 @@
 
 using namespace b200np;
 
+namespace b200np {
+int launch_gemm_umma(const b200np_gemm_desc& d, int a_vec, int b_vec, cudaStream_t st);  // gemm_umma.cu
+}
+
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 16, APAD = 4;
@@ -180,6 +184,10 @@ extern "C" int b200np_gemm(const b200np_gemm_desc* dp, void* stream) {
     if (!aligned16(d.B[i])) g.b_vec = 0;
   }
   for (int i = d.groups; i < 8; ++i) { g.d.A[i] = nullptr; g.d.B[i] = nullptr; g.d.C[i] = nullptr; g.d.bias[i] = nullptr; }
+  {  // tensor-core path for everything that fills a tile; CUDA cores for the tiny layers and fp32 mode
+    int rc = launch_gemm_umma(g.d, g.a_vec, g.b_vec, as_stream(stream));
+    if (rc != B200NP_E_UNSUPPORTED) return rc;
+  }
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.groups);
   gemm_kernel<<<grid, 128, 0, as_stream(stream)>>>(g);
   return launch_status();

@@ -1,0 +1,245 @@
+// tcgen05 / TMEM implementation of the strided, grouped GEMM of gemm.cu (same descriptor, same epilogue)
+// for the dense layers and the FAVOR+ feature projections.
+//
+//   C[128 x 64 tile] (+)= A[128 x 32] * B[32 x 64] per K-block, fp32 accumulators in TMEM.
+//
+// The three autograd roles of a dense layer differ only in which index of an operand is contiguous in
+// memory, which maps 1:1 onto the tensor core's operand "major" modes:
+//   forward   A k-contiguous (K-major)   B = W[n][k]  k-contiguous (K-major)
+//   dgrad     A k-contiguous (K-major)   B = W[k][n]  n-contiguous (MN-major)
+//   wgrad     A = dZ[k][m] m-contiguous (MN-major)   B = X[k][n] n-contiguous (MN-major)
+// K-major tiles use SWIZZLE_128B (row = 32 k), MN-major tiles SWIZZLE_128B_BASE32B (row = one k, 32 m|n),
+// see tapconv_umma.cu.  Operands are staged through registers (rn_tf32 rounding / hi-lo split as in the
+// convolutions), two smem stages, loads of K-block kb+2 in flight while kb+1 is staged.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200np {
+
+using namespace umma;
+
+namespace {
+
+constexpr uint32_t kGA = 128 * 32 * 4, kGB = 64 * 32 * 4;  // 16 KB, 8 KB per plane
+
+struct GemmUArgs {
+  b200np_gemm_desc d;
+  int a_vec, b_vec;  // 16-byte loads legal for A / B (pointer and leading-dimension alignment)
+};
+
+// MN-major descriptor / offsets (same as the weight-gradient kernel): 32-wide blocks LBO = 4096 B apart,
+// 4-row groups SBO = 512 B apart, 32-byte swizzle units
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(4096 >> 4) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t mn_off(int block, int k, int chunk) {
+  return static_cast<uint32_t>(block * 4096 + (k >> 2) * 512 + (k & 3) * 128 + (((chunk >> 1) ^ (k & 3)) << 5) +
+                               ((chunk & 1) << 4));
+}
+// 4 consecutive floats from p[0..3] where only the first `valid` exist (valid <= 0: all zero)
+__device__ __forceinline__ float4 load4_guarded(const float* p, int valid, bool vec) {
+  if (valid >= 4 && vec) return ldg4(p);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid > 0) v.x = __ldg(p);
+  if (valid > 1) v.y = __ldg(p + 1);
+  if (valid > 2) v.z = __ldg(p + 2);
+  if (valid > 3) v.w = __ldg(p + 3);
+  return v;
+}
+
+// AK / BK: operand is k-contiguous (K-major) or m|n-contiguous (MN-major)
+template <bool X3, bool AK, bool BK>
+__global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
+  constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kGA + kGB);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
+  const b200np_gemm_desc& d = g.d;
+  const int grp = blockIdx.z;
+  const float* __restrict__ A = d.A[grp];
+  const float* __restrict__ B = d.B[grp];
+  float* __restrict__ C = d.C[grp];
+  const float* __restrict__ bias = d.bias[grp];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
+  const int M = d.M, N = d.N, K = d.K;
+
+  if (tid == 0) {
+    for (int s = 0; s <= kStages; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(AccCfg<X3>::kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  const int KB = (K + 31) / 32;
+  float4 av0[8], bv0[4], av1[8], bv1[4];
+  auto fetch = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
+    const int k0 = kb * 32;
+    if (AK) {  // thread = row m0+tid, 32 consecutive k
+      const int m = m0 + tid;
+      const float* p = A + (long long)m * d.a_rs + k0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) av[c] = load4_guarded(p + 4 * c, m < M ? K - k0 - 4 * c : 0, g.a_vec);
+    } else {   // thread = (k row tid>>2, 32-wide m block tid&3)
+      const int k = k0 + (tid >> 2), mb = m0 + (tid & 3) * 32;
+      const float* p = A + (long long)k * d.a_cs + mb;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) av[c] = load4_guarded(p + 4 * c, k < K ? M - mb - 4 * c : 0, g.a_vec);
+    }
+    if (BK) {  // thread = (row n0 + tid>>1, 16 consecutive k at (tid&1)*16)
+      const int n = n0 + (tid >> 1), kb0 = k0 + (tid & 1) * 16;
+      const float* p = B + (long long)n * d.b_cs + kb0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bv[c] = load4_guarded(p + 4 * c, n < N ? K - kb0 - 4 * c : 0, g.b_vec);
+    } else {   // thread = (k row tid>>2, 16 consecutive n at (tid&3)*16)
+      const int k = k0 + (tid >> 2), nb = n0 + (tid & 3) * 16;
+      const float* p = B + (long long)k * d.b_rs + nb;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bv[c] = load4_guarded(p + 4 * c, k < K ? N - nb - 4 * c : 0, g.b_vec);
+    }
+  };
+  constexpr uint32_t kIdesc = kIdescTf32_128x64 | (AK ? 0u : (1u << 15)) | (BK ? 0u : (1u << 16));
+
+  if (KB > 0) fetch(0, av0, bv0);
+  if (KB > 1) fetch(1, av1, bv1);
+  auto step = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
+    const int s = kb % kStages;
+    const int use = kb / kStages;
+    if (use >= 1) mbar_wait(bars + s, (use - 1) & 1);
+    uint8_t* st = smem + s * kStageBytes;
+    uint8_t* a_hi = st;
+    uint8_t* a_lo = st + kGA;
+    uint8_t* b_hi = st + (X3 ? 2 : 1) * kGA;
+    uint8_t* b_lo = b_hi + kGB;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      split_store(a_hi, a_lo, AK ? sw128_offset(tid, c) : mn_off(tid & 3, tid >> 2, c), av[c], X3);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      split_store(b_hi, b_lo,
+                  BK ? sw128_offset(tid >> 1, (tid & 1) * 4 + c) : mn_off((tid & 3) >> 1, tid >> 2, ((tid & 1) * 4) + c),
+                  bv[c], X3);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ah = AK ? make_kmajor_sw128_desc(smem_u32(a_hi)) : mn_desc(smem_u32(a_hi));
+      const uint64_t bh = BK ? make_kmajor_sw128_desc(smem_u32(b_hi)) : mn_desc(smem_u32(b_hi));
+      constexpr uint64_t ka = AK ? 2 : 64, kbs = BK ? 2 : 64;  // descriptor advance per k-step of 8
+      const uint32_t d_hi = tmem_d + (kb % AccCfg<X3>::kHi) * 64;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_tf32(d_hi, ah + ka * k, bh + kbs * k, kIdesc, (kb >= AccCfg<X3>::kHi) | (k != 0));
+      if (X3) {
+        const uint64_t al = AK ? make_kmajor_sw128_desc(smem_u32(a_lo)) : mn_desc(smem_u32(a_lo));
+        const uint64_t bl = BK ? make_kmajor_sw128_desc(smem_u32(b_lo)) : mn_desc(smem_u32(b_lo));
+        const uint32_t d_lo = tmem_d + AccCfg<X3>::kHi * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + ka * k, bh + kbs * k, kIdesc, (kb | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + ka * k, bl + kbs * k, kIdesc, 1u);
+      }
+      umma_commit(bars + s);
+      if (kb == KB - 1) umma_commit(bars + kStages);
+    }
+    if (kb + 2 < KB) fetch(kb + 2, av, bv);
+  };
+  for (int kb = 0; kb < KB; kb += 2) {
+    step(kb, av0, bv0);
+    if (kb + 1 < KB) step(kb + 1, av1, bv1);
+  }
+
+  // epilogue: thread = row m0 + 32*warp + lane, 64 columns
+  if (KB > 0) {
+    mbar_wait(bars + kStages, 0);
+    tc_fence_after();
+  }
+  const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+  const int hi_used = KB < AccCfg<X3>::kHi ? KB : AccCfg<X3>::kHi;
+  const int m = m0 + tid;
+  const bool use_rs = d.row_scale != nullptr && grp == 0;
+  const float rs = (use_rs && m < M) ? __ldg(d.row_scale + m) : 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float acc[32];
+    if (KB > 0) {
+      gather_acc<X3>(taddr, half * 32, hi_used, acc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    }
+    if (m < M) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + half * 32 + j;
+        if (n < N) {
+          float v = d.alpha * acc[j];
+          if (bias) v += __ldg(bias + n);
+          float* cp = C + (long long)m * d.ldc + n;
+          if (d.beta != 0.f) v = fmaf(d.beta, *cp, v);
+          if (use_rs) v = fmaf(rs, __ldg(d.addend + (long long)m * d.ld_add + n), v);
+          if (d.act == B200NP_ACT_RELU) v = fmaxf(v, 0.f);
+          else if (d.act == B200NP_ACT_TANH) v = tanhf(v);
+          *cp = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(AccCfg<X3>::kCols)
+                 : "memory");
+  }
+}
+
+template <bool X3, bool AK, bool BK>
+int launch(const GemmUArgs& g, cudaStream_t st) {
+  constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kGA + kGB);
+  const size_t smem = kStages * kStageBytes + 1024 + 64;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_umma_kernel<X3, AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return B200NP_E_LAUNCH;
+    configured = true;
+  }
+  dim3 grid((g.d.M + 127) / 128, (g.d.N + 63) / 64, g.d.groups);
+  gemm_umma_kernel<X3, AK, BK><<<grid, 128, smem, st>>>(g);
+  return launch_status();
+}
+
+}  // namespace
+
+// Returns B200NP_E_UNSUPPORTED when the shape is better served by the CUDA-core kernel.
+int launch_gemm_umma(const b200np_gemm_desc& d, int a_vec, int b_vec, cudaStream_t st) {
+  if (d.precision == B200NP_PREC_FP32_SIMT) return B200NP_E_UNSUPPORTED;
+  if (d.K < 32 || d.N < 16 || (long long)d.M * d.N < 64 * 64) return B200NP_E_UNSUPPORTED;  // tiny: not worth a tile
+  const bool AK = d.a_cs == 1, BK = d.b_rs == 1;
+  if (!AK && BK) return B200NP_E_UNSUPPORTED;  // (A m-contiguous, B k-contiguous) never occurs on the path
+  GemmUArgs g;
+  g.d = d;
+  g.a_vec = a_vec;
+  g.b_vec = b_vec;
+  const bool x3 = d.precision != B200NP_PREC_TF32;
+  if (AK && BK) return x3 ? launch<true, true, true>(g, st) : launch<false, true, true>(g, st);
+  if (AK && !BK) return x3 ? launch<true, true, false>(g, st) : launch<false, true, false>(g, st);
+  return x3 ? launch<true, false, false>(g, st) : launch<false, false, false>(g, st);
+}
+
+}  // namespace b200np
