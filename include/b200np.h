@@ -241,6 +241,11 @@ int b200np_loss_fwd_bwd(const float* mu, const float* y, float* loss, float* dmu
 int b200np_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale,
                      void* stream);
+/* Same, with the step counter in device memory (*step_dev is incremented, then used): no host value
+ * changes between steps, so a captured CUDA graph of the whole meta-train step can be replayed. */
+int b200np_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int* step_dev, float grad_scale,
+                         void* stream);
 
 #ifdef __cplusplus
 }

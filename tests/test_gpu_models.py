@@ -190,3 +190,42 @@ def test_fused_adam_training_steps_match_oracle():
         num += float(((sd[k].cpu().double() - w0) - (v.detach().double() - w0)).pow(2).sum())
         den += float((v.detach().double() - w0).pow(2).sum())
     assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
+
+
+def test_cuda_graph_step_equals_eager():
+    """The captured-graph step replays exactly the eager step (same kernels, same order)."""
+    from b200np import engine
+    from b200np.optim import FlatParams, FusedAdam, GraphedStep
+    from trainer.losses import LossFunc
+    engine.set_precision("tf32x3")
+    case = "anp_distractor"
+    method, task, agg, img_agg, extra, T, nc, nt = CASES[case]
+    batches = [[torch.from_numpy(a).cuda() for a in synth.task_batch(task, T, nc, nt, seed=40 + i)] for i in range(3)]
+    finals = []
+    for graphed in (False, True):
+        model, cfg = build_product_model(case, device="cuda")
+        model = model.to("cuda")
+        opt = FusedAdam(FlatParams(model), lr=1e-3)
+        lossf = LossFunc("mse", task)
+        losses = []
+        if graphed:
+            init = {k: v.clone() for k, v in model.state_dict().items()}
+            g = GraphedStep(model, lossf, opt, batches[0], warmup=1)
+            # capture + warm-up advanced the weights: rewind parameters and optimizer state
+            model.load_state_dict(init)
+            opt.m.zero_(), opt.v.zero_(), opt.t_dev.zero_()
+            for b in batches:
+                losses.append(float(g(b)))
+        else:
+            for cx, cy, tx, ty in batches:
+                opt.zero_grad()
+                mu, _, _ = model(cx, cy, tx)
+                loss = lossf.calc_loss(mu, None, ty)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.detach()))
+        torch.cuda.synchronize()
+        finals.append((losses, {k: v.clone() for k, v in model.state_dict().items()}))
+    assert finals[0][0] == pytest.approx(finals[1][0], rel=1e-6)
+    for k in finals[0][1]:
+        assert torch.allclose(finals[0][1][k], finals[1][1][k], rtol=1e-5, atol=1e-7), k

@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200np_favor_key_fixup": (_i, [_p, _p, _p, _p, _p, _ll, _i, _ll, _p]),
     "b200np_loss_fwd_bwd": (_i, [_p, _p, _p, _p, _ll, _i, _i, _i, _p]),
     "b200np_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
+    "b200np_adam_step_dev": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _f, _p]),
 }
 
 

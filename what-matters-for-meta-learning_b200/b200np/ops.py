@@ -300,3 +300,8 @@ def loss_fwd_bwd(mu, y, kind, want_grad=True):
 def adam_step(p, g, m, v, n, lr, b1, b2, eps, wd, step, grad_scale=1.0):
     check(LIB.b200np_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, step, grad_scale,
                                _stream()), "adam_step")
+
+
+def adam_step_dev(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, grad_scale=1.0):
+    check(LIB.b200np_adam_step_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, _ptr(step_dev),
+                                   grad_scale, _stream()), "adam_step_dev")

@@ -368,9 +368,17 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   float denom = sqrtf(v) * inv_bc2_sqrt + eps;
   p = p - step_size * (m / denom);
 }
+__global__ void adam_tick_kernel(int* step) { *step += 1; }
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float b1, float b2, float eps, float wd,
-                            float step_size, float inv_bc2_sqrt, float gs, int vec) {
+                            float step_size, float inv_bc2_sqrt, float gs, int vec, const int* __restrict__ step_dev,
+                            float lr) {
+  if (step_dev) {  // CUDA-graph friendly: the step count lives on the device, bias corrections are derived here
+    const double t = (double)__ldg(step_dev);
+    step_size = (float)((double)lr / (1.0 - pow((double)b1, t)));
+    inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
+  }
   long long st = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (vec) {
@@ -404,6 +412,18 @@ extern "C" int b200np_adam_step(float* p, const float* g, float* m, float* v, lo
   float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   int vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
   adam_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(
-      p, g, m, v, n, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale, vec);
+      p, g, m, v, n, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale, vec, nullptr, lr);
   return launch_status();
+}
+
+extern "C" int b200np_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr,
+                                    float beta1, float beta2, float eps, float weight_decay, int* step_dev,
+                                    float grad_scale, void* stream) {
+  if (n <= 0) return B200NP_OK;
+  if (!p || !g || !m || !v || !step_dev) return B200NP_E_BADARG;
+  int vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
+  adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
+  adam_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, beta1, beta2, eps, weight_decay,
+                                                                        0.f, 0.f, grad_scale, vec, step_dev, lr);
+  return launch_status(2);
 }
