@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Where does the persistent halo kernel wait?  Per-role blocked cycles (diagnostic hook in tapconv_halo.cu)."""
+import ctypes, os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "what-matters-for-meta-learning_b200")]
+from b200np import ops
+from b200np.lib import LIB
+prec = {"tf32x3": 1, "tf32": 2}[sys.argv[1] if len(sys.argv) > 1 else "tf32x3"]
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 1140
+g = torch.Generator().manual_seed(0)
+x = torch.rand(N, 64, 64, 64, generator=g).cuda(); h = torch.rand(N, 32, 32, 64, generator=g).cuda()
+w2 = ops.pack_conv_weight((torch.randn(64, 64, 3, 3, generator=g) * 0.04).cuda())
+ws = ops.pack_conv_weight((torch.randn(64, 64, 1, 1, generator=g) * 0.1).cuda())
+b = torch.zeros(64, device="cuda")
+dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+LIB.b200np_debug_set_halo_timing.argtypes = [ctypes.c_void_p]
+for name, fn in (("fwd conv2+skip", lambda: ops.conv_fwd(h, w2, b, 1, 1, prec, skip=(x, ws, b, 2))),
+                 ("dgrad s1", lambda: ops.conv_dgrad(h, w2, h.shape, 1, prec, mask_src=h))):
+    fn(); torch.cuda.synchronize()
+    LIB.b200np_debug_set_halo_timing(ctypes.c_void_p(dbg.data_ptr()))
+    dbg.zero_(); fn(); torch.cuda.synchronize()
+    LIB.b200np_debug_set_halo_timing(ctypes.c_void_p(0))
+    d = dbg.view(148, 8).double().mean(0).tolist()
+    tiles = N * 8 / 148
+    print(f"{name}: tiles/CTA {tiles:.0f}; cycles per tile: MMA-lane total {d[6]/tiles:.0f} = wait acc_empty {d[3]/tiles:.0f} + wait a_full {d[4]/tiles:.0f} "
+          f"+ wait b_full {d[5]/tiles:.0f} + issue/other {(d[6]-d[3]-d[4]-d[5])/tiles:.0f} | producer total {d[1]/tiles:.0f}, blocked on a_empty {d[0]/tiles:.0f} "
+          f"| weight warp blocked on b_empty {d[2]/tiles:.0f} | epilogue blocked on acc_full {d[7]/tiles:.0f}")

@@ -31,6 +31,11 @@ namespace b200np {
 
 using namespace umma;
 
+// Diagnostic hook (tools/halo_stalls.py): when set, every CTA writes the cycles its MMA lane, producers and
+// epilogue spent blocked on each barrier.  nullptr in normal operation.
+static long long* g_halo_dbg = nullptr;
+extern "C" void b200np_debug_set_halo_timing(long long* buf) { g_halo_dbg = buf; }
+
 namespace {
 
 constexpr int kTileRows = 16, kTileCols = 8;
@@ -56,6 +61,7 @@ struct HaloArgs {
   // whatever the two halo stages leave -- its depth is what hides the L2 latency of the bulk copies
   uint32_t halo_bytes, stage_bytes, b_off, bar_off;
   int nb;                       // weight ring depth
+  long long* dbg;               // optional [gridDim.x][8] stall-cycle counters
 };
 
 constexpr uint32_t kSmemBudget = 227 * 1024;
@@ -73,6 +79,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc, bool timed) {
+  if (!timed) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 
 struct Ring {
@@ -132,6 +145,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
     // rounded up to 8, so the skip tile starts 1024-aligned and the plain K-major layout "row m at m*128,
     // chunk c at c ^ (m & 7)" coincides with the halo's absolute-address swizzle: ONE store formula).
     Ring st;
+    long long dbg_a = 0;
+    const long long dbg_t0 = clock64();
     const int c = tid & 7, s0 = tid >> 3;
     const int step_y = kSlotsPerPass / h.HC, step_x = kSlotsPerPass - step_y * h.HC;
     const int hy0 = s0 / h.HC, hx0 = s0 - hy0 * h.HC;
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           hx += step_x;
           if (hx >= h.HC) { hx -= h.HC; ++hy; }
         }
-        mbar_wait(a_empty + st.idx, st.phase ^ 1);
+        mbar_wait_timed(a_empty + st.idx, st.phase ^ 1, dbg_a, h.dbg != nullptr);
         uint8_t* plane_hi = smem + st.idx * h.stage_bytes;
         uint8_t* plane_lo = plane_hi + plane;
         slot = s0;
@@ -180,22 +195,25 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
         st.advance(kAStages);
       }
     }
+    if (h.dbg && tid == 0) { h.dbg[blockIdx.x * 8 + 0] = dbg_a; h.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
   } else if (warp == kWeightWarp) {
     // ===================== weight producer =====================
     if (lane == 0) {
       Ring bs;
+      long long dbg_b = 0;
       for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
         for (int half = 0; half < 2; ++half) {
           for (int t = 0; t < ntaps; ++t) {
             const Tap tp = a.taps[t];
             const float* src = h.bp[tp.src] + ((long long)half * h.nslabs[tp.src] + tp.slab) * (kBSlotBytes / 4);
-            mbar_wait(b_empty + bs.idx, bs.phase ^ 1);
+            mbar_wait_timed(b_empty + bs.idx, bs.phase ^ 1, dbg_b, h.dbg != nullptr);
             mbar_expect_tx(b_full + bs.idx, kBSlot);
             bulk_g2s(smem + h.b_off + bs.idx * kBSlot, src, kBSlot, b_full + bs.idx);
             bs.advance(nb);
           }
         }
       }
+      if (h.dbg) h.dbg[blockIdx.x * 8 + 2] = dbg_b;
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
@@ -203,14 +221,17 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       Ring st, bs;
       int acc_set = 0;
       uint32_t acc_phase = 0;
+      long long w_acc = 0, w_a = 0, w_b = 0;
+      const bool timed = h.dbg != nullptr;
+      const long long t_start = clock64();
       const uint32_t sbo_halo = (uint32_t)h.HC * 128u;
       for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
-        mbar_wait(acc_empty + acc_set, acc_phase ^ 1);   // epilogue has drained this accumulator set
+        mbar_wait_timed(acc_empty + acc_set, acc_phase ^ 1, w_acc, timed);   // epilogue has drained this set
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc_set * kAccCols;
         int kb = 0;                                      // K-block counter of this tile (hi accumulator rotation)
         for (int half = 0; half < 2; ++half) {
-          mbar_wait(a_full + st.idx, st.phase);
+          mbar_wait_timed(a_full + st.idx, st.phase, w_a, timed);
           tc_fence_after();
           uint8_t* stage = smem + st.idx * h.stage_bytes;
           const uint32_t plane = h.halo_bytes + (h.has_skip ? kSkipBytes : 0u);
@@ -218,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           const uint32_t skip_hi = halo_hi + h.halo_bytes, skip_lo = skip_hi + plane;
           for (int t = 0; t < ntaps; ++t, ++kb) {
             const Tap tp = a.taps[t];
-            mbar_wait(b_full + bs.idx, bs.phase);
+            mbar_wait_timed(b_full + bs.idx, bs.phase, w_b, timed);
             tc_fence_after();
             uint32_t ah_addr, al_addr, sbo;
             if (tp.src == 0) {
@@ -254,6 +275,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
         umma_commit(acc_full + acc_set);
         if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
       }
+      if (timed) {
+        long long* o = h.dbg + blockIdx.x * 8;
+        o[3] = w_acc; o[4] = w_a; o[5] = w_b; o[6] = clock64() - t_start;
+      }
     }
   } else {
     // ===================== epilogue =====================
@@ -261,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
     const int m = q * 32 + lane;                         // accumulator row = output pixel of the tile
     int acc_set = 0;
     uint32_t acc_phase = 0;
+    long long w_e = 0;
     const int kb_total = 2 * ntaps;
     const int hi_used = kb_total < AccCfg<X3>::kHi ? kb_total : AccCfg<X3>::kHi;
     for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
@@ -269,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       const int n = r0 / a.OH, oy = r0 - n * a.OH + (m >> 3), ox = xt * kTileCols + (m & 7);
       const long long off =
           (((long long)n * a.dstH + (long long)oy * a.dst_s + a.dst_oy) * a.dstW + (long long)ox * a.dst_s + a.dst_ox) * 64;
-      mbar_wait(acc_full + acc_set, acc_phase);
+      mbar_wait_timed(acc_full + acc_set, acc_phase, w_e, h.dbg != nullptr);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_set * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
@@ -305,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       }
       if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
     }
+    if (h.dbg && warp == kEpiWarp0 && lane == 0) h.dbg[blockIdx.x * 8 + 7] = w_e;
   }
 
   tc_fence_before();
@@ -353,6 +380,7 @@ int launch_tapconv_halo(const TapConvArgs& a, const float* bp0, int nslabs0, con
   if (a.ntaps < 4) return B200NP_E_UNSUPPORTED;
   HaloArgs h{};
   h.t = a;
+  h.dbg = g_halo_dbg;
   h.bp[0] = bp0; h.bp[1] = bp1; h.nslabs[0] = nslabs0; h.nslabs[1] = nslabs1;
   int dy_min = 127, dy_max = -127, dx_min = 127, dx_max = -127, n0 = 0, n1 = 0;
   for (int t = 0; t < a.ntaps; ++t) {
