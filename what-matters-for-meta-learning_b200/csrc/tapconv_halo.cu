@@ -217,6 +217,19 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
+    // One lane issues every tcgen05.mma of the CTA, so this loop's instruction count IS the kernel's critical
+    // path (measured: 21 k of 25 k cycles per tile were spent here, not waiting).  Everything that does not
+    // change per tile is precomputed: per-tap descriptor words live in a small shared table, descriptors are
+    // assembled from 32-bit halves, the k-step is an immediate add on the low word.
+    uint32_t* tap_tab = tmem_slot + 4;                    // [ntaps][2]: {A offset >> 4 (bit 31: skip tile), desc high word}
+    if (lane < ntaps) {
+      const Tap tp = a.taps[lane];
+      const uint32_t sbo = tp.src == 0 ? (uint32_t)h.HC * 128u : 1024u;
+      const uint32_t off = tp.src == 0 ? (uint32_t)((tp.dy - h.dy_min) * h.HC + (tp.dx - h.dx_min)) * 8u : 0x80000000u;
+      tap_tab[lane * 2 + 0] = off;
+      tap_tab[lane * 2 + 1] = (sbo >> 4) | (1u << 14) | (2u << 29);   // SBO, descriptor version 1, SWIZZLE_128B
+    }
+    __syncwarp();
     if (lane == 0) {
       Ring st, bs;
       int acc_set = 0;
@@ -224,50 +237,55 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       long long w_acc = 0, w_a = 0, w_b = 0;
       const bool timed = h.dbg != nullptr;
       const long long t_start = clock64();
-      const uint32_t sbo_halo = (uint32_t)h.HC * 128u;
+      const uint32_t plane16 = (h.halo_bytes + (h.has_skip ? kSkipBytes : 0u)) >> 4;
+      const uint32_t skip16 = h.halo_bytes >> 4;
+      const uint32_t lbo_bits = 1u << 16;                 // LBO field (ignored for swizzled K-major; 1 by convention)
+      const uint32_t b_hi_word = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t b_base16 = (smem_u32(smem + h.b_off) & 0x3FFFFu) >> 4;
+      auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t acc) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi_word), "r"(kIdescTf32_128x64), "r"(acc)
+            : "memory");
+      };
       for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
         mbar_wait_timed(acc_empty + acc_set, acc_phase ^ 1, w_acc, timed);   // epilogue has drained this set
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc_set * kAccCols;
-        int kb = 0;                                      // K-block counter of this tile (hi accumulator rotation)
+        const uint32_t d_lo = d0 + AccCfg<X3>::kHi * 64;
+        uint32_t rot = 0;                                 // hi accumulator rotation (kb % kHi without a division)
+        bool first_lo = true;
+        int kb = 0;
         for (int half = 0; half < 2; ++half) {
           mbar_wait_timed(a_full + st.idx, st.phase, w_a, timed);
           tc_fence_after();
-          uint8_t* stage = smem + st.idx * h.stage_bytes;
-          const uint32_t plane = h.halo_bytes + (h.has_skip ? kSkipBytes : 0u);
-          const uint32_t halo_hi = smem_u32(stage), halo_lo = halo_hi + plane;
-          const uint32_t skip_hi = halo_hi + h.halo_bytes, skip_lo = skip_hi + plane;
+          const uint32_t stage16 = (smem_u32(smem + st.idx * h.stage_bytes) & 0x3FFFFu) >> 4;
           for (int t = 0; t < ntaps; ++t, ++kb) {
-            const Tap tp = a.taps[t];
+            const uint32_t off = tap_tab[t * 2], a_hi_word = tap_tab[t * 2 + 1];
+            const uint32_t a16 = stage16 + ((off & 0x80000000u) ? skip16 : off);
+            const uint32_t ah = a16 | lbo_bits, al = (a16 + plane16) | lbo_bits;
+            const uint32_t b16 = b_base16 + bs.idx * (kBSlot >> 4);
+            const uint32_t bh = b16 | lbo_bits, bl = (b16 + (kBBytes >> 4)) | lbo_bits;
             mbar_wait_timed(b_full + bs.idx, bs.phase, w_b, timed);
             tc_fence_after();
-            uint32_t ah_addr, al_addr, sbo;
-            if (tp.src == 0) {
-              const uint32_t off = (uint32_t)((tp.dy - h.dy_min) * h.HC + (tp.dx - h.dx_min)) * 128u;
-              ah_addr = halo_hi + off; al_addr = halo_lo + off; sbo = sbo_halo;
-            } else {
-              ah_addr = skip_hi; al_addr = skip_lo; sbo = 1024u;
-            }
-            const uint32_t b_addr = smem_u32(smem + h.b_off + bs.idx * kBSlot);
-            // descriptors: same bit layout as make_kmajor_sw128_desc, with a per-operand SBO
-            const uint64_t hi_bits = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
-                                     (static_cast<uint64_t>(1) << 16);
-            const uint64_t ah = hi_bits | ((uint64_t)(sbo >> 4) << 32) | ((ah_addr & 0x3FFFFu) >> 4);
-            const uint64_t al = hi_bits | ((uint64_t)(sbo >> 4) << 32) | ((al_addr & 0x3FFFFu) >> 4);
-            const uint64_t bh = make_kmajor_sw128_desc(b_addr), bl = make_kmajor_sw128_desc(b_addr + kBBytes);
-            const uint32_t d_hi = d0 + (kb % AccCfg<X3>::kHi) * 64;
+            const uint32_t d_hi = d0 + rot * 64;
+            const uint32_t acc_first = kb >= AccCfg<X3>::kHi;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_tf32(d_hi, ah + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb >= AccCfg<X3>::kHi) | (k != 0));
+            for (int k = 0; k < 4; ++k) mma(d_hi, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u);
             if (X3) {
-              const uint32_t d_lo = d0 + AccCfg<X3>::kHi * 64;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k) mma(d_lo, al + 2 * k, a_hi_word, bh + 2 * k, (k == 0 && first_lo) ? 0u : 1u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + 2 * k, bl + 2 * k, kIdescTf32_128x64, 1u);
+              for (int k = 0; k < 4; ++k) mma(d_lo, ah + 2 * k, a_hi_word, bl + 2 * k, 1u);
+              first_lo = false;
             }
             umma_commit(b_empty + bs.idx);
             bs.advance(nb);
+            if (++rot == AccCfg<X3>::kHi) rot = 0;
           }
           umma_commit(a_empty + st.idx);
           st.advance(kAStages);
@@ -348,7 +366,7 @@ int launch_halo(HaloArgs& h, cudaStream_t st) {
   h.halo_bytes = ((uint32_t)(h.HR * h.HC) * 128u + 1023u) & ~1023u;
   h.stage_bytes = planes * (h.halo_bytes + (h.has_skip ? kSkipBytes : 0u));
   h.b_off = kAStages * h.stage_bytes;
-  const uint32_t tail = 1024 /*alignment slack*/ + 256 /*barriers*/;
+  const uint32_t tail = 1024 /*alignment slack*/ + 512 /*barriers + tap table*/;
   int nb = (int)((kSmemBudget - tail - h.b_off) / b_slot_bytes<X3>());
   if (nb > kMaxBStages) nb = kMaxBStages;
   if (nb < 2) return B200NP_E_UNSUPPORTED;
