@@ -34,6 +34,8 @@ using namespace umma;
 // Diagnostic hook (tools/halo_stalls.py): when set, every CTA writes the cycles its MMA lane, producers and
 // epilogue spent blocked on each barrier.  nullptr in normal operation.
 static long long* g_halo_dbg = nullptr;
+static int g_halo_min_taps = 1;
+extern "C" void b200np_debug_set_halo_min_taps(int n) { g_halo_min_taps = n; }
 extern "C" void b200np_debug_set_halo_timing(long long* buf) { g_halo_dbg = buf; }
 
 namespace {
@@ -393,9 +395,9 @@ int launch_tapconv_halo(const TapConvArgs& a, const float* bp0, int nslabs0, con
   if (a.Cin != 64 || a.Cout != 64 || a.ntaps < 1 || a.ntaps > kMaxTaps || !bp0) return B200NP_E_UNSUPPORTED;
   if (a.act != B200NP_ACT_NONE && a.act != B200NP_ACT_RELU) return B200NP_E_UNSUPPORTED;
   if (a.OH % kTileRows != 0 || a.OW % kTileCols != 0 || a.in_s[0] != 1) return B200NP_E_UNSUPPORTED;
-  // A tile costs a fixed halo load + epilogue; with fewer than 4 taps (the sparse parity classes of a
-  // stride-2 data gradient) the gather kernel is faster (measured: 2.7 ms vs 2.4 ms for the 4 classes).
-  if (a.ntaps < 4) return B200NP_E_UNSUPPORTED;
+  // Even the sparse parity classes of a stride-2 data gradient (1-2 taps) are faster here than in the gather
+  // kernel since the producers went to 8 warps (measured 1.39 ms vs 1.96 ms for the 4 classes of layer1).
+  if (a.ntaps < g_halo_min_taps) return B200NP_E_UNSUPPORTED;
   HaloArgs h{};
   h.t = a;
   h.dbg = g_halo_dbg;
