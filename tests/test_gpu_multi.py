@@ -1,0 +1,67 @@
+"""Two-GPU data-parallel parity (needs >= 2 GPUs; run with `gpurun --gpus 2`): sharding the meta-batch by task
+over 2 ranks with the NCCL exchanges of b200np.dist (flat-gradient SUM, FAVOR+ key-max MAX and its gradient
+SUM) reproduces the single-GPU gradient of the whole meta-batch."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as td
+ROOT = sys.argv[1]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "what-matters-for-meta-learning_b200"), os.path.join(ROOT, "tests")]
+from conftest import make_config
+from b200np import dist, engine
+from b200np.optim import FlatParams
+from networks.ANPDistractor import ANPDistractor
+from oracle import synth
+from trainer.losses import LossFunc
+rank = int(os.environ["RANK"]); dev = torch.device(f"cuda:{int(os.environ['LOCAL_RANK'])}")
+torch.cuda.set_device(dev)
+td.init_process_group("nccl", device_id=dev)
+engine.set_precision("tf32x3")
+T, nc, nt, W = 4, 3, 4, td.get_world_size()
+batch = [torch.from_numpy(a).to(dev) for a in synth.task_batch("distractor", T, nc, nt, seed=5)]
+lossf = LossFunc("mse", "distractor")
+def grads(model, b):
+    flat = FlatParams(model); flat.zero_grad()
+    mu, _, _ = model(b[0], b[1], b[2]); loss = lossf.calc_loss(mu, None, b[3]); loss.backward(); flat.gather_grads()
+    return flat, float(loss.detach())
+# sharded
+cfg = make_config("ANPDistractor", "distractor", T // W, "attention", "max", device=str(dev), dim_w=16)
+lo, hi = dist.shard_tasks(T)
+flat, loss_local = grads(ANPDistractor(cfg).to(dev), [t[lo:hi].contiguous() for t in batch])
+dist.all_reduce_grads(flat.grad); g_sharded = flat.grad / W
+lt = torch.tensor([loss_local], device=dev); td.all_reduce(lt); loss_sharded = float(lt) / W
+# whole batch on one GPU, no process group in the way of the collectives: world size 1 semantics via a fresh group
+td.barrier()
+if rank == 0:
+    saved = dist.world_size
+    dist.world_size = lambda: 1   # full-batch reference: no cross-rank exchange
+    cfg1 = make_config("ANPDistractor", "distractor", T, "attention", "max", device=str(dev), dim_w=16)
+    flat1, loss_full = grads(ANPDistractor(cfg1).to(dev), batch)
+    dist.world_size = saved
+    err = float((g_sharded - flat1.grad).norm() / flat1.grad.norm())
+    print(f"RESULT loss_sharded={loss_sharded:.7f} loss_full={loss_full:.7f} grad_rel_err={err:.3e}", flush=True)
+    assert abs(loss_sharded - loss_full) < 1e-5 * abs(loss_full)
+    assert err < 1e-4, err
+td.barrier()
+td.destroy_process_group()
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_gradient_equals_full_batch(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29641", str(script), ROOT]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "RESULT" in out.stdout
+    print(out.stdout[out.stdout.index("RESULT"):].splitlines()[0])
