@@ -224,11 +224,24 @@ def run_b200_arm(args, rank, world, local_rank):
         e2e_step(0)
         ms_e2e = timed(e2e_step, e2e_steps)
 
-    roof = dominant_kernel_roofline(args, dev) if (rank == 0 and not args.profile) else None
-    if rank != 0:
+    def finish():
+        """Common exit: a captured graph holds NCCL kernels, so drop it before the communicator; every rank
+        leaves through the same barrier; multi-rank processes then exit without interpreter teardown (an
+        orderly NCCL shutdown after graph capture was observed to stall for minutes)."""
+        nonlocal run
+        if args.graph:
+            run = None
+        torch.cuda.synchronize()
         if world > 1:
-            td.destroy_process_group()
+            td.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
+    roof = dominant_kernel_roofline(args, dev) if not args.profile else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline and not args.profile:
         sample = 2
@@ -254,8 +267,7 @@ def run_b200_arm(args, rank, world, local_rank):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        td.destroy_process_group()
+    finish()
 
 
 def dominant_kernel_roofline(args, dev):

@@ -99,10 +99,13 @@ int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, const float* 
 
 size_t b200np_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int stride);
 /* dw [Cout,Cin,R,R] (torch layout) = sum over pixels of dy (x) im2col(x);  db [Cout] = sum dy
- * (db may be NULL).  x [N,H,W,Cin], dy [N,H/stride,W/stride,Cout]. */
+ * (db may be NULL).  x [N,H,W,Cin], dy [N,H/stride,W/stride,Cout].
+ * Optional fused skip projection (64x64 layers): xs [N,OH*stride_s,OW*stride_s,64] is the input of the
+ * 1x1 stride_s conv that was added to this conv's output, dws [64,64] receives its weight gradient
+ * (it sees the same dy); pass xs = dws = NULL to disable. */
 int b200np_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W,
-                      int Cin, int Cout, int R, int stride, int precision, void* ws, size_t ws_bytes,
-                      void* stream);
+                      int Cin, int Cout, int R, int stride, const float* xs, float* dws, int stride_s,
+                      int precision, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pooling / flatten at the end of the CNN (networks/models.py:105-113, networks/ResNet.py:151-152)

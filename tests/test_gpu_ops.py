@@ -92,16 +92,19 @@ def test_conv_block_ops(prec, cin, cout, hw, n):
         y.backward(gy)
         dz = (gy * (y > 0)).detach()        # gradient at the pre-activation of the block output
         dzg = nhwc(dz)
-        dw2, db2 = ops.conv_wgrad(hgx, dzg, 3, 1, P)
-        dws, _ = ops.conv_wgrad(xg, dzg, 1, 2, P, want_db=False)
+        dw2, db2, _ = ops.conv_wgrad(hgx, dzg, 3, 1, P)
+        dws, _, _ = ops.conv_wgrad(xg, dzg, 1, 2, P, want_db=False)
         assert rel(dw2, w2.grad) < tol and rel(db2, b2.grad) < 1e-5 and rel(dws, ws.grad) < tol
+        if prec != "fp32":   # fused: the skip projection's gradient as an extra tap of conv2's weight gradient
+            dw2f, db2f, dwsf = ops.conv_wgrad(hgx, dzg, 3, 1, P, skip=(xg, 2))
+            assert rel(dw2f, w2.grad) < tol and rel(db2f, b2.grad) < 1e-5 and rel(dwsf, ws.grad) < tol
         dh = ops.conv_dgrad(dzg, p2, hgx.shape, 1, P, mask_src=hgx)
         # reference dh: gradient at conv1's pre-activation
         hh = h.detach().requires_grad_()
         F.conv2d(hh, w2.detach(), None, padding=1).backward(dz)
         dh_ref = hh.grad * (h > 0)
         assert rel(from_nhwc(dh), dh_ref) < tol
-        dw1, db1 = ops.conv_wgrad(xg, dh, 3, 2, P)
+        dw1, db1, _ = ops.conv_wgrad(xg, dh, 3, 2, P)
         assert rel(dw1, w1.grad) < tol and rel(db1, b1.grad) < max(tol, 2e-5)
         dx = ops.conv_dgrad(dh, p1, xg.shape, 2, P, mask_src=xg, skip=(dzg, ps, 2))
         assert rel(from_nhwc(dx), x.grad * (x > 0)) < tol
@@ -109,7 +112,7 @@ def test_conv_block_ops(prec, cin, cout, hw, n):
         gy = rnd(*h.shape, seed=8)
         h.backward(gy)
         dz = nhwc((gy * (h > 0)).detach())
-        dw1, db1 = ops.conv_wgrad(xg, dz, 3, 2, P)
+        dw1, db1, _ = ops.conv_wgrad(xg, dz, 3, 2, P)
         assert rel(dw1, w1.grad) < tol and rel(db1, b1.grad) < max(tol, 2e-5)
         dx = ops.conv_dgrad(dz, p1, xg.shape, 2, P, mask_src=None)
         assert rel(from_nhwc(dx), x.grad) < tol

@@ -80,10 +80,10 @@ def convops_diag():
     wd2 = ops.pack_conv_weight(w2.detach().float().cuda())
     wds = ops.pack_conv_weight(ws.detach().float().cuda())
     for name, prec in (("fp32-simt", 0), ("tf32x3", 1), ("tf32", 2)):
-        dw2, _ = ops.conv_wgrad(hg, dzg, 3, 1, prec)
-        dws, _ = ops.conv_wgrad(xg, dzg, 1, 2, prec, want_db=False)
+        dw2, _, _ = ops.conv_wgrad(hg, dzg, 3, 1, prec)
+        dws, _, _ = ops.conv_wgrad(xg, dzg, 1, 2, prec, want_db=False)
         dh = ops.conv_dgrad(dzg, wd2, hg.shape, 1, prec, mask_src=hg)
-        dw1, _ = ops.conv_wgrad(xg, nh(dh_ref), 3, 2, prec)
+        dw1, _, _ = ops.conv_wgrad(xg, nh(dh_ref), 3, 2, prec)
         dx = ops.conv_dgrad(nh(dh_ref), wd1, xg.shape, 2, prec, mask_src=xg, skip=(dzg, wds, 2))
         P(f"stage bwd {name:10s} dgrad_s1 {rel(dh.permute(0, 3, 1, 2), dh_ref):.2e} dgrad_s2+skip {rel(dx.permute(0, 3, 1, 2), x.grad):.2e} "
           f"wgrad3x3s1 {rel(dw2, w2.grad):.2e} wgrad3x3s2 {rel(dw1, w1.grad):.2e} wgrad1x1s2 {rel(dws, ws.grad):.2e}")

@@ -60,6 +60,6 @@ if what in ("all", "stem"):
     timed("stem 5x5 s2 wgrad", lambda: ops.conv_small_wgrad(img, dy0, wst.shape), 2.0 * N * 4096 * 64 * 25)
 if what in ("all", "wgrad"):
     # accuracy of the long pixel contraction at full size: tensor-core modes against the CUDA-core fp32 kernel
-    ref, _ = ops.conv_wgrad(h, dz, 3, 1, 0)
-    got, _ = ops.conv_wgrad(h, dz, 3, 1, prec)
+    ref, _, _ = ops.conv_wgrad(h, dz, 3, 1, 0)
+    got, _, _ = ops.conv_wgrad(h, dz, 3, 1, prec)
     print(f"wgrad 3x3 s1 full size: rel-L2 vs fp32 CUDA-core kernel = {float((got - ref).norm() / ref.norm()):.3e}", flush=True)

@@ -97,10 +97,13 @@ class TrunkFn(Function):
         for l in (3, 2, 1, 0):
             x, h, _ = ctx.acts[l]
             p1, p2, ps = ctx.packs[l]
-            dw2, db2 = ops.conv_wgrad(h, dy, 3, 1, prec)
-            dws, _ = ops.conv_wgrad(x, dy, 1, 2, prec, want_db=False)
+            if prec == PREC_FP32_SIMT:
+                dw2, db2, _ = ops.conv_wgrad(h, dy, 3, 1, prec)
+                dws, _, _ = ops.conv_wgrad(x, dy, 1, 2, prec, want_db=False)
+            else:  # the skip projection's weight gradient rides along as a 10th tap of conv2's
+                dw2, db2, dws = ops.conv_wgrad(h, dy, 3, 1, prec, skip=(x, 2))
             dh = ops.conv_dgrad(dy, p2, h.shape, 1, prec, mask_src=h)
-            dw1, db1 = ops.conv_wgrad(x, dh, 3, 2, prec)
+            dw1, db1, _ = ops.conv_wgrad(x, dh, 3, 2, prec)
             dx = ops.conv_dgrad(dh, p1, x.shape, 2, prec, mask_src=x, skip=(dy, ps, 2))
             grads[2 + 6 * l: 8 + 6 * l] = [dw1, db1, dw2, db2, dws, db2.clone()]
             dy = dx
@@ -155,10 +158,10 @@ class EncoderW0Fn(Function):
         for n, do in zip(Ns, douts):
             ops.nchw_flat_to_nhwc(do.contiguous(), x4[off:off + n], d4[off:off + n])
             off += n
-        dw5, db5 = ops.conv_wgrad(x3, d4, 3, 2, prec)
+        dw5, db5, _ = ops.conv_wgrad(x3, d4, 3, 2, prec)
         d3 = ops.conv_dgrad(d4, wd5, x3.shape, 2, prec, mask_src=None)
         d2 = ops.maxpool2x2_bwd(d3, pidx, x2)
-        dw2, db2 = ops.conv_wgrad(x1, d2, 3, 2, prec)
+        dw2, db2, _ = ops.conv_wgrad(x1, d2, 3, 2, prec)
         d1 = ops.conv_dgrad(d2, wd2, x1.shape, 2, prec, mask_src=x1)
         off, dw0, db0 = 0, None, None
         for im, n in zip(ctx.imgs, Ns):

@@ -37,7 +37,7 @@ SIGNATURES = {
     "b200np_conv_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "b200np_conv_dgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
     "b200np_conv_wgrad_workspace": (_sz, [_i] * 7),
-    "b200np_conv_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "b200np_conv_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _sz, _p]),
     "b200np_adaptive_maxpool2x2_flatten_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "b200np_adaptive_maxpool2x2_flatten_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "b200np_nhwc_to_nchw_flat": (_i, [_p, _p, _i, _i, _i, _i, _p]),

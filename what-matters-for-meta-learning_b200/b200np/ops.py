@@ -118,7 +118,9 @@ def conv_dgrad(dy, pw, x_shape, stride, prec, mask_src=None, skip=None):
     return dx
 
 
-def conv_wgrad(x, dy, R, stride, prec, want_db=True):
+def conv_wgrad(x, dy, R, stride, prec, want_db=True, skip=None):
+    """-> (dw [Cout,Cin,R,R], db [Cout] | None, dws [64,64,1,1] | None).  skip = (xs, stride_s) also returns the
+    weight gradient of the 1x1 projection of xs that was fused into this conv's output."""
     _chk(x, "x"), _chk(dy, "dy")
     N, H, W, Cin = x.shape
     Cout = dy.shape[3]
@@ -126,9 +128,15 @@ def conv_wgrad(x, dy, R, stride, prec, want_db=True):
     ws = torch.empty(max(ws_bytes // 4, 1), device=x.device, dtype=F32)
     dw = empty((Cout, Cin, R, R), x)
     db = empty((Cout,), x) if want_db else None
-    check(LIB.b200np_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), N, H, W, Cin, Cout, R, stride, prec,
-                                _ptr(ws), ws_bytes, _stream()), "conv_wgrad")
-    return dw, db
+    xs = dws = None
+    ss = 1
+    if skip is not None:
+        xs, ss = skip
+        _chk(xs, "xs")
+        dws = empty((Cout, xs.shape[3], 1, 1), x)
+    check(LIB.b200np_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), N, H, W, Cin, Cout, R, stride, _ptr(xs),
+                                _ptr(dws), ss, prec, _ptr(ws), ws_bytes, _stream()), "conv_wgrad")
+    return dw, db, dws
 
 
 # ----------------------------------------------------------------------------------------------

@@ -61,7 +61,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 // out[map(j)] = sum_{p < nparts} part[p * n + j], j < n.  Deterministic (fixed order), coalesced, 8 partial
 // lanes per output.  map: 0 = identity; 1 = weight-gradient permutation (t, co, ci) -> (co, ci, t) with
-// a = ntaps, b = Cout, c = Cin;  2 = small-conv partials [co][KGp] -> dw[co][KK] / db[co] (a = KK, b = KGp).
+// a = ntaps, b = Cout, c = Cin (an extra tap index a, if present, goes to out2[co][ci]);  2 = small-conv partials [co][KGp] -> dw[co][KK] / db[co] (a = KK, b = KGp).
 struct ReduceMap { int kind, a, b, c; float* out2; };
 int launch_reduce_partials(const float* part, float* out, int nparts, int n, ReduceMap map, cudaStream_t st);
 

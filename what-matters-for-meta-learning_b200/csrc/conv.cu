@@ -171,15 +171,17 @@ extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, co
 extern "C" size_t b200np_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int stride) {
   if (N <= 0 || stride <= 0) return 0;
   long long M = (long long)N * (H / stride) * (W / stride);
-  int nt = R * R;
+  int nt = R * R + 1;  // room for a fused skip-projection tap
   int chunks = wgrad_chunks(M, nt);
   size_t part = (size_t)chunks * nt * Cout * Cin * sizeof(float);
   return part + b200np_colsum_workspace(M, Cout);
 }
 
 extern "C" int b200np_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int Cin,
-                                 int Cout, int R, int stride, int precision, void* ws, size_t ws_bytes, void* stream) {
+                                 int Cout, int R, int stride, const float* xs, float* dws, int stride_s,
+                                 int precision, void* ws, size_t ws_bytes, void* stream) {
   if (!x || !dy || !dw || N <= 0 || H <= 0 || W <= 0) return B200NP_E_BADARG;
+  if (xs && (!dws || Cin != 64 || Cout != 64 || stride_s < 1 || !aligned16(xs))) return B200NP_E_UNSUPPORTED;
   if ((R != 1 && R != 3) || (stride != 1 && stride != 2) || H % stride || W % stride) return B200NP_E_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(dy) || !aligned16(ws)) return B200NP_E_BADARG;
   if (!ws || ws_bytes < b200np_conv_wgrad_workspace(N, H, W, Cin, Cout, R, stride)) return B200NP_E_WORKSPACE;
@@ -191,6 +193,10 @@ extern "C" int b200np_conv_wgrad(const float* x, const float* dy, float* dw, flo
   int nt = 0;
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < R; ++s) a.taps[nt++] = Tap{0, (int8_t)(r - pad), (int8_t)(s - pad), (int8_t)(r * R + s)};
+  if (xs) {  // the skip projection sees the same dy: one more tap on a second source
+    a.src2 = xs; a.src2H = a.OH * stride_s; a.src2W = a.OW * stride_s; a.in_s2 = stride_s;
+    a.taps[nt++] = Tap{1, 0, 0, (int8_t)(R * R)};
+  }
   a.ntaps = nt;
   const long long M = (long long)N * a.OH * a.OW;
   a.chunks = wgrad_chunks(M, nt);
@@ -201,7 +207,7 @@ extern "C" int b200np_conv_wgrad(const float* x, const float* dy, float* dw, flo
   if (rc == B200NP_E_UNSUPPORTED) rc = launch_tapwgrad_simt(a, st);
   if (rc != B200NP_OK) return rc;
   int per = nt * Cout * Cin;
-  rc = launch_reduce_partials(a.part, dw, a.chunks, per, ReduceMap{1, nt, Cout, Cin, nullptr}, st);
+  rc = launch_reduce_partials(a.part, dw, a.chunks, per, ReduceMap{1, R * R, Cout, Cin, dws}, st);
   if (rc != B200NP_OK) return rc;
   if (db) {
     size_t part_bytes = (size_t)a.chunks * per * sizeof(float);

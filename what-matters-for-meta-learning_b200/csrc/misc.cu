@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     } else if (map.kind == 1) {
       const int ci = j % map.c, r = j / map.c;
       const int co = r % map.b, tp = r / map.b;
-      out[((long long)co * map.c + ci) * map.a + tp] = t;
+      if (tp < map.a) out[((long long)co * map.c + ci) * map.a + tp] = t;
+      else map.out2[(long long)co * map.c + ci] = t;   // fused 1x1 skip projection: [Cout][Cin]
     } else {
       const int co = j / map.b, k = j - co * map.b;
       if (k < map.a) out[co * map.a + k] = t;

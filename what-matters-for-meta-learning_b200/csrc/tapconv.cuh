@@ -46,6 +46,8 @@ struct TapConvArgs {
 struct TapWgradArgs {
   const float* src;    // [N, srcH, srcW, Cin]
   int srcH, srcW, in_s, Cin;
+  const float* src2;   // optional second source for taps with src == 1 (fused skip projection), 64 channels
+  int src2H, src2W, in_s2;
   const float* dy;     // [N, OH, OW, Cout]
   int N, OH, OW, Cout;
   int ntaps;

@@ -174,9 +174,10 @@ __global__ void __launch_bounds__(128) tapwgrad_simt_kernel(const TapWgradArgs a
           const long long q = p / a.OW;
           const int oy = (int)(q % a.OH);
           const long long n = q / a.OH;
-          const int iy = oy * a.in_s + tp.dy, ix = ox * a.in_s + tp.dx;
-          if (iy >= 0 && iy < a.srcH && ix >= 0 && ix < a.srcW)
-            bv[h] = ldg4(a.src + ((n * a.srcH + iy) * a.srcW + ix) * a.Cin + c4);
+          const float* sp = tp.src ? a.src2 : a.src;
+          const int sH = tp.src ? a.src2H : a.srcH, sW = tp.src ? a.src2W : a.srcW, ss = tp.src ? a.in_s2 : a.in_s;
+          const int iy = oy * ss + tp.dy, ix = ox * ss + tp.dx;
+          if (iy >= 0 && iy < sH && ix >= 0 && ix < sW) bv[h] = ldg4(sp + ((n * sH + iy) * sW + ix) * a.Cin + c4);
         }
       }
     }

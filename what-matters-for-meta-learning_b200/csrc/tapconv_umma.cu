@@ -268,40 +268,51 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
   const int b_k = tid >> 2, b_half = (tid >> 1) & 1, b_sub = tid & 1;
 
   const long long KB = p_begin < p_end ? ((p_end - p_begin + kWgK - 1) / kWgK) : 0;
+  // source of this thread's tap (the fused skip projection reads a second tensor at its own stride)
+  const float* a_src = tp.src ? a.src2 : a.src;
+  const int a_H = tp.src ? a.src2H : a.srcH, a_W = tp.src ? a.src2W : a.srcW, a_s = tp.src ? a.in_s2 : a.in_s;
+  // fetches run over consecutive K-blocks: walk (n, oy, ox) of this thread's pixel incrementally
+  // (two 64-bit divisions per K-block were a large share of the producers' instructions)
+  long long f_p = p_begin + a_k, f_n;
+  int f_ox, f_oy;
+  {
+    f_ox = (int)(f_p % a.OW);
+    const long long q = f_p / a.OW;
+    f_oy = (int)(q % a.OH);
+    f_n = q / a.OH;
+  }
+  long long f_pb = p_begin + b_k;
   float4 av0[8], bv0[4], av1[8], bv1[4];
-  auto fetch = [&](long long kb, float4 (&av)[8], float4 (&bv)[4]) {
-    const long long p0 = p_begin + kb * kWgK;
+  auto fetch = [&](long long, float4 (&av)[8], float4 (&bv)[4]) {
     {
-      const long long p = p0 + a_k;
-      bool ok = a_tap_ok && p < p_end;
-      const float* ap = nullptr;
+      bool ok = a_tap_ok && f_p < p_end;
+      const int iy = f_oy * a_s + tp.dy, ix = f_ox * a_s + tp.dx;
+      ok = ok && iy >= 0 && iy < a_H && ix >= 0 && ix < a_W;
       if (ok) {
-        const int ox = (int)(p % a.OW);
-        const long long q = p / a.OW;
-        const int oy = (int)(q % a.OH);
-        const long long n = q / a.OH;
-        const int iy = oy * a.in_s + tp.dy, ix = ox * a.in_s + tp.dx;
-        ok = iy >= 0 && iy < a.srcH && ix >= 0 && ix < a.srcW;
-        ap = a.src + ((n * a.srcH + iy) * a.srcW + ix) * 64 + a_half * 32;
-      }
-      if (ok) {
+        const float* ap = a_src + ((f_n * a_H + iy) * a_W + ix) * 64 + a_half * 32;
 #pragma unroll
         for (int c = 0; c < 8; ++c) av[c] = ldg4(ap + 4 * c);
       } else {
 #pragma unroll
         for (int c = 0; c < 8; ++c) av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      f_p += kWgK;
+      f_ox += kWgK;
+      while (f_ox >= a.OW) {
+        f_ox -= a.OW;
+        if (++f_oy == a.OH) { f_oy = 0; ++f_n; }
+      }
     }
     {
-      const long long p = p0 + b_k;
-      if (p < p_end) {
-        const float* bp = a.dy + p * 64 + b_half * 32 + b_sub * 16;
+      if (f_pb < p_end) {
+        const float* bp = a.dy + f_pb * 64 + b_half * 32 + b_sub * 16;
 #pragma unroll
         for (int c = 0; c < 4; ++c) bv[c] = ldg4(bp + 4 * c);
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) bv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      f_pb += kWgK;
     }
   };
 
