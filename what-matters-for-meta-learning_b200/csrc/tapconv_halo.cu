@@ -45,6 +45,7 @@ constexpr int kMaxHaloSlots = 184;                       // 18 x 10 = 180, round
 constexpr uint32_t kHaloBytes = kMaxHaloSlots * 128;     // 23,552 B (multiple of 1024)
 constexpr uint32_t kSkipBytes = 128 * 128;               // 16 KB
 constexpr int kAStages = 2, kMaxBStages = 10;
+constexpr int kRot = 2;   // rotating accumulator blocks per accumulator set
 constexpr uint32_t kBSlotBytes = 2 * kBBytes;            // hi + lo = 16 KB
 constexpr int kProducerWarps = 8, kProducerThreads = 32 * kProducerWarps;
 constexpr int kWeightWarp = kProducerWarps, kMmaWarp = kProducerWarps + 1, kEpiWarp0 = kProducerWarps + 2;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
 
   const TapConvArgs& a = h.t;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t kAccCols = AccCfg<X3>::kCols;      // columns per accumulator set
+  constexpr uint32_t kAccCols = X3 ? 256u : 128u;       // columns per accumulator set: kRot blocks of 128 | 64
   constexpr uint32_t kTmemCols = 2 * kAccCols;
 
   if (tid == 0) {
@@ -244,23 +245,27 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       const uint32_t lbo_bits = 1u << 16;                 // LBO field (ignored for swizzled K-major; 1 by convention)
       const uint32_t b_hi_word = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t b_base16 = (smem_u32(smem + h.b_off) & 0x3FFFFu) >> 4;
-      auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t acc) {
+      // fp32-grade mode: the weight slot holds [B_hi (64 rows) ; B_lo (64 rows)] contiguously, i.e. one 128-row
+      // K-major operand.  A_hi x [B_hi;B_lo] as ONE N=128 MMA yields hi*hi (columns 0-63) and hi*lo (64-127)
+      // for 64 cycles instead of 2 x 54.5 (N=64 MMAs are shared-memory-bandwidth bound: tools/probe), then
+      // A_lo x B_hi (N=64) adds the other cross term into columns 64-127.  Blocks of 128 columns rotate
+      // (kRot = 2) to bound the truncating accumulator's bias; the epilogue sums all column groups.
+      constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t acc, uint32_t idesc) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
             "mov.b64 da, {%1, %2};\n\t"
             "mov.b64 db, {%3, %4};\n\t"
             "setp.ne.b32 p, %6, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
-            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi_word), "r"(kIdescTf32_128x64), "r"(acc)
+            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi_word), "r"(idesc), "r"(acc)
             : "memory");
       };
       for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
         mbar_wait_timed(acc_empty + acc_set, acc_phase ^ 1, w_acc, timed);   // epilogue has drained this set
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc_set * kAccCols;
-        const uint32_t d_lo = d0 + AccCfg<X3>::kHi * 64;
-        uint32_t rot = 0;                                 // hi accumulator rotation (kb % kHi without a division)
-        bool first_lo = true;
+        uint32_t rot = 0;                                 // accumulator block rotation (kb % kRot without a division)
         int kb = 0;
         for (int half = 0; half < 2; ++half) {
           mbar_wait_timed(a_full + st.idx, st.phase, w_a, timed);
@@ -271,23 +276,23 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             const uint32_t a16 = stage16 + ((off & 0x80000000u) ? skip16 : off);
             const uint32_t ah = a16 | lbo_bits, al = (a16 + plane16) | lbo_bits;
             const uint32_t b16 = b_base16 + bs.idx * (kBSlot >> 4);
-            const uint32_t bh = b16 | lbo_bits, bl = (b16 + (kBBytes >> 4)) | lbo_bits;
+            const uint32_t bh = b16 | lbo_bits;
             mbar_wait_timed(b_full + bs.idx, bs.phase, w_b, timed);
             tc_fence_after();
-            const uint32_t d_hi = d0 + rot * 64;
-            const uint32_t acc_first = kb >= AccCfg<X3>::kHi;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma(d_hi, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u);
+            const uint32_t d_blk = d0 + rot * (X3 ? 128u : 64u);
+            const uint32_t acc_first = kb >= kRot;
             if (X3) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) mma(d_lo, al + 2 * k, a_hi_word, bh + 2 * k, (k == 0 && first_lo) ? 0u : 1u);
+              for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescN128);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) mma(d_lo, ah + 2 * k, a_hi_word, bl + 2 * k, 1u);
-              first_lo = false;
+              for (int k = 0; k < 4; ++k) mma(d_blk + 64, al + 2 * k, a_hi_word, bh + 2 * k, 1u, kIdescTf32_128x64);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescTf32_128x64);
             }
             umma_commit(b_empty + bs.idx);
             bs.advance(nb);
-            if (++rot == AccCfg<X3>::kHi) rot = 0;
+            if (++rot == kRot) rot = 0;
           }
           umma_commit(a_empty + st.idx);
           st.advance(kAStages);
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
     uint32_t acc_phase = 0;
     long long w_e = 0;
     const int kb_total = 2 * ntaps;
-    const int hi_used = kb_total < AccCfg<X3>::kHi ? kb_total : AccCfg<X3>::kHi;
+    const int blocks_used = kb_total < kRot ? kb_total : kRot;
     for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
       const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
       const int r0 = rb * kTileRows;
@@ -321,7 +326,27 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float acc[32];
-        gather_acc<X3>(taddr, hf * 32, hi_used, acc);
+        {   // sum the rotating blocks (and, fp32-grade, their cross-term column group), smallest terms first
+          uint32_t r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+          if (X3) {
+#pragma unroll
+            for (int b = 0; b < kRot; ++b)
+              if (b < blocks_used) {
+                tmem_ld32(taddr + b * 128 + 64 + hf * 32, r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+              }
+          }
+#pragma unroll
+          for (int b = 0; b < kRot; ++b)
+            if (b < blocks_used) {
+              tmem_ld32(taddr + b * (X3 ? 128 : 64) + hf * 32, r);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+            }
+        }
         if (hf == 1) {                                   // all TMEM reads of this set are done
           tc_fence_before();
           mbar_arrive(acc_empty + acc_set);
