@@ -229,3 +229,27 @@ def test_cuda_graph_step_equals_eager():
     assert finals[0][0] == pytest.approx(finals[1][0], rel=1e-6)
     for k in finals[0][1]:
         assert torch.allclose(finals[0][1][k], finals[1][1][k], rtol=1e-5, atol=1e-7), k
+
+
+def test_evaluation_shapes_and_degree_loss():
+    """evaluation.py path: no-grad forward with the eval split sizes -- 25 context images and all
+    36 views as targets (dataset/shapenet_distractor.py:289-291) -- plus ShapeNet1D's test-time degree error
+    (trainer/losses.py:63-76) through the drop-in LossFunc, against the CPU oracle."""
+    from b200np import engine
+    from trainer.losses import LossFunc
+    engine.set_precision("tf32x3")
+    for case, nc, nt in (("anp_distractor", 25, 36), ("anp_1d", 25, 30)):
+        method, task, agg, img_agg, extra, T, _, _ = CASES[case]
+        model, cfg = build_product_model(case, device="cuda")
+        model = model.to("cuda").eval()
+        batch = synth.task_batch(task, T, nc, nt, seed=3)
+        cx, cy, tx, ty = (torch.from_numpy(a).cuda() for a in batch)
+        with torch.no_grad():
+            mu, var, kl = model(cx, cy, tx, test=True)
+            loss = LossFunc("mse", task).calc_loss(mu, None, ty, test=True)
+        tr = np_oracle.OracleTrainer(method, oracle_cfg(cfg), {k: v.cpu() for k, v in model.state_dict().items()})
+        with torch.no_grad():
+            mu_o = np_oracle.FORWARD[method](tr.sd, tr.cfg, *(torch.from_numpy(a) for a in batch[:3]))
+            loss_o = np_oracle.calc_loss(task, mu_o, torch.from_numpy(batch[3]), test=True)
+        assert rel_l2(mu.cpu().numpy(), mu_o.numpy()) < 1e-3, case
+        assert abs(float(loss) - float(loss_o)) < 1e-3 * abs(float(loss_o)), (case, float(loss), float(loss_o))
