@@ -1,29 +1,38 @@
-// Halo-tile tcgen05 implementation of the tap convolution for unit-input-stride stencils
-// (forward 3x3 s1 [+ fused 1x1 s2 skip projection], data gradient of a 3x3 s1 conv, and the four
-// parity classes of a stride-2 data gradient [+ skip gradient]).
+// Halo-tile tcgen05 implementation of the tap convolution: forward 3x3 s1 (+ fused 1x1 s2 skip
+// projection), forward 3x3 s2, data gradient of a 3x3 s1 conv, and the four parity classes of a
+// stride-2 data gradient (+ skip gradient).
 //
-// Why: the gather kernel (tapconv_umma.cu) re-reads and re-splits every input pixel once per tap
-// (9x) and is bound by the latency of those loads (ncu: long_scoreboard, tensor pipe 14 %).  Here an
-// output tile is 16 rows x 8 pixels of one image; its input HALO ((16+dy_span) x (8+dx_span) pixels) is
-// loaded, split into tf32 hi/lo and stored in shared memory ONCE per 32-channel half, in the K-major
-// SWIZZLE_128B layout with one 128-byte "slot" per halo pixel.  A tap is then nothing but a
-// descriptor: start = slot(dy,dx), 8 consecutive slots = 8 consecutive output pixels, stride between
-// the 16 row groups (SBO) = halo pitch * 128 B.  (The tensor core applies the 128B swizzle to absolute
-// shared-memory address bits, so start addresses at any 128-byte slot and any SBO are legal as long as
-// the data is stored with the same absolute-address swizzle -- verified on B200 by tools/probe.)
+// Why: the gather kernel (tapconv_umma.cu) re-reads and re-splits every input pixel once per tap (9x) and
+// is bound by the latency of those loads (ncu: long_scoreboard, tensor pipe 14 %).  Here an output tile is
+// 16 rows x 8 pixels of one image; the input pixels it needs are loaded, split into tf32 hi/lo and stored
+// in shared memory ONCE per 32-channel half, as one or more PLANES in the K-major SWIZZLE_128B layout with
+// one 128-byte "slot" per pixel:
+//   * a plane is a dense (16+dy_span) x (8+dx_span) window of one source tensor sampled at stride `scale`
+//     with phase (py, px).  Stride-1 stencils need one plane (the halo).  A stride-2 forward conv needs the
+//     four parity planes x[2i+py, 2j+px]: in each of them consecutive OUTPUT pixels are consecutive slots.
+//     The fused skip projection / skip gradient is one more plane (16 x 8, no halo).
+//   * a tap is then nothing but a descriptor: start = slot(plane, dy, dx), 8 consecutive slots = 8
+//     consecutive output pixels, stride between the 16 row groups (SBO) = plane pitch * 128 B.
+//     (The tensor core applies the 128B swizzle to absolute shared-memory address bits, so start addresses
+//     at any 128-byte slot and any SBO are legal as long as the data is stored with the same
+//     absolute-address swizzle -- verified on B200 by tools/probe.)
 //
 // Weights arrive pre-split (hi/lo) and pre-swizzled from b200np_pack_conv_weight, one 16 KB K-block
-// (tap, channel half) per cp.async.bulk into a 3-deep ring.
+// (tap, channel half) per cp.async.bulk into a ring that takes whatever shared memory the stages leave.
 //
 // Persistent, warp-specialised CTA (one per SM), tiles round-robin:
-//   warps 0-7   halo producers (gather + split + store), 2 stages of one channel half each; eight warps
-//               because the producers are instruction-issue bound (ncu: 1 warp per scheduler stalled on
-//               fixed-latency dependencies), not memory bound
+//   warps 0-7   plane producers (gather + split + store), one stage = one channel half of one tile; eight
+//               warps because the producers are instruction-issue bound, not memory bound (ncu)
 //   warp  8     weight producer (one lane issues bulk copies); also owns the TMEM allocation
 //   warp  9     MMA issuer (one lane)
 //   warps 10-13 epilogue (TMEM -> registers -> bias / ReLU mask / activation -> NHWC global)
-// Two accumulator sets in TMEM (2 x 256 columns in the fp32-grade mode) let the epilogue of tile i
-// overlap the MMAs of tile i+1.
+// Two accumulator sets in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// fp32-grade mode: N = 64 tf32 MMAs are shared-memory-bandwidth bound (54.5 cycles instead of 32,
+// tools/probe/probe_mma_rate.cu), so the weight slot [B_hi ; B_lo] is used as ONE 128-row operand:
+// A_hi x [B_hi;B_lo] (N = 128, 64 cycles) yields hi*hi (columns 0-63) and hi*lo (64-127), then A_lo x B_hi
+// (N = 64) adds the other cross term into columns 64-127.  Accumulator blocks of 128 columns rotate (kRot)
+// to bound the bias of the tensor core's truncating fp32 accumulation; the epilogue sums them.
 #include "tapconv.cuh"
 #include "umma.cuh"
 
@@ -31,8 +40,7 @@ namespace b200np {
 
 using namespace umma;
 
-// Diagnostic hook (tools/halo_stalls.py): when set, every CTA writes the cycles its MMA lane, producers and
-// epilogue spent blocked on each barrier.  nullptr in normal operation.
+// Diagnostic hooks (tools/halo_stalls.py): per-role blocked-cycle counters; nullptr in normal operation.
 static long long* g_halo_dbg = nullptr;
 static int g_halo_min_taps = 1;
 extern "C" void b200np_debug_set_halo_min_taps(int n) { g_halo_min_taps = n; }
@@ -41,33 +49,40 @@ extern "C" void b200np_debug_set_halo_timing(long long* buf) { g_halo_dbg = buf;
 namespace {
 
 constexpr int kTileRows = 16, kTileCols = 8;
-constexpr int kMaxHaloSlots = 184;                       // 18 x 10 = 180, rounded up to a multiple of 8
-constexpr uint32_t kHaloBytes = kMaxHaloSlots * 128;     // 23,552 B (multiple of 1024)
-constexpr uint32_t kSkipBytes = 128 * 128;               // 16 KB
-constexpr int kAStages = 2, kMaxBStages = 10;
-constexpr int kRot = 2;   // rotating accumulator blocks per accumulator set
+constexpr int kMaxPlanes = 5;
+constexpr int kMaxBStages = 10;
+constexpr int kRot = 2;                                  // rotating accumulator blocks per accumulator set
 constexpr uint32_t kBSlotBytes = 2 * kBBytes;            // hi + lo = 16 KB
 constexpr int kProducerWarps = 8, kProducerThreads = 32 * kProducerWarps;
 constexpr int kWeightWarp = kProducerWarps, kMmaWarp = kProducerWarps + 1, kEpiWarp0 = kProducerWarps + 2;
 constexpr int kThreads = 32 * (kProducerWarps + 2 + 4);
-constexpr int kSlotsPerPass = kProducerThreads / 8;                       // slots covered by one pass of the producers
-constexpr int kMaxTasks = (kMaxHaloSlots + 128 + kSlotsPerPass - 1) / kSlotsPerPass;  // chunk tasks per producer thread
+constexpr int kSlotsPerPass = kProducerThreads / 8;      // slots covered by one pass of the producers
+constexpr uint32_t kSmemBudget = 227 * 1024;
 
-struct HaloArgs {
-  TapConvArgs t;
-  const float* bp[2];   // pre-split, pre-swizzled weights per source: [half][slab][hi 8 KB | lo 8 KB]
-  int nslabs[2];
-  int dy_min, dx_min, HR, HC;   // halo geometry (src 0)
-  int has_skip;                 // one extra tap on src 1 at offset (0,0)
-  int tiles_x, tiles_total;
-  // shared-memory plan (bytes from the 1024-aligned base), sized per launch: the weight ring takes
-  // whatever the two halo stages leave -- its depth is what hides the L2 latency of the bulk copies
-  uint32_t halo_bytes, stage_bytes, b_off, bar_off;
-  int nb;                       // weight ring depth
-  long long* dbg;               // optional [gridDim.x][8] stall-cycle counters
+struct Plane {
+  const float* src;     // NHWC tensor [N, srcH, srcW, 64]
+  int srcH, srcW;
+  int scale, py, px;    // source pixel = ((oy0 + dy_min + hy) * scale + py, (ox0 + dx_min + hx) * scale + px)
+  int dy_min, dx_min, HR, HC;
+  int slot0, nslots;    // slots [slot0, slot0 + nslots) of the stage; both multiples of 8
 };
 
-constexpr uint32_t kSmemBudget = 227 * 1024;
+struct HaloArgs {
+  TapConvArgs t;        // epilogue fields, tap list (src / slab), output geometry
+  const float* bp[2];   // pre-split, pre-swizzled weights per source: [half][slab][hi 8 KB | lo 8 KB]
+  int nslabs[2];
+  int nplanes;
+  Plane pl[kMaxPlanes];
+  int tap_off[kMaxTaps];   // first slot of the tap's window inside the stage
+  int tap_hc[kMaxTaps];    // pitch (slots per plane row) of the tap's plane
+  int total_slots;         // per stage plane
+  int a_stages;            // 1 or 2 plane stages
+  int tiles_x, tiles_total;
+  uint32_t plane_bytes, stage_bytes, b_off, bar_off;
+  int nb;                  // weight ring depth
+  long long* dbg;          // optional [gridDim.x][8] stall-cycle counters
+};
+
 template <bool X3>
 constexpr uint32_t b_slot_bytes() { return X3 ? kBSlotBytes : kBBytes; }
 
@@ -83,7 +98,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-
 __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc, bool timed) {
   if (!timed) { mbar_wait(bar, parity); return; }
   const long long t0 = clock64();
@@ -99,20 +113,22 @@ struct Ring {
   }
 };
 
-template <bool X3>
+// MAXT = 16-byte chunk tasks per producer thread and stage (ceil(total_slots / 32))
+template <bool X3, int MAXT>
 __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArgs h) {
   constexpr uint32_t kBSlot = b_slot_bytes<X3>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + h.bar_off);
-  uint64_t* a_full = bars;                  // [kAStages] producers -> MMA            (count 128)
-  uint64_t* a_empty = bars + 2;             // [kAStages] MMA commit -> producers     (count 1)
+  uint64_t* a_full = bars;                  // [a_stages] producers -> MMA            (count 256)
+  uint64_t* a_empty = bars + 2;             // [a_stages] MMA commit -> producers     (count 1)
   uint64_t* acc_full = bars + 4;            // [2] MMA commit -> epilogue             (count 1)
   uint64_t* acc_empty = bars + 6;           // [2] epilogue -> MMA                    (count 128)
   uint64_t* b_full = bars + 8;              // [nb] bulk copy tx -> MMA               (count 1 + tx)
   uint64_t* b_empty = b_full + kMaxBStages; // [nb] MMA commit -> weight warp         (count 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMaxBStages);
-  const int nb = h.nb;
+  uint32_t* tap_tab = tmem_slot + 4;        // [ntaps][2]: {window start >> 4, descriptor high word}
+  const int nb = h.nb, a_stages = h.a_stages;
 
   const TapConvArgs& a = h.t;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -120,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
   constexpr uint32_t kTmemCols = 2 * kAccCols;
 
   if (tid == 0) {
-    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full + s, kProducerThreads); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < a_stages; ++s) { mbar_init(a_full + s, kProducerThreads); mbar_init(a_empty + s, 1); }
     for (int s = 0; s < nb; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,67 +151,61 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  const int hslots = h.HR * h.HC;
   const int ntaps = a.ntaps;
 
   if (warp < kProducerWarps) {
-    // ===================== halo producers =====================
-    // Thread = fixed 16-byte chunk c of slots s0, s0+16, s0+32, ...  The (row, column) of those slots
-    // advances by a constant (16 / HC, 16 % HC) step, so no division appears in the per-tile loop (with
-    // one producer warp per scheduler, address arithmetic was the producers' critical path).
-    // Slot space of a stage plane: [0, hslots) halo pixels, [hpad, hpad + 128) the skip tile (hpad = hslots
-    // rounded up to 8, so the skip tile starts 1024-aligned and the plain K-major layout "row m at m*128,
-    // chunk c at c ^ (m & 7)" coincides with the halo's absolute-address swizzle: ONE store formula).
+    // ===================== plane producers =====================
+    // Thread = fixed 16-byte chunk c of slots s0, s0+32, s0+64, ...  Which plane / row / column each of
+    // those slots is does not depend on the tile: it is decoded once into `meta` (no division in the loop;
+    // with one or two producer warps per scheduler, address arithmetic is the producers' critical path).
     Ring st;
     long long dbg_a = 0;
     const long long dbg_t0 = clock64();
     const int c = tid & 7, s0 = tid >> 3;
-    const int step_y = kSlotsPerPass / h.HC, step_x = kSlotsPerPass - step_y * h.HC;
-    const int hy0 = s0 / h.HC, hx0 = s0 - hy0 * h.HC;
-    const int hpad = (hslots + 7) & ~7;
-    const int nslots = h.has_skip ? hpad + 128 : hslots;
-    const long long row_pitch = (long long)a.srcW[0] * 64;
-    const uint32_t plane = h.halo_bytes + (h.has_skip ? kSkipBytes : 0u);
+    int meta[MAXT];                                      // (plane << 16) | (hy << 8) | hx, or -1: zero-fill slot
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i) {
+      const int slot = s0 + i * kSlotsPerPass;
+      meta[i] = -1;
+      for (int p = 0; p < h.nplanes; ++p) {
+        const int local = slot - h.pl[p].slot0;
+        if (local >= 0 && local < h.pl[p].nslots) {
+          const int hy = local / h.pl[p].HC, hx = local - hy * h.pl[p].HC;
+          if (hy < h.pl[p].HR) meta[i] = (p << 16) | (hy << 8) | hx;
+        }
+      }
+    }
     for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
       const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
       const int r0 = rb * kTileRows;
       const int n = r0 / a.OH, oy0 = r0 - n * a.OH, ox0 = xt * kTileCols;
-      const int iy_base = oy0 + h.dy_min, ix_base = ox0 + h.dx_min;
       for (int half = 0; half < 2; ++half) {
-        const float* base0 = a.src[0] + ((long long)n * a.srcH[0] * a.srcW[0]) * 64 + half * 32 + c * 4;
-        const float* base1 = h.has_skip ? a.src[1] + ((long long)n * a.srcH[1] * a.srcW[1]) * 64 + half * 32 + c * 4
-                                        : nullptr;
-        float4 v[kMaxTasks];
-        int slot = s0, hy = hy0, hx = hx0;
+        const int coff = half * 32 + c * 4;
+        float4 v[MAXT];
 #pragma unroll
-        for (int i = 0; i < kMaxTasks; ++i) {
+        for (int i = 0; i < MAXT; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (slot < hslots) {
-            const int iy = iy_base + hy, ix = ix_base + hx;
-            if (iy >= 0 && iy < a.srcH[0] && ix >= 0 && ix < a.srcW[0]) v[i] = ldg4(base0 + iy * row_pitch + ix * 64);
-          } else if (slot >= hpad && slot < nslots) {
-            const int m = slot - hpad;                   // output pixel (row group m>>3, column m&7)
-            const int iy = (oy0 + (m >> 3)) * a.in_s[1], ix = (ox0 + (m & 7)) * a.in_s[1];
-            v[i] = ldg4(base1 + ((long long)iy * a.srcW[1] + ix) * 64);
+          const int mt = meta[i];
+          if (mt >= 0) {
+            const Plane& P = h.pl[mt >> 16];
+            const int iy = (oy0 + P.dy_min + ((mt >> 8) & 0xff)) * P.scale + P.py;
+            const int ix = (ox0 + P.dx_min + (mt & 0xff)) * P.scale + P.px;
+            if (iy >= 0 && iy < P.srcH && ix >= 0 && ix < P.srcW)
+              v[i] = ldg4(P.src + (((long long)n * P.srcH + iy) * P.srcW + ix) * 64 + coff);
           }
-          slot += kSlotsPerPass;
-          hy += step_y;
-          hx += step_x;
-          if (hx >= h.HC) { hx -= h.HC; ++hy; }
         }
         mbar_wait_timed(a_empty + st.idx, st.phase ^ 1, dbg_a, h.dbg != nullptr);
         uint8_t* plane_hi = smem + st.idx * h.stage_bytes;
-        uint8_t* plane_lo = plane_hi + plane;
-        slot = s0;
+        uint8_t* plane_lo = plane_hi + h.plane_bytes;
 #pragma unroll
-        for (int i = 0; i < kMaxTasks; ++i) {
-          if (slot < nslots) split_store(plane_hi, plane_lo, (uint32_t)(slot * 128 + ((c ^ (slot & 7)) << 4)), v[i], X3);
-          slot += kSlotsPerPass;
+        for (int i = 0; i < MAXT; ++i) {
+          const int slot = s0 + i * kSlotsPerPass;
+          // stage bases are 1024-aligned, so the absolute-address swizzle phase of a slot is slot & 7
+          if (slot < h.total_slots) split_store(plane_hi, plane_lo, (uint32_t)(slot * 128 + ((c ^ (slot & 7)) << 4)), v[i], X3);
         }
         fence_proxy_async();
         mbar_arrive(a_full + st.idx);
-        st.advance(kAStages);
+        st.advance(a_stages);
       }
     }
     if (h.dbg && tid == 0) { h.dbg[blockIdx.x * 8 + 0] = dbg_a; h.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
@@ -220,17 +230,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    // One lane issues every tcgen05.mma of the CTA, so this loop's instruction count IS the kernel's critical
-    // path (measured: 21 k of 25 k cycles per tile were spent here, not waiting).  Everything that does not
-    // change per tile is precomputed: per-tap descriptor words live in a small shared table, descriptors are
-    // assembled from 32-bit halves, the k-step is an immediate add on the low word.
-    uint32_t* tap_tab = tmem_slot + 4;                    // [ntaps][2]: {A offset >> 4 (bit 31: skip tile), desc high word}
+    // One lane issues every tcgen05.mma of the CTA.  Everything that does not change per tile is
+    // precomputed: per-tap descriptor words live in a small shared table, descriptors are assembled from
+    // 32-bit halves, the k-step is an immediate add on the low word.
     if (lane < ntaps) {
-      const Tap tp = a.taps[lane];
-      const uint32_t sbo = tp.src == 0 ? (uint32_t)h.HC * 128u : 1024u;
-      const uint32_t off = tp.src == 0 ? (uint32_t)((tp.dy - h.dy_min) * h.HC + (tp.dx - h.dx_min)) * 8u : 0x80000000u;
-      tap_tab[lane * 2 + 0] = off;
-      tap_tab[lane * 2 + 1] = (sbo >> 4) | (1u << 14) | (2u << 29);   // SBO, descriptor version 1, SWIZZLE_128B
+      tap_tab[lane * 2 + 0] = (uint32_t)h.tap_off[lane] * 8u;                           // slots -> 16-byte units
+      tap_tab[lane * 2 + 1] = (((uint32_t)h.tap_hc[lane] * 128u) >> 4) | (1u << 14) | (2u << 29);  // SBO, v1, SW128
     }
     __syncwarp();
     if (lane == 0) {
@@ -240,16 +245,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       long long w_acc = 0, w_a = 0, w_b = 0;
       const bool timed = h.dbg != nullptr;
       const long long t_start = clock64();
-      const uint32_t plane16 = (h.halo_bytes + (h.has_skip ? kSkipBytes : 0u)) >> 4;
-      const uint32_t skip16 = h.halo_bytes >> 4;
+      const uint32_t plane16 = h.plane_bytes >> 4;
       const uint32_t lbo_bits = 1u << 16;                 // LBO field (ignored for swizzled K-major; 1 by convention)
       const uint32_t b_hi_word = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t b_base16 = (smem_u32(smem + h.b_off) & 0x3FFFFu) >> 4;
-      // fp32-grade mode: the weight slot holds [B_hi (64 rows) ; B_lo (64 rows)] contiguously, i.e. one 128-row
-      // K-major operand.  A_hi x [B_hi;B_lo] as ONE N=128 MMA yields hi*hi (columns 0-63) and hi*lo (64-127)
-      // for 64 cycles instead of 2 x 54.5 (N=64 MMAs are shared-memory-bandwidth bound: tools/probe), then
-      // A_lo x B_hi (N=64) adds the other cross term into columns 64-127.  Blocks of 128 columns rotate
-      // (kRot = 2) to bound the truncating accumulator's bias; the epilogue sums all column groups.
       constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t acc, uint32_t idesc) {
         asm volatile(
@@ -272,11 +271,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           tc_fence_after();
           const uint32_t stage16 = (smem_u32(smem + st.idx * h.stage_bytes) & 0x3FFFFu) >> 4;
           for (int t = 0; t < ntaps; ++t, ++kb) {
-            const uint32_t off = tap_tab[t * 2], a_hi_word = tap_tab[t * 2 + 1];
-            const uint32_t a16 = stage16 + ((off & 0x80000000u) ? skip16 : off);
+            const uint32_t a16 = stage16 + tap_tab[t * 2], a_hi_word = tap_tab[t * 2 + 1];
             const uint32_t ah = a16 | lbo_bits, al = (a16 + plane16) | lbo_bits;
-            const uint32_t b16 = b_base16 + bs.idx * (kBSlot >> 4);
-            const uint32_t bh = b16 | lbo_bits;
+            const uint32_t bh = (b_base16 + bs.idx * (kBSlot >> 4)) | lbo_bits;
             mbar_wait_timed(b_full + bs.idx, bs.phase, w_b, timed);
             tc_fence_after();
             const uint32_t d_blk = d0 + rot * (X3 ? 128u : 64u);
@@ -295,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             if (++rot == kRot) rot = 0;
           }
           umma_commit(a_empty + st.idx);
-          st.advance(kAStages);
+          st.advance(a_stages);
         }
         umma_commit(acc_full + acc_set);
         if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
@@ -386,30 +383,40 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
   }
 }
 
-template <bool X3>
-int launch_halo(HaloArgs& h, cudaStream_t st) {
-  // plan shared memory: two halo stages (+ skip tiles when fused), then as deep a weight ring as fits
-  const uint32_t planes = X3 ? 2u : 1u;
-  h.halo_bytes = ((uint32_t)(h.HR * h.HC) * 128u + 1023u) & ~1023u;
-  h.stage_bytes = planes * (h.halo_bytes + (h.has_skip ? kSkipBytes : 0u));
-  h.b_off = kAStages * h.stage_bytes;
-  const uint32_t tail = 1024 /*alignment slack*/ + 512 /*barriers + tap table*/;
-  int nb = (int)((kSmemBudget - tail - h.b_off) / b_slot_bytes<X3>());
-  if (nb > kMaxBStages) nb = kMaxBStages;
-  if (nb < 2) return B200NP_E_UNSUPPORTED;
-  h.nb = nb;
-  h.bar_off = h.b_off + nb * b_slot_bytes<X3>();
-  const size_t smem = h.bar_off + tail;
+template <bool X3, int MAXT>
+int launch_halo_t(const HaloArgs& h, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
-    if (cudaFuncSetAttribute(tapconv_halo_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+    if (cudaFuncSetAttribute(tapconv_halo_kernel<X3, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
       return B200NP_E_LAUNCH;
     configured = smem;
   }
   int grid = h.tiles_total < kNumSMs ? h.tiles_total : kNumSMs;
-  tapconv_halo_kernel<X3><<<grid, kThreads, smem, st>>>(h);
+  tapconv_halo_kernel<X3, MAXT><<<grid, kThreads, smem, st>>>(h);
   return launch_status();
+}
+
+template <bool X3>
+int launch_halo(HaloArgs& h, cudaStream_t st) {
+  // shared-memory plan: one or two plane stages, then as deep a weight ring as fits (>= 2 slots)
+  const uint32_t planes = X3 ? 2u : 1u;
+  h.plane_bytes = (uint32_t)h.total_slots * 128u;
+  h.stage_bytes = planes * h.plane_bytes;
+  const uint32_t tail = 1024 /*alignment slack*/ + 512 /*barriers + tap table*/;
+  const uint32_t bslot = b_slot_bytes<X3>();
+  h.a_stages = (2 * h.stage_bytes + 2 * bslot + tail <= kSmemBudget) ? 2 : 1;
+  if (h.a_stages * h.stage_bytes + 2 * bslot + tail > kSmemBudget) return B200NP_E_UNSUPPORTED;
+  h.b_off = h.a_stages * h.stage_bytes;
+  int nb = (int)((kSmemBudget - tail - h.b_off) / bslot);
+  if (nb > kMaxBStages) nb = kMaxBStages;
+  h.nb = nb;
+  h.bar_off = h.b_off + nb * bslot;
+  const size_t smem = h.bar_off + tail;
+  const int tasks = (h.total_slots + kSlotsPerPass - 1) / kSlotsPerPass;
+  if (tasks <= 10) return launch_halo_t<X3, 10>(h, smem, st);
+  if (tasks <= 18) return launch_halo_t<X3, 18>(h, smem, st);
+  return B200NP_E_UNSUPPORTED;
 }
 
 }  // namespace
@@ -419,31 +426,60 @@ int launch_tapconv_halo(const TapConvArgs& a, const float* bp0, int nslabs0, con
                         int precision, cudaStream_t st) {
   if (a.Cin != 64 || a.Cout != 64 || a.ntaps < 1 || a.ntaps > kMaxTaps || !bp0) return B200NP_E_UNSUPPORTED;
   if (a.act != B200NP_ACT_NONE && a.act != B200NP_ACT_RELU) return B200NP_E_UNSUPPORTED;
-  if (a.OH % kTileRows != 0 || a.OW % kTileCols != 0 || a.in_s[0] != 1) return B200NP_E_UNSUPPORTED;
-  // Even the sparse parity classes of a stride-2 data gradient (1-2 taps) are faster here than in the gather
-  // kernel since the producers went to 8 warps (measured 1.39 ms vs 1.96 ms for the 4 classes of layer1).
+  if (a.OH % kTileRows != 0 || a.OW % kTileCols != 0) return B200NP_E_UNSUPPORTED;
+  if (a.in_s[0] != 1 && a.in_s[0] != 2) return B200NP_E_UNSUPPORTED;
   if (a.ntaps < g_halo_min_taps) return B200NP_E_UNSUPPORTED;
   HaloArgs h{};
   h.t = a;
   h.dbg = g_halo_dbg;
   h.bp[0] = bp0; h.bp[1] = bp1; h.nslabs[0] = nslabs0; h.nslabs[1] = nslabs1;
-  int dy_min = 127, dy_max = -127, dx_min = 127, dx_max = -127, n0 = 0, n1 = 0;
+  // group the taps into planes: (source, row parity, column parity) for a stride-2 source, one plane otherwise
+  struct Key { int src, py, px; } keys[kMaxPlanes];
+  int lo_y[kMaxPlanes], hi_y[kMaxPlanes], lo_x[kMaxPlanes], hi_x[kMaxPlanes];
+  int tap_plane[kMaxTaps], tap_dy[kMaxTaps], tap_dx[kMaxTaps];
+  int np = 0;
   for (int t = 0; t < a.ntaps; ++t) {
     const Tap& tp = a.taps[t];
-    if (tp.src == 0) {
-      ++n0;
-      dy_min = tp.dy < dy_min ? tp.dy : dy_min; dy_max = tp.dy > dy_max ? tp.dy : dy_max;
-      dx_min = tp.dx < dx_min ? tp.dx : dx_min; dx_max = tp.dx > dx_max ? tp.dx : dx_max;
-    } else {
-      ++n1;
+    int py = 0, px = 0, dy = tp.dy, dx = tp.dx;
+    if (tp.src == 1) {
       if (tp.dy != 0 || tp.dx != 0 || !bp1) return B200NP_E_UNSUPPORTED;
+    } else if (a.in_s[0] == 2) {
+      py = tp.dy & 1; px = tp.dx & 1;          // x[2o + d] = plane(d & 1)[o + (d - (d & 1)) / 2]
+      dy = (tp.dy - py) / 2; dx = (tp.dx - px) / 2;
     }
+    int p = 0;
+    for (; p < np; ++p)
+      if (keys[p].src == tp.src && keys[p].py == py && keys[p].px == px) break;
+    if (p == np) {
+      if (np == kMaxPlanes) return B200NP_E_UNSUPPORTED;
+      keys[np] = Key{tp.src, py, px};
+      lo_y[np] = hi_y[np] = dy; lo_x[np] = hi_x[np] = dx;
+      ++np;
+    } else {
+      lo_y[p] = dy < lo_y[p] ? dy : lo_y[p]; hi_y[p] = dy > hi_y[p] ? dy : hi_y[p];
+      lo_x[p] = dx < lo_x[p] ? dx : lo_x[p]; hi_x[p] = dx > hi_x[p] ? dx : hi_x[p];
+    }
+    tap_plane[t] = p; tap_dy[t] = dy; tap_dx[t] = dx;
   }
-  if (n0 < 1 || n1 > 1) return B200NP_E_UNSUPPORTED;
-  h.dy_min = dy_min; h.dx_min = dx_min;
-  h.HR = kTileRows + dy_max - dy_min; h.HC = kTileCols + dx_max - dx_min;
-  if (h.HR * h.HC > kMaxHaloSlots) return B200NP_E_UNSUPPORTED;
-  h.has_skip = n1;
+  int slot = 0;
+  for (int p = 0; p < np; ++p) {
+    Plane& P = h.pl[p];
+    const int s = keys[p].src;
+    P.src = a.src[s]; P.srcH = a.srcH[s]; P.srcW = a.srcW[s];
+    P.scale = a.in_s[s]; P.py = keys[p].py; P.px = keys[p].px;
+    P.dy_min = lo_y[p]; P.dx_min = lo_x[p];
+    P.HR = kTileRows + hi_y[p] - lo_y[p]; P.HC = kTileCols + hi_x[p] - lo_x[p];
+    if (P.HR > 255 || P.HC > 255) return B200NP_E_UNSUPPORTED;
+    P.slot0 = slot; P.nslots = (P.HR * P.HC + 7) & ~7;
+    slot += P.nslots;
+  }
+  h.nplanes = np;
+  h.total_slots = slot;
+  for (int t = 0; t < a.ntaps; ++t) {
+    const Plane& P = h.pl[tap_plane[t]];
+    h.tap_off[t] = P.slot0 + (tap_dy[t] - P.dy_min) * P.HC + (tap_dx[t] - P.dx_min);
+    h.tap_hc[t] = P.HC;
+  }
   h.tiles_x = a.OW / kTileCols;
   const long long tiles = (long long)a.N * a.OH / kTileRows * h.tiles_x;
   if (tiles <= 0) return B200NP_OK;
