@@ -158,7 +158,12 @@ typedef struct b200np_gemm_desc {
   const float* addend;
   long long ld_add;
   int precision;
+  void* workspace;        /* optional split-K scratch (b200np_gemm_workspace bytes); NULL: single pass */
+  size_t workspace_bytes;
 } b200np_gemm_desc;
+/* bytes of scratch with which b200np_gemm spreads the K range of a GEMM with few output tiles over the idle
+ * SMs (deterministic: partial tiles are reduced in a fixed order); 0 when the shape does not profit */
+size_t b200np_gemm_workspace(const b200np_gemm_desc* d);
 int b200np_gemm(const b200np_gemm_desc* d, void* stream);
 
 /* dz = dy * act'(y)  (ReLU: y>0; Tanh: 1-y^2), elementwise over n floats; dz may alias dy */

@@ -20,7 +20,8 @@ class GemmDesc(C.Structure):
     _fields_ = [("A", _p * 8), ("B", _p * 8), ("C", _p * 8), ("bias", _p * 8), ("groups", _i),
                 ("M", _i), ("N", _i), ("K", _i), ("a_rs", _ll), ("a_cs", _ll), ("b_rs", _ll),
                 ("b_cs", _ll), ("ldc", _ll), ("alpha", _f), ("beta", _f), ("act", _i),
-                ("row_scale", _p), ("addend", _p), ("ld_add", _ll), ("precision", _i)]
+                ("row_scale", _p), ("addend", _p), ("ld_add", _ll), ("precision", _i),
+                ("workspace", _p), ("workspace_bytes", _sz)]
 
 
 # name: (restype, [argtypes])  -- one entry per symbol in include/b200np.h
@@ -44,6 +45,7 @@ SIGNATURES = {
     "b200np_nchw_flat_to_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "b200np_maxpool2x2_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "b200np_maxpool2x2_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "b200np_gemm_workspace": (_sz, [C.POINTER(GemmDesc)]),
     "b200np_gemm": (_i, [C.POINTER(GemmDesc), _p]),
     "b200np_act_bwd": (_i, [_p, _p, _p, _ll, _i, _p]),
     "b200np_colsum_workspace": (_sz, [_ll, _i]),

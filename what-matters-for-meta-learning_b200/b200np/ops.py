@@ -215,6 +215,11 @@ def gemm(A, B, Cmat, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, bias=None, alpha=1.0,
     d.row_scale = 0 if row_scale is None else row_scale.data_ptr()
     d.addend = 0 if addend is None else addend.data_ptr()
     d.ld_add, d.precision = ld_add, prec
+    d.workspace, d.workspace_bytes = 0, 0
+    ws_bytes = LIB.b200np_gemm_workspace(C.byref(d))
+    if ws_bytes:  # split-K scratch for the GEMMs with too few output tiles to fill the chip
+        ws = torch.empty(ws_bytes // 4, device="cuda", dtype=F32)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws_bytes
     check(LIB.b200np_gemm(C.byref(d), _stream()), "gemm")
 
 

@@ -10,6 +10,7 @@ using namespace b200np;
 
 namespace b200np {
 int launch_gemm_umma(const b200np_gemm_desc& d, int a_vec, int b_vec, cudaStream_t st);  // gemm_umma.cu
+int gemm_umma_splits(const b200np_gemm_desc& d);
 }
 
 namespace {
@@ -161,6 +162,12 @@ __global__ void __launch_bounds__(128) gemm_kernel(const GemmArgs g) {
 }
 
 }  // namespace
+
+extern "C" size_t b200np_gemm_workspace(const b200np_gemm_desc* dp) {
+  if (!dp || dp->M <= 0 || dp->N <= 0) return 0;
+  const int s = gemm_umma_splits(*dp);
+  return s > 1 ? (size_t)s * dp->M * dp->N * sizeof(float) : 0;
+}
 
 extern "C" int b200np_gemm(const b200np_gemm_desc* dp, void* stream) {
   if (!dp) return B200NP_E_BADARG;

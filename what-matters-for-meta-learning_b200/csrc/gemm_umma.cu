@@ -25,6 +25,7 @@ constexpr uint32_t kGA = 128 * 32 * 4, kGB = 64 * 32 * 4;  // 16 KB, 8 KB per pl
 struct GemmUArgs {
   b200np_gemm_desc d;
   int a_vec, b_vec;  // 16-byte loads legal for A / B (pointer and leading-dimension alignment)
+  int splits;        // split-K: blockIdx.z = group * splits + split; partial tiles are atomically added to C
 };
 
 // MN-major descriptor / offsets (same as the weight-gradient kernel): 32-wide blocks LBO = 4096 B apart,
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
   const b200np_gemm_desc& d = g.d;
-  const int grp = blockIdx.z;
+  const int grp = blockIdx.z / g.splits, sp = blockIdx.z - grp * g.splits;
   const float* __restrict__ A = d.A[grp];
   const float* __restrict__ B = d.B[grp];
   float* __restrict__ C = d.C[grp];
@@ -86,10 +87,14 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  const int KB = (K + 31) / 32;
+  // this CTA's K-block range (split-K: the small dense layers have 16 output tiles for 148 SMs)
+  const int KB_all = (K + 31) / 32;
+  const int kb_per = (KB_all + g.splits - 1) / g.splits;
+  const int kb_lo = sp * kb_per;
+  const int KB = KB_all - kb_lo < kb_per ? (KB_all - kb_lo > 0 ? KB_all - kb_lo : 0) : kb_per;
   float4 av0[8], bv0[4], av1[8], bv1[4];
   auto fetch = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
-    const int k0 = kb * 32;
+    const int k0 = (kb_lo + kb) * 32;
     if (AK) {  // thread = row m0+tid, 32 consecutive k
       const int m = m0 + tid;
       const float* p = A + (long long)m * d.a_rs + k0;
@@ -188,9 +193,13 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
       for (int j = 0; j < 32; ++j) {
         const int n = n0 + half * 32 + j;
         if (n < N) {
+          if (g.splits > 1) {  // raw partial sum; splitk_epilogue_kernel reduces the splits in a fixed order
+            static_cast<float*>(d.workspace)[((long long)sp * M + m) * N + n] = acc[j];
+            continue;
+          }
           float v = d.alpha * acc[j];
-          if (bias) v += __ldg(bias + n);
           float* cp = C + (long long)m * d.ldc + n;
+          if (bias) v += __ldg(bias + n);
           if (d.beta != 0.f) v = fmaf(d.beta, *cp, v);
           if (use_rs) v = fmaf(rs, __ldg(d.addend + (long long)m * d.ld_add + n), v);
           if (d.act == B200NP_ACT_RELU) v = fmaxf(v, 0.f);
@@ -219,12 +228,44 @@ int launch(const GemmUArgs& g, cudaStream_t st) {
       return B200NP_E_LAUNCH;
     configured = true;
   }
-  dim3 grid((g.d.M + 127) / 128, (g.d.N + 63) / 64, g.d.groups);
+  dim3 grid((g.d.M + 127) / 128, (g.d.N + 63) / 64, g.d.groups * g.splits);
   gemm_umma_kernel<X3, AK, BK><<<grid, 128, smem, st>>>(g);
   return launch_status();
 }
 
+// C = act(alpha * sum_s part[s] + bias + beta * C + row_scale * addend): the split-K partial tiles summed in
+// split order (deterministic), then the same epilogue as the single-pass kernel
+__global__ void splitk_epilogue_kernel(const b200np_gemm_desc d, int splits) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long MN = (long long)d.M * d.N;
+  if (i >= MN) return;
+  const int m = (int)(i / d.N), n = (int)(i - (long long)m * d.N);
+  const float* part = static_cast<const float*>(d.workspace) + i;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += __ldg(part + s * MN);
+  float* cp = d.C[0] + (long long)m * d.ldc + n;
+  float v = d.alpha * acc;
+  if (d.bias[0]) v += __ldg(d.bias[0] + n);
+  if (d.beta != 0.f) v = fmaf(d.beta, *cp, v);
+  if (d.row_scale) v = fmaf(__ldg(d.row_scale + m), __ldg(d.addend + (long long)m * d.ld_add + n), v);
+  if (d.act == B200NP_ACT_RELU) v = fmaxf(v, 0.f);
+  else if (d.act == B200NP_ACT_TANH) v = tanhf(v);
+  *cp = v;
+}
+
 }  // namespace
+
+// Split-K factor: the dense layers of the path have a few hundred rows, i.e. ~16 output tiles for 148 SMs;
+// their K range is spread over the idle SMs and the partial tiles are reduced from the caller's workspace.
+int gemm_umma_splits(const b200np_gemm_desc& d) {
+  if (d.precision == B200NP_PREC_FP32_SIMT || d.groups != 1) return 1;
+  const int tiles = ((d.M + 127) / 128) * ((d.N + 63) / 64);
+  const int KB = (d.K + 31) / 32;
+  if (tiles * 2 > kNumSMs || KB < 8) return 1;
+  int s = kNumSMs / tiles;
+  if (s > KB / 4) s = KB / 4;
+  return s > 1 ? s : 1;
+}
 
 // Returns B200NP_E_UNSUPPORTED when the shape is better served by the CUDA-core kernel.
 int launch_gemm_umma(const b200np_gemm_desc& d, int a_vec, int b_vec, cudaStream_t st) {
@@ -236,10 +277,17 @@ int launch_gemm_umma(const b200np_gemm_desc& d, int a_vec, int b_vec, cudaStream
   g.d = d;
   g.a_vec = a_vec;
   g.b_vec = b_vec;
+  g.splits = gemm_umma_splits(d);
+  if ((size_t)g.splits * d.M * d.N * sizeof(float) > d.workspace_bytes || !d.workspace) g.splits = 1;
   const bool x3 = d.precision != B200NP_PREC_TF32;
-  if (AK && BK) return x3 ? launch<true, true, true>(g, st) : launch<false, true, true>(g, st);
-  if (AK && !BK) return x3 ? launch<true, true, false>(g, st) : launch<false, true, false>(g, st);
-  return x3 ? launch<true, false, false>(g, st) : launch<false, false, false>(g, st);
+  int rc;
+  if (AK && BK) rc = x3 ? launch<true, true, true>(g, st) : launch<false, true, true>(g, st);
+  else if (AK && !BK) rc = x3 ? launch<true, true, false>(g, st) : launch<false, true, false>(g, st);
+  else rc = x3 ? launch<true, false, false>(g, st) : launch<false, false, false>(g, st);
+  if (rc != B200NP_OK || g.splits == 1) return rc;
+  const long long n = (long long)d.M * d.N;
+  splitk_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, g.splits);
+  return launch_status();
 }
 
 }  // namespace b200np
