@@ -55,15 +55,18 @@ long long b200np_launch_count(void);
  * (networks/CNPShapeNet1D.py:47-48).  x NCHW [N,Cin,H,W] (Cin<=4), w torch layout
  * [Cout,Cin,R,R], y NHWC [N,H/stride,W/stride,Cout].
  * ------------------------------------------------------------------------------------------ */
+/* precision (B200NP_PREC_*): the 1-channel 5x5 stem runs on tcgen05 in the TF32 modes (im2col tile built
+ * in shared memory, K = 25 padded to one 32-wide K-block); every other variant and fp32 mode run on
+ * CUDA cores in exact fp32. */
 int b200np_conv_small_fwd(const float* x, const float* w, const float* bias, float* y, int N,
                           int Cin, int H, int W, int Cout, int R, int stride, int pad, int relu,
-                          void* stream);
+                          int precision, void* stream);
 size_t b200np_conv_small_wgrad_workspace(int N, int Cin, int H, int W, int Cout, int R, int stride,
-                                         int pad);
+                                         int pad, int precision);
 /* dy NHWC is the gradient w.r.t. the pre-activation output; writes dw [Cout,Cin,R,R], db [Cout] */
 int b200np_conv_small_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int Cin,
-                            int H, int W, int Cout, int R, int stride, int pad, void* ws,
-                            size_t ws_bytes, void* stream);
+                            int H, int W, int Cout, int R, int stride, int pad, int precision,
+                            void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Channel-dense NHWC convolutions as implicit GEMM (pixels x Cout x taps*Cin).

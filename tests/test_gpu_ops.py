@@ -40,21 +40,28 @@ def from_nhwc(t):
 
 
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cin,r,cout,hw", [(1, 5, 64, 32), (3, 5, 64, 16), (1, 3, 32, 32), (1, 5, 64, 128)])
-def test_conv_small_fwd_and_wgrad(cin, r, cout, hw):
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("cin,r,cout,hw,n", [(1, 5, 64, 32, 3), (3, 5, 64, 16, 3), (1, 3, 32, 32, 3), (1, 5, 64, 128, 3),
+                                             (1, 5, 64, 6, 1), (1, 5, 64, 64, 37)])
+def test_conv_small_fwd_and_wgrad(prec, cin, r, cout, hw, n):
+    """Stem convolutions: CUDA-core fp32 kernels, and the tcgen05 kernels of the 1-channel 5x5 stem in the
+    TF32 modes (ragged last tile, K-blocks that straddle images, chunk counts below and above the cap)."""
     ops = _ops()
-    N = 3
-    x, w, b = rnd(N, cin, hw, hw, seed=1), rnd(cout, cin, r, r, seed=2, scale=0.2), rnd(cout, seed=3)
+    from b200np import lib
+    P = {"fp32": lib.PREC_FP32_SIMT, "tf32x3": lib.PREC_TF32X3, "tf32": lib.PREC_TF32}[prec]
+    tc = prec != "fp32" and (cin, r, cout) == (1, 5, 64)
+    tol_y, tol_g = (2e-6, 1e-5) if not tc else ((3e-6, 1e-5) if prec == "tf32x3" else (2e-3, 2e-3))
+    x, w, b = rnd(n, cin, hw, hw, seed=1), rnd(cout, cin, r, r, seed=2, scale=0.2), rnd(cout, seed=3)
     w.requires_grad_(True), b.requires_grad_(True)
     ref = F.relu(F.conv2d(x, w, b, stride=2, padding=r // 2))
-    y = ops.conv_small_fwd(x.float().cuda(), w.detach().float().cuda(), b.detach().float().cuda())
-    assert rel(from_nhwc(y), ref) < 2e-6
+    y = ops.conv_small_fwd(x.float().cuda(), w.detach().float().cuda(), b.detach().float().cuda(), prec=P)
+    assert rel(from_nhwc(y), ref) < tol_y
     dy = rnd(*ref.shape, seed=4) * (ref > 0)  # gradient w.r.t. the pre-activation
     pre = F.conv2d(x, w, b, stride=2, padding=r // 2)
     pre.backward(dy)
-    dw, db = ops.conv_small_wgrad(x.float().cuda(), nhwc(dy), w.shape)
-    assert rel(dw, w.grad) < 1e-5
-    assert rel(db, b.grad) < 1e-5
+    dw, db = ops.conv_small_wgrad(x.float().cuda(), nhwc(dy), w.shape, P)
+    assert rel(dw, w.grad) < tol_g
+    assert rel(db, b.grad) < tol_g
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])

@@ -56,8 +56,8 @@ if what in ("all", "stem"):
     img = torch.rand(N, 1, 128, 128, generator=g).to(dev)
     wst = (torch.randn(64, 1, 5, 5, generator=g) * 0.2).to(dev)
     dy0 = torch.randn(N, 64, 64, 64, generator=g).to(dev)
-    timed("stem 5x5 s2 fwd", lambda: ops.conv_small_fwd(img, wst, b), 2.0 * N * 4096 * 64 * 25)
-    timed("stem 5x5 s2 wgrad", lambda: ops.conv_small_wgrad(img, dy0, wst.shape), 2.0 * N * 4096 * 64 * 25)
+    timed("stem 5x5 s2 fwd", lambda: ops.conv_small_fwd(img, wst, b, prec=prec), 2.0 * N * 4096 * 64 * 25)
+    timed("stem 5x5 s2 wgrad", lambda: ops.conv_small_wgrad(img, dy0, wst.shape, prec), 2.0 * N * 4096 * 64 * 25)
 if what in ("all", "wgrad"):
     # accuracy of the long pixel contraction at full size: tensor-core modes against the CUDA-core fp32 kernel
     ref, _, _ = ops.conv_wgrad(h, dz, 3, 1, 0)

@@ -52,7 +52,7 @@ class TrunkFn(Function):
         x0 = ops.empty((N, H // 2, W // 2, 64), imgs[0])
         off = 0
         for im, n in zip(imgs, Ns):
-            ops.conv_small_fwd(im, c1w, c1b, out=x0[off:off + n], relu=True)
+            ops.conv_small_fwd(im, c1w, c1b, out=x0[off:off + n], relu=True, prec=prec)
             off += n
         x, acts, packs = x0, [], []
         for l in range(4):
@@ -109,7 +109,7 @@ class TrunkFn(Function):
             dy = dx
         off, dw_acc, db_acc = 0, None, None
         for im, n in zip(ctx.imgs, Ns):
-            dw, db = ops.conv_small_wgrad(im, dy[off:off + n], ctx.c1w_shape)
+            dw, db = ops.conv_small_wgrad(im, dy[off:off + n], ctx.c1w_shape, prec)
             if dw_acc is None:
                 dw_acc, db_acc = dw, db
             else:
@@ -135,7 +135,7 @@ class EncoderW0Fn(Function):
         x1 = ops.empty((N, H // 2, W // 2, w0.shape[0]), imgs[0])
         off = 0
         for im, n in zip(imgs, Ns):
-            ops.conv_small_fwd(im, w0, b0, out=x1[off:off + n], relu=True)
+            ops.conv_small_fwd(im, w0, b0, out=x1[off:off + n], relu=True, prec=prec)
             off += n
         wd2, wd5 = ops.pack_conv_weight(w2), ops.pack_conv_weight(w5)
         x2 = ops.conv_fwd(x1, wd2, b2, 2, ACT_RELU, prec)
@@ -165,7 +165,7 @@ class EncoderW0Fn(Function):
         d1 = ops.conv_dgrad(d2, wd2, x1.shape, 2, prec, mask_src=x1)
         off, dw0, db0 = 0, None, None
         for im, n in zip(ctx.imgs, Ns):
-            dw, db = ops.conv_small_wgrad(im, d1[off:off + n], w0_shape)
+            dw, db = ops.conv_small_wgrad(im, d1[off:off + n], w0_shape, prec)
             if dw0 is None:
                 dw0, db0 = dw, db
             else:

@@ -36,7 +36,7 @@ def empty(shape, like, dtype=F32):
 # ----------------------------------------------------------------------------------------------
 # convolutions
 # ----------------------------------------------------------------------------------------------
-def conv_small_fwd(x, w, b, out=None, relu=True):
+def conv_small_fwd(x, w, b, out=None, relu=True, prec=lib.PREC_FP32_SIMT):
     """x NCHW [N,Cin,H,W] -> NHWC [N,H/2,W/2,Cout] (stride 2, pad R//2)."""
     for t, n in ((x, "x"), (w, "w"), (b, "b"), (out, "out")):
         _chk(t, n)
@@ -45,20 +45,20 @@ def conv_small_fwd(x, w, b, out=None, relu=True):
     if out is None:
         out = empty((N, H // 2, W // 2, Cout), x)
     check(LIB.b200np_conv_small_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(out), N, Cin, H, W, Cout, R, 2, R // 2,
-                                    int(relu), _stream()), "conv_small_fwd")
+                                    int(relu), prec, _stream()), "conv_small_fwd")
     return out
 
 
-def conv_small_wgrad(x, dy, w_shape):
+def conv_small_wgrad(x, dy, w_shape, prec=lib.PREC_FP32_SIMT):
     N, Cin, H, W = x.shape
     Cout, _, R, _ = w_shape
     _chk(x, "x"), _chk(dy, "dy")
-    ws_bytes = LIB.b200np_conv_small_wgrad_workspace(N, Cin, H, W, Cout, R, 2, R // 2)
+    ws_bytes = LIB.b200np_conv_small_wgrad_workspace(N, Cin, H, W, Cout, R, 2, R // 2, prec)
     ws = torch.empty(max(ws_bytes // 4, 1), device=x.device, dtype=F32)
     dw = empty(tuple(w_shape), x)
     db = empty((Cout,), x)
     check(LIB.b200np_conv_small_wgrad(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), N, Cin, H, W, Cout, R, 2, R // 2,
-                                      _ptr(ws), ws_bytes, _stream()), "conv_small_wgrad")
+                                      prec, _ptr(ws), ws_bytes, _stream()), "conv_small_wgrad")
     return dw, db
 
 

@@ -39,11 +39,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
 }
 
 // Pixel chunks per weight gradient.  The tcgen05 kernel runs one CTA per (tap pair, chunk), two CTAs
-// per SM: size the grid to two full waves (a ragged second wave doubled the run time).  The CUDA-core
-// kernel runs one CTA per (tap, chunk).
+// per SM: size the grid to four full waves (a ragged last wave costs a whole wave; shorter chunks also
+// halve the number of truncating fp32 accumulations per TMEM block).  The CUDA-core kernel runs one CTA
+// per (tap, chunk).
 int wgrad_chunks(long long M, int ntaps) {
   const int pairs = (ntaps + 1) / 2;
-  long long want = (4LL * kNumSMs) / pairs;
+  long long want = (8LL * kNumSMs) / pairs;
   long long maxc = ceil_div(M, 64);
   if (want > maxc) want = maxc;
   return (int)(want < 1 ? 1 : want);

@@ -10,6 +10,15 @@
 
 using namespace b200np;
 
+namespace b200np {  // conv_stem_umma.cu
+bool stem_umma_supported(int Cin, int R, int Cout, int precision);
+int launch_stem_fwd_umma(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int relu,
+                         int precision, cudaStream_t st);
+size_t stem_wgrad_umma_workspace(int N, int H, int W);
+int launch_stem_wgrad_umma(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int precision,
+                           void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace b200np
+
 namespace {
 
 constexpr int kTW = 32;  // output tile width
@@ -263,12 +272,14 @@ bool supported(int Cin, int R, int Cout, int stride, int pad, int H, int W) {
 }  // namespace
 
 extern "C" int b200np_conv_small_fwd(const float* x, const float* w, const float* bias, float* y, int N, int Cin,
-                                     int H, int W, int Cout, int R, int stride, int pad, int relu, void* stream) {
+                                     int H, int W, int Cout, int R, int stride, int pad, int relu, int precision,
+                                     void* stream) {
   if (!x || !w || !bias || !y || N <= 0) return B200NP_E_BADARG;
   if (!supported(Cin, R, Cout, stride, pad, H, W)) return B200NP_E_UNSUPPORTED;
   if (!aligned16(y) || !aligned16(bias)) return B200NP_E_BADARG;
   const int OH = H / 2, OW = W / 2;
   cudaStream_t st = as_stream(stream);
+  if (stem_umma_supported(Cin, R, Cout, precision)) return launch_stem_fwd_umma(x, w, bias, y, N, H, W, relu, precision, st);
   const long long tiles = (long long)N * ((OH + kFwdTH - 1) / kFwdTH) * ((OW + kTW - 1) / kTW);
   const long long cap = 8LL * kNumSMs;
   const int grid = (int)(tiles < cap ? tiles : cap);
@@ -279,18 +290,21 @@ extern "C" int b200np_conv_small_fwd(const float* x, const float* w, const float
 }
 
 extern "C" size_t b200np_conv_small_wgrad_workspace(int N, int Cin, int H, int W, int Cout, int R, int stride,
-                                                    int pad) {
+                                                    int pad, int precision) {
   (void)pad;
   if (N <= 0 || stride != 2) return 0;
+  if (stem_umma_supported(Cin, R, Cout, precision)) return stem_wgrad_umma_workspace(N, H, W);
   return wg_cfg(N, Cin, H, W, Cout, R).ws;
 }
 
 extern "C" int b200np_conv_small_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int Cin, int H,
-                                       int W, int Cout, int R, int stride, int pad, void* ws, size_t ws_bytes,
-                                       void* stream) {
+                                       int W, int Cout, int R, int stride, int pad, int precision, void* ws,
+                                       size_t ws_bytes, void* stream) {
   if (!x || !dy || !dw || N <= 0) return B200NP_E_BADARG;
   if (!supported(Cin, R, Cout, stride, pad, H, W)) return B200NP_E_UNSUPPORTED;
   if (!aligned16(dy) || !aligned16(ws)) return B200NP_E_BADARG;
+  if (stem_umma_supported(Cin, R, Cout, precision))
+    return launch_stem_wgrad_umma(x, dy, dw, db, N, H, W, precision, ws, ws_bytes, as_stream(stream));
   const WgCfg c = wg_cfg(N, Cin, H, W, Cout, R);
   if (!ws || ws_bytes < c.ws) return B200NP_E_WORKSPACE;
   cudaStream_t st = as_stream(stream);

@@ -214,6 +214,8 @@ constexpr int kWgK = 32;                             // pixels per K-block
 constexpr uint32_t kWgABytes = 128 * kWgK * 4;        // 16 KB : 4 channel blocks x 4 pixel groups x 1 KB
 constexpr uint32_t kWgBBytes = 64 * kWgK * 4;         //  8 KB : 2 channel blocks x 4 pixel groups x 1 KB
 constexpr uint32_t kIdescTf32_128x64_MN = kIdescTf32_128x64 | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+constexpr uint32_t kIdescTf32_128x128_MN =
+    (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -327,26 +329,38 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
     uint8_t* a_lo = st + kWgABytes;
     uint8_t* b_hi = st + (X3 ? 2 : 1) * kWgABytes;
     uint8_t* b_lo = b_hi + kWgBBytes;
+    // The eight threads of a quarter-warp cover four pixel rows (four 32-byte swizzle units) and both channel
+    // halves; the halves are 4096 B apart, i.e. the same banks.  The odd half therefore walks its 16-byte chunks
+    // in swapped order (c ^ 1), which makes every quarter-warp store hit all 32 banks.
 #pragma unroll
-    for (int c = 0; c < 8; ++c) split_store(a_hi, a_lo, mn_offset(a_tl * 2 + a_half, a_k, c), av[c], X3);
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = a_half ? av[c ^ 1] : av[c];
+      split_store(a_hi, a_lo, mn_offset(a_tl * 2 + a_half, a_k, c) ^ (uint32_t)(a_half << 4), v, X3);
+    }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) split_store(b_hi, b_lo, mn_offset(b_half, b_k, b_sub * 4 + c), bv[c], X3);
+    for (int c = 0; c < 4; ++c) {
+      const float4 v = b_half ? bv[c ^ 1] : bv[c];
+      split_store(b_hi, b_lo, mn_offset(b_half, b_k, b_sub * 4 + c) ^ (uint32_t)(b_half << 4), v, X3);
+    }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
       const uint64_t ah = make_mnmajor_sw128_desc(smem_u32(a_hi)), bh = make_mnmajor_sw128_desc(smem_u32(b_hi));
-      const uint32_t d_hi = tmem_d + (uint32_t)(kb % AccCfg<X3>::kHi) * 64;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)  // next group of 8 pixels: +1024 B = +64 in the address field
-        umma_tf32(d_hi, ah + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, (kb >= AccCfg<X3>::kHi) | (k != 0));
       if (X3) {
-        const uint64_t al = make_mnmajor_sw128_desc(smem_u32(a_lo)), bl = make_mnmajor_sw128_desc(smem_u32(b_lo));
-        const uint32_t d_lo = tmem_d + AccCfg<X3>::kHi * 64;
+        // dY_hi and dY_lo are adjacent 32-channel blocks of one MN-major tile, so a single N = 128 MMA forms
+        // X_hi * [dY_hi | dY_lo] (64 vs 2 x 54 cycles, and X_hi is read from shared memory once); X_lo * dY_hi
+        // goes on top of the cross-term columns.  Two rotating 128-column blocks (see AccCfg) per CTA.
+        const uint64_t al = make_mnmajor_sw128_desc(smem_u32(a_lo));
+        const uint32_t d_blk = tmem_d + (uint32_t)(kb & 1) * 128;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, (kb | k) != 0);
+        for (int k = 0; k < 4; ++k)  // next group of 8 pixels: +1024 B = +64 in the address field
+          umma_tf32(d_blk, ah + 64 * k, bh + 64 * k, kIdescTf32_128x128_MN, (kb >= 2) | (k != 0));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + 64 * k, bl + 64 * k, kIdescTf32_128x64_MN, 1u);
+        for (int k = 0; k < 4; ++k) umma_tf32(d_blk + 64, al + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, 1u);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, (kb | k) != 0);
       }
       umma_commit(bars + s);
       if (kb == KB - 1) umma_commit(bars + kStages);
@@ -367,13 +381,27 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
   }
   {
     const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-    const int hi_used = KB < AccCfg<X3>::kHi ? (int)KB : AccCfg<X3>::kHi;
     float* po = a.part + ((long long)chunk * a.ntaps + (tap < a.ntaps ? tap : 0)) * 64 * 64 + ci;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       float acc[32];
       if (KB > 0) {
-        gather_acc<X3>(taddr, half * 32, hi_used, acc);
+        if (X3) {  // cross-term columns first (smallest magnitude), then the main products, both blocks
+          uint32_t r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int blk = q & 1, cross = q < 2;
+            if (blk < KB) {
+              tmem_ld32(taddr + blk * 128 + cross * 64 + half * 32, r);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+            }
+          }
+        } else {
+          gather_acc<false>(taddr, half * 32, 1, acc);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = 0.f;
