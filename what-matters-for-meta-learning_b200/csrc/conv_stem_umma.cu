@@ -63,12 +63,14 @@ __global__ void __launch_bounds__(128, 4)
   uint8_t* smem = align1024(smem_raw);
   uint8_t* a_hi = smem;
   uint8_t* a_lo = smem + kA;
-  uint8_t* b_hi = smem + (X3 ? 2 : 1) * kA;
+  uint8_t* b_hi = smem + 2 * kA;  // a_lo doubles as epilogue staging in single-pass mode
   uint8_t* b_lo = b_hi + kB;
-  float* bias_s = reinterpret_cast<float*>(b_hi + (X3 ? 2 : 1) * kB);
+  float* bias_s = reinterpret_cast<float*>(b_hi + 2 * kB);
   uint64_t* bar = reinterpret_cast<uint64_t*>(bias_s + 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const uint32_t leader = elect_one_sync();
   const int OH = H / 2, OW = W / 2;
   const long long M = (long long)N * OH * OW;
 
@@ -139,28 +141,31 @@ __global__ void __launch_bounds__(128, 4)
     fence_proxy_async();
     tc_fence_before();  // orders the previous tile's TMEM reads before this tile's MMAs
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {  // all 32 lanes: descriptors stay in uniform registers, the elected lane issues
       tc_fence_after();
       const uint64_t ah = make_kmajor_sw128_desc(smem_u32(a_hi)), bh = make_kmajor_sw128_desc(smem_u32(b_hi));
       if (X3) {
         const uint64_t al = make_kmajor_sw128_desc(smem_u32(a_lo));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 2 * k, bh + 2 * k, tf32_idesc(128, 128, false), k != 0);
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 2 * k, bh + 2 * k, tf32_idesc(128, 128, false), k != 0, leader);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d + 64, al + 2 * k, bh + 2 * k, tf32_idesc(128, 64, false), 1u);
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d + 64, al + 2 * k, bh + 2 * k, tf32_idesc(128, 64, false), 1u, leader);
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 2 * k, bh + 2 * k, tf32_idesc(128, 64, false), k != 0);
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 2 * k, bh + 2 * k, tf32_idesc(128, 64, false), k != 0, leader);
       }
-      umma_commit(bar);
+      umma_commit(bar, leader);
     }
-    const long long p_out = tile * 128 + tid;
     if (tile + gridDim.x < tiles) fetch(tile + gridDim.x);  // next tile's loads fly during the MMAs and the epilogue
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
+    // Epilogue.  A thread holds the 64 channels of ONE pixel; stored directly, a warp-wide 16-byte store
+    // would touch 32 different 128-byte lines (half-written sectors, 32 L1 wavefronts).  The warp instead
+    // transposes its 32 x 64 tile through the shared memory of its own im2col rows (idle until the next
+    // tile is staged) and writes 512 contiguous bytes per instruction.
     const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-    float* yp = y + p_out * 64;
+    const int lane = tid & 31;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t r[32];
@@ -177,16 +182,28 @@ __global__ void __launch_bounds__(128, 4)
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
       }
-      if (p_out < M) {
+      uint8_t* piece = (half ? a_lo : a_hi) + warp * 4096 + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + half * 32 + j);
-          float4 o = make_float4(acc[j] + b4.x, acc[j + 1] + b4.y, acc[j + 2] + b4.z, acc[j + 3] + b4.w);
-          if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-          *reinterpret_cast<float4*>(yp + half * 32 + j) = o;
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + half * 32 + 4 * j);
+        float4 o = make_float4(acc[4 * j] + b4.x, acc[4 * j + 1] + b4.y, acc[4 * j + 2] + b4.z, acc[4 * j + 3] + b4.w);
+        if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+        *reinterpret_cast<float4*>(piece + ((j ^ (lane & 7)) << 4)) = o;
       }
     }
+    __syncwarp();
+    {
+      const long long p_base = tile * 128 + warp * 32;
+      const int c = lane & 15, h = c >> 3, j = c & 7;
+      const uint8_t* piece = (h ? a_lo : a_hi) + warp * 4096;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int rr = it * 2 + (lane >> 4);
+        const float4 o = *reinterpret_cast<const float4*>(piece + rr * 128 + ((j ^ (rr & 7)) << 4));
+        if (p_base + rr < M) *reinterpret_cast<float4*>(y + (p_base + rr) * 64 + c * 4) = o;
+      }
+    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -199,7 +216,8 @@ __global__ void __launch_bounds__(128, 4)
 // weight (and bias) gradient.  One CTA per chunk of pixels, K-blocks of 32 pixels, two stages.
 //   A stage (16 KB): MN-major, four 32-channel blocks: dY_hi co 0-31 | dY_hi co 32-63 | dY_lo ... | dY_lo ...
 //   B stage ( 8 KB): MN-major, two 32-tap blocks: Xcol_hi | Xcol_lo
-// thread = (pixel k = tid / 4, quarter q = tid % 4): 16 dY channels and 8 taps of that pixel.
+// Xcol: thread = (pixel k = tid / 4, quarter q = tid % 4) gathers 8 taps of that pixel; dY: lanes walk
+// consecutive 16-byte chunks, so every warp load is 512 contiguous bytes.
 // part[(chunk * 2 + hi|lo)][co][32]: summed (with the other chunks) by the reducer into dw[co][25], db[co].
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kWA = 4 * 4096, kWB = 2 * 4096, kWStage = kWA + kWB;
@@ -212,7 +230,9 @@ __global__ void __launch_bounds__(128, 4)
   uint8_t* smem = align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kWStage);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const uint32_t leader = elect_one_sync();
   const int OH = H / 2, OW = W / 2;
   const long long M = (long long)N * OH * OW;
   const long long p_begin = (long long)blockIdx.x * pix_per_chunk;
@@ -240,7 +260,7 @@ __global__ void __launch_bounds__(128, 4)
 
   const int k = tid >> 2, q = tid & 3;
   // this thread's pixel of the current fetch, walked incrementally (+32 pixels per K-block)
-  long long f_p = p_begin + k, f_n;
+  long long f_p = p_begin + k, f_n, f_pb = p_begin;
   int f_ox, f_oy;
   {
     f_ox = (int)(f_p % OW);
@@ -251,10 +271,14 @@ __global__ void __launch_bounds__(128, 4)
   float4 dv0[4], dv1[4];
   float xv0[8], xv1[8];
   auto fetch = [&](float4 (&dv)[4], float (&xv)[8]) {
-    if (f_p < p_end) {
-      const float* dp = dy + f_p * 64 + q * 16;
+    // dY: lanes walk consecutive 16-byte chunks (a warp instruction reads 512 contiguous bytes = 2 pixels)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dv[j] = ldg4(dp + 4 * j);
+    for (int j = 0; j < 4; ++j) {
+      const long long pd = f_pb + 8 * warp + 2 * j + (lane >> 4);
+      dv[j] = pd < p_end ? ldg4(dy + pd * 64 + (lane & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    f_pb += 32;
+    if (f_p < p_end) {
       const float* img = x + f_n * H * W;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -270,8 +294,6 @@ __global__ void __launch_bounds__(128, 4)
         xv[e] = val;
       }
     } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) xv[e] = 0.f;
     }
@@ -292,16 +314,11 @@ __global__ void __launch_bounds__(128, 4)
     uint8_t* a = smem + s * kWStage;
     uint8_t* b = a + kWA;
     // bank-conflict-free 16-byte stores: the eight threads of a quarter-warp must hit eight different
-    // 16-byte slots of the 128-byte line.  dY: the two channel halves (blocks 4096 B apart) would collide,
-    // the upper half walks its chunks in swapped order.  Xcol: odd pixels swap the two chunks.
-    {
-      const int blk = q >> 1, sw = blk;
+    // 16-byte slots of the 128-byte line.  dY: a quarter-warp holds the eight chunks of one 32-channel block
+    // of one pixel.  Xcol: odd pixels swap the two chunks.
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 val = sw ? dv[j ^ 1] : dv[j];
-        split_store(a, a + 2 * 4096, mn_off(blk, k, (q & 1) * 4 + j) ^ (uint32_t)(sw << 4), val, X3);
-      }
-    }
+    for (int j = 0; j < 4; ++j)
+      split_store(a, a + 2 * 4096, mn_off((lane >> 3) & 1, 8 * warp + 2 * j + (lane >> 4), lane & 7), dv[j], X3);
     {
       const int sw = k & 1;
       const float4 c0 = make_float4(xv[0], xv[1], xv[2], xv[3]), c1 = make_float4(xv[4], xv[5], xv[6], xv[7]);
@@ -310,15 +327,15 @@ __global__ void __launch_bounds__(128, 4)
     }
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {  // all 32 lanes: descriptors stay in uniform registers, the elected lane issues
       tc_fence_after();
       const uint64_t ad = mn_desc(smem_u32(a)), bd = mn_desc(smem_u32(b));
       const uint32_t d_blk = tmem_d + (uint32_t)(kb & 1) * 64;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)  // next 8 pixels: +1024 B
-        umma_tf32(d_blk, ad + 64 * ks, bd + 64 * ks, tf32_idesc(128, X3 ? 64 : 32, true), (kb >= 2) | (ks != 0));
-      umma_commit(bars + s);
-      if (kb == KB - 1) umma_commit(bars + 2);
+        umma_tf32(d_blk, ad + 64 * ks, bd + 64 * ks, tf32_idesc(128, X3 ? 64 : 32, true), (kb >= 2) | (ks != 0), leader);
+      umma_commit(bars + s, leader);
+      if (kb == KB - 1) umma_commit(bars + 2, leader);
     }
     if (kb + 2 < KB) fetch(dv, xv);
   };
@@ -380,10 +397,10 @@ int launch_stem_fwd_umma(const float* x, const float* w, const float* bias, floa
   const bool x3 = precision != B200NP_PREC_TF32;
   const long long M = (long long)N * (H / 2) * (W / 2);
   const long long tiles = ceil_div(M, 128);
-  const size_t smem = (x3 ? 2 : 1) * (128 * 32 * 4 + 64 * 32 * 4) + 256 + 64 + 1024;
+  const size_t smem = 2 * (128 * 32 * 4 + 64 * 32 * 4) + 256 + 64 + 1024;
   static bool configured = false;
   if (!configured) {
-    if (!set_smem(stem_fwd_umma_kernel<true>, 2 * 24576 + 1344) || !set_smem(stem_fwd_umma_kernel<false>, 24576 + 1344))
+    if (!set_smem(stem_fwd_umma_kernel<true>, smem) || !set_smem(stem_fwd_umma_kernel<false>, smem))
       return B200NP_E_LAUNCH;
     configured = true;
   }

@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
   float* __restrict__ C = d.C[grp];
   const float* __restrict__ bias = d.bias[grp];
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const uint32_t leader = elect_one_sync();
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
   const int M = d.M, N = d.N, K = d.K;
 
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
                   bv[c], X3);
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {  // all 32 lanes: descriptors stay in uniform registers, the elected lane issues
       tc_fence_after();
       const uint64_t ah = AK ? make_kmajor_sw128_desc(smem_u32(a_hi)) : mn_desc(smem_u32(a_hi));
       const uint64_t bh = BK ? make_kmajor_sw128_desc(smem_u32(b_hi)) : mn_desc(smem_u32(b_hi));
@@ -149,18 +151,18 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
       const uint32_t d_hi = tmem_d + (kb % AccCfg<X3>::kHi) * 64;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_tf32(d_hi, ah + ka * k, bh + kbs * k, kIdesc, (kb >= AccCfg<X3>::kHi) | (k != 0));
+        umma_tf32(d_hi, ah + ka * k, bh + kbs * k, kIdesc, (kb >= AccCfg<X3>::kHi) | (k != 0), leader);
       if (X3) {
         const uint64_t al = AK ? make_kmajor_sw128_desc(smem_u32(a_lo)) : mn_desc(smem_u32(a_lo));
         const uint64_t bl = BK ? make_kmajor_sw128_desc(smem_u32(b_lo)) : mn_desc(smem_u32(b_lo));
         const uint32_t d_lo = tmem_d + AccCfg<X3>::kHi * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + ka * k, bh + kbs * k, kIdesc, (kb | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + ka * k, bh + kbs * k, kIdesc, (kb | k) != 0, leader);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + ka * k, bl + kbs * k, kIdesc, 1u);
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + ka * k, bl + kbs * k, kIdesc, 1u, leader);
       }
-      umma_commit(bars + s);
-      if (kb == KB - 1) umma_commit(bars + kStages);
+      umma_commit(bars + s, leader);
+      if (kb == KB - 1) umma_commit(bars + kStages, leader);
     }
     if (kb + 2 < KB) fetch(kb + 2, av, bv);
   };

@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
     if (h.dbg && tid == 0) { h.dbg[blockIdx.x * 8 + 0] = dbg_a; h.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
   } else if (warp == kWeightWarp) {
     // ===================== weight producer =====================
-    if (lane == 0) {
+    // (all lanes run the loop, the elected one issues: the bulk copy also takes uniform-register operands)
+    const bool leader = elect_one_sync();
+    {
       Ring bs;
       long long dbg_b = 0;
       for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
@@ -220,25 +222,25 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             const Tap tp = a.taps[t];
             const float* src = h.bp[tp.src] + ((long long)half * h.nslabs[tp.src] + tp.slab) * (kBSlotBytes / 4);
             mbar_wait_timed(b_empty + bs.idx, bs.phase ^ 1, dbg_b, h.dbg != nullptr);
-            mbar_expect_tx(b_full + bs.idx, kBSlot);
-            bulk_g2s(smem + h.b_off + bs.idx * kBSlot, src, kBSlot, b_full + bs.idx);
+            if (leader) {
+              mbar_expect_tx(b_full + bs.idx, kBSlot);
+              bulk_g2s(smem + h.b_off + bs.idx * kBSlot, src, kBSlot, b_full + bs.idx);
+            }
             bs.advance(nb);
           }
         }
       }
-      if (h.dbg) h.dbg[blockIdx.x * 8 + 2] = dbg_b;
+      if (h.dbg && leader) h.dbg[blockIdx.x * 8 + 2] = dbg_b;
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    // One lane issues every tcgen05.mma of the CTA.  Everything that does not change per tile is
-    // precomputed: per-tap descriptor words live in a small shared table, descriptors are assembled from
-    // 32-bit halves, the k-step is an immediate add on the low word.
-    if (lane < ntaps) {
-      tap_tab[lane * 2 + 0] = (uint32_t)h.tap_off[lane] * 8u;                           // slots -> 16-byte units
-      tap_tab[lane * 2 + 1] = (((uint32_t)h.tap_hc[lane] * 128u) >> 4) | (1u << 14) | (2u << 29);  // SBO, v1, SW128
-    }
-    __syncwarp();
-    if (lane == 0) {
+    // One elected lane issues every tcgen05.mma of the CTA, but ALL 32 lanes run the loop: tcgen05.mma takes
+    // its descriptors from uniform registers, and only values computed in warp-uniform control flow live
+    // there.  With the whole loop inside `if (lane == 0)` the compiler wrapped every MMA in an
+    // ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall" (~100 cycles per MMA, more than the MMA itself takes).
+    // The per-tap descriptor words come from the kernel parameters (constant bank, uniform index).
+    const bool leader = elect_one_sync();
+    {
       Ring st, bs;
       int acc_set = 0;
       uint32_t acc_phase = 0;
@@ -271,33 +273,36 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           tc_fence_after();
           const uint32_t stage16 = (smem_u32(smem + st.idx * h.stage_bytes) & 0x3FFFFu) >> 4;
           for (int t = 0; t < ntaps; ++t, ++kb) {
-            const uint32_t a16 = stage16 + tap_tab[t * 2], a_hi_word = tap_tab[t * 2 + 1];
+            const uint32_t a16 = stage16 + (uint32_t)h.tap_off[t] * 8u;  // slots -> 16-byte units
+            const uint32_t a_hi_word = (((uint32_t)h.tap_hc[t] * 128u) >> 4) | (1u << 14) | (2u << 29);  // SBO, v1, SW128
             const uint32_t ah = a16 | lbo_bits, al = (a16 + plane16) | lbo_bits;
             const uint32_t bh = (b_base16 + bs.idx * (kBSlot >> 4)) | lbo_bits;
             mbar_wait_timed(b_full + bs.idx, bs.phase, w_b, timed);
             tc_fence_after();
             const uint32_t d_blk = d0 + rot * (X3 ? 128u : 64u);
             const uint32_t acc_first = kb >= kRot;
-            if (X3) {
+            if (leader) {
+              if (X3) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescN128);
+                for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescN128);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) mma(d_blk + 64, al + 2 * k, a_hi_word, bh + 2 * k, 1u, kIdescTf32_128x64);
-            } else {
+                for (int k = 0; k < 4; ++k) mma(d_blk + 64, al + 2 * k, a_hi_word, bh + 2 * k, 1u, kIdescTf32_128x64);
+              } else {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescTf32_128x64);
+                for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescTf32_128x64);
+              }
+              umma_commit(b_empty + bs.idx);
             }
-            umma_commit(b_empty + bs.idx);
             bs.advance(nb);
             if (++rot == kRot) rot = 0;
           }
-          umma_commit(a_empty + st.idx);
+          if (leader) umma_commit(a_empty + st.idx);
           st.advance(a_stages);
         }
-        umma_commit(acc_full + acc_set);
+        if (leader) umma_commit(acc_full + acc_set);
         if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
       }
-      if (timed) {
+      if (timed && leader) {
         long long* o = h.dbg + blockIdx.x * 8;
         o[3] = w_acc; o[4] = w_a; o[5] = w_b; o[6] = clock64() - t_start;
       }

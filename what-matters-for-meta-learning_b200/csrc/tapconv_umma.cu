@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const uint32_t leader = elect_one_sync();
   const long long M = (long long)a.N * a.OH * a.OW;
   const long long m0 = (long long)blockIdx.x * kBM;
 
@@ -105,23 +107,23 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
     for (int c = 0; c < 4; ++c) split_store(b_hi, b_lo, sw128_offset(brow, bhalf * 4 + c), bv[c], X3);
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {  // all 32 lanes: descriptors stay in uniform registers, the elected lane issues
       tc_fence_after();
       const uint64_t ah = make_kmajor_sw128_desc(smem_u32(a_hi)), bh = make_kmajor_sw128_desc(smem_u32(b_hi));
       const uint32_t d_hi = tmem_d + (kb % AccCfg<X3>::kHi) * 64;
 #pragma unroll
       for (int k = 0; k < 4; ++k)  // +32 B (8 tf32) along K inside the swizzle atom = +2 in the address field
-        umma_tf32(d_hi, ah + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb >= AccCfg<X3>::kHi) | (k != 0));
+        umma_tf32(d_hi, ah + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb >= AccCfg<X3>::kHi) | (k != 0), leader);
       if (X3) {
         const uint64_t al = make_kmajor_sw128_desc(smem_u32(a_lo)), bl = make_kmajor_sw128_desc(smem_u32(b_lo));
         const uint32_t d_lo = tmem_d + AccCfg<X3>::kHi * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb | k) != 0, leader);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + 2 * k, bl + 2 * k, kIdescTf32_128x64, 1u);
+        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + 2 * k, bl + 2 * k, kIdescTf32_128x64, 1u, leader);
       }
-      umma_commit(bars + s);                       // stage reusable once these MMAs retire
-      if (kb == KB - 1) umma_commit(bars + kStages);  // accumulator complete
+      umma_commit(bars + s, leader);                       // stage reusable once these MMAs retire
+      if (kb == KB - 1) umma_commit(bars + kStages, leader);  // accumulator complete
     }
     if (kb + 2 < KB) fetch(kb + 2, av, bv);
   };
@@ -240,6 +242,8 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const uint32_t leader = elect_one_sync();
   const int chunk = blockIdx.y, pair = blockIdx.x;
   const long long M = (long long)a.N * a.OH * a.OW;
   const long long p_begin = (long long)chunk * a.pix_per_chunk;
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
     }
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {  // all 32 lanes: descriptors stay in uniform registers, the elected lane issues
       tc_fence_after();
       const uint64_t ah = make_mnmajor_sw128_desc(smem_u32(a_hi)), bh = make_mnmajor_sw128_desc(smem_u32(b_hi));
       if (X3) {
@@ -355,15 +359,15 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
         const uint32_t d_blk = tmem_d + (uint32_t)(kb & 1) * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // next group of 8 pixels: +1024 B = +64 in the address field
-          umma_tf32(d_blk, ah + 64 * k, bh + 64 * k, kIdescTf32_128x128_MN, (kb >= 2) | (k != 0));
+          umma_tf32(d_blk, ah + 64 * k, bh + 64 * k, kIdescTf32_128x128_MN, (kb >= 2) | (k != 0), leader);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_blk + 64, al + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, 1u);
+        for (int k = 0; k < 4; ++k) umma_tf32(d_blk + 64, al + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, 1u, leader);
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, (kb | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 64 * k, bh + 64 * k, kIdescTf32_128x64_MN, (kb | k) != 0, leader);
       }
-      umma_commit(bars + s);
-      if (kb == KB - 1) umma_commit(bars + kStages);
+      umma_commit(bars + s, leader);
+      if (kb == KB - 1) umma_commit(bars + kStages, leader);
     }
     if (kb + 2 < KB) fetch(kb + 2, av, bv);
   };

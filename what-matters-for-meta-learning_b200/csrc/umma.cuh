@@ -34,21 +34,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 22)) __trap();
   }
 }
+// One lane of a converged warp (the lowest active one).  The MMA-issuing code runs warp-uniformly and only
+// the tcgen05.mma / tcgen05.commit instructions sit under this predicate, so that descriptors stay in
+// uniform registers (see tapconv_halo.cu).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+// `issue`: instruction-level guard.  tcgen05.mma / tcgen05.commit read their operands from UNIFORM registers,
+// and the compiler keeps a value there only if it is computed in warp-uniform control flow.  The issuing warp
+// therefore runs its loop with all 32 lanes and passes issue = (this lane is the elected one); wrapping the
+// whole loop in `if (tid == 0)` instead costs an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall per MMA.
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t issue = 1u) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(issue)
+      : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate, issued by one thread.
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+                                          uint32_t accumulate, uint32_t issue = 1u) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
