@@ -14,14 +14,27 @@ ws = ops.pack_conv_weight((torch.randn(64, 64, 1, 1, generator=g) * 0.1).cuda())
 b = torch.zeros(64, device="cuda")
 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 LIB.b200np_debug_set_halo_timing.argtypes = [ctypes.c_void_p]
-for name, fn in (("fwd conv2+skip", lambda: ops.conv_fwd(h, w2, b, 1, 1, prec, skip=(x, ws, b, 2))),
-                 ("dgrad s1", lambda: ops.conv_dgrad(h, w2, h.shape, 1, prec, mask_src=h))):
-    fn(); torch.cuda.synchronize()
-    LIB.b200np_debug_set_halo_timing(ctypes.c_void_p(dbg.data_ptr()))
-    dbg.zero_(); fn(); torch.cuda.synchronize()
-    LIB.b200np_debug_set_halo_timing(ctypes.c_void_p(0))
+flag_list = [int(f) for f in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+ev = lambda: torch.cuda.Event(enable_timing=True)
+def report(name, fl):
     d = dbg.view(148, 8).double().mean(0).tolist()
     tiles = N * 8 / 148
-    print(f"{name}: tiles/CTA {tiles:.0f}; cycles per tile: MMA-lane total {d[6]/tiles:.0f} = wait acc_empty {d[3]/tiles:.0f} + wait a_full {d[4]/tiles:.0f} "
+    print(f"  [{fl}] cycles per tile: MMA-lane total {d[6]/tiles:.0f} = wait acc_empty {d[3]/tiles:.0f} + wait a_full {d[4]/tiles:.0f} "
           f"+ wait b_full {d[5]/tiles:.0f} + issue/other {(d[6]-d[3]-d[4]-d[5])/tiles:.0f} | producer total {d[1]/tiles:.0f}, blocked on a_empty {d[0]/tiles:.0f} "
           f"| weight warp blocked on b_empty {d[2]/tiles:.0f} | epilogue blocked on acc_full {d[7]/tiles:.0f}")
+
+
+for name, fn in (("fwd conv2+skip", lambda: ops.conv_fwd(h, w2, b, 1, 1, prec, skip=(x, ws, b, 2))),
+                 ("dgrad s1", lambda: ops.conv_dgrad(h, w2, h.shape, 1, prec, mask_src=h))):
+    for fl in flag_list:  # diagnostic flags, see tapconv_halo.cu (1 weights, 2 planes, 4 epilogue, 8 cross MMAs, 16 MMAs)
+        LIB.b200np_debug_set_halo_flags(fl)
+        fn(); torch.cuda.synchronize()
+        e0, e1 = ev(), ev(); e0.record()
+        for _ in range(5): fn()
+        e1.record(); torch.cuda.synchronize()
+        print(f"{name}: flags {fl:2d}: {e0.elapsed_time(e1) / 5:.3f} ms")
+        LIB.b200np_debug_set_halo_timing(ctypes.c_void_p(dbg.data_ptr()))
+        dbg.zero_(); fn(); torch.cuda.synchronize()
+        LIB.b200np_debug_set_halo_timing(ctypes.c_void_p(0))
+        report(name, fl)
+    LIB.b200np_debug_set_halo_flags(0)

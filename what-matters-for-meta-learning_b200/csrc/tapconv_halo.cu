@@ -43,6 +43,9 @@ using namespace umma;
 // Diagnostic hooks (tools/halo_stalls.py): per-role blocked-cycle counters; nullptr in normal operation.
 static long long* g_halo_dbg = nullptr;
 static int g_halo_min_taps = 1;
+static int g_halo_flags = 0;   // diagnostics (results are garbage): 1 = no weight copies, 2 = no plane loads/stores,
+                               // 4 = no epilogue stores / mask loads, 8 = no cross-term MMAs, 16 = no MMAs
+extern "C" void b200np_debug_set_halo_flags(int f) { g_halo_flags = f; }
 extern "C" void b200np_debug_set_halo_min_taps(int n) { g_halo_min_taps = n; }
 extern "C" void b200np_debug_set_halo_timing(long long* buf) { g_halo_dbg = buf; }
 
@@ -50,6 +53,7 @@ namespace {
 
 constexpr int kTileRows = 16, kTileCols = 8;
 constexpr int kMaxPlanes = 5;
+constexpr bool kPipeProducers = false;  // two register buffers per producer thread: measured slower (register pressure)
 constexpr int kMaxBStages = 10;
 constexpr int kRot = 2;                                  // rotating accumulator blocks per accumulator set
 constexpr uint32_t kBSlotBytes = 2 * kBBytes;            // hi + lo = 16 KB
@@ -80,6 +84,7 @@ struct HaloArgs {
   int tiles_x, tiles_total;
   uint32_t plane_bytes, stage_bytes, b_off, bar_off;
   int nb;                  // weight ring depth
+  int dbg_flags;
   long long* dbg;          // optional [gridDim.x][8] stall-cycle counters
 };
 
@@ -114,7 +119,8 @@ struct Ring {
 };
 
 // MAXT = 16-byte chunk tasks per producer thread and stage (ceil(total_slots / 32))
-template <bool X3, int MAXT>
+// DBG: diagnostic build (stall counters, work-elimination flags); the production build compiles them out
+template <bool X3, int MAXT, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArgs h) {
   constexpr uint32_t kBSlot = b_slot_bytes<X3>();
   extern __shared__ uint8_t smem_raw[];
@@ -127,10 +133,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
   uint64_t* b_full = bars + 8;              // [nb] bulk copy tx -> MMA               (count 1 + tx)
   uint64_t* b_empty = b_full + kMaxBStages; // [nb] MMA commit -> weight warp         (count 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMaxBStages);
-  uint32_t* tap_tab = tmem_slot + 4;        // [ntaps][2]: {window start >> 4, descriptor high word}
   const int nb = h.nb, a_stages = h.a_stages;
 
   const TapConvArgs& a = h.t;
+  const int dflags = DBG ? h.dbg_flags : 0;
+  long long* const dbgp = DBG ? h.dbg : nullptr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kAccCols = X3 ? 256u : 128u;       // columns per accumulator set: kRot blocks of 128 | 64
   constexpr uint32_t kTmemCols = 2 * kAccCols;
@@ -175,40 +182,61 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
         }
       }
     }
-    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
+    auto load_stage = [&](int tile, int half, float4 (&v)[MAXT]) {
       const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
       const int r0 = rb * kTileRows;
       const int n = r0 / a.OH, oy0 = r0 - n * a.OH, ox0 = xt * kTileCols;
-      for (int half = 0; half < 2; ++half) {
-        const int coff = half * 32 + c * 4;
-        float4 v[MAXT];
+      const int coff = half * 32 + c * 4;
 #pragma unroll
-        for (int i = 0; i < MAXT; ++i) {
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int mt = meta[i];
-          if (mt >= 0) {
-            const Plane& P = h.pl[mt >> 16];
-            const int iy = (oy0 + P.dy_min + ((mt >> 8) & 0xff)) * P.scale + P.py;
-            const int ix = (ox0 + P.dx_min + (mt & 0xff)) * P.scale + P.px;
-            if (iy >= 0 && iy < P.srcH && ix >= 0 && ix < P.srcW)
-              v[i] = ldg4(P.src + (((long long)n * P.srcH + iy) * P.srcW + ix) * 64 + coff);
-          }
+      for (int i = 0; i < MAXT; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int mt = meta[i];
+        if (mt >= 0 && !(dflags & 2)) {
+          const Plane& P = h.pl[mt >> 16];
+          const int iy = (oy0 + P.dy_min + ((mt >> 8) & 0xff)) * P.scale + P.py;
+          const int ix = (ox0 + P.dx_min + (mt & 0xff)) * P.scale + P.px;
+          if (iy >= 0 && iy < P.srcH && ix >= 0 && ix < P.srcW)
+            v[i] = ldg4(P.src + (((long long)n * P.srcH + iy) * P.srcW + ix) * 64 + coff);
         }
-        mbar_wait_timed(a_empty + st.idx, st.phase ^ 1, dbg_a, h.dbg != nullptr);
-        uint8_t* plane_hi = smem + st.idx * h.stage_bytes;
-        uint8_t* plane_lo = plane_hi + h.plane_bytes;
-#pragma unroll
-        for (int i = 0; i < MAXT; ++i) {
-          const int slot = s0 + i * kSlotsPerPass;
-          // stage bases are 1024-aligned, so the absolute-address swizzle phase of a slot is slot & 7
-          if (slot < h.total_slots) split_store(plane_hi, plane_lo, (uint32_t)(slot * 128 + ((c ^ (slot & 7)) << 4)), v[i], X3);
-        }
-        fence_proxy_async();
-        mbar_arrive(a_full + st.idx);
-        st.advance(a_stages);
       }
+    };
+    auto store_stage = [&](float4 (&v)[MAXT]) {
+      mbar_wait_timed(a_empty + st.idx, st.phase ^ 1, dbg_a, dbgp != nullptr);
+      uint8_t* plane_hi = smem + st.idx * h.stage_bytes;
+      uint8_t* plane_lo = plane_hi + h.plane_bytes;
+#pragma unroll
+      for (int i = 0; i < MAXT; ++i) {
+        const int slot = s0 + i * kSlotsPerPass;
+        // stage bases are 1024-aligned, so the absolute-address swizzle phase of a slot is slot & 7
+        if (slot < h.total_slots && !(dflags & 2))
+          split_store(plane_hi, plane_lo, (uint32_t)(slot * 128 + ((c ^ (slot & 7)) << 4)), v[i], X3);
+      }
+      fence_proxy_async();
+      mbar_arrive(a_full + st.idx);
+      st.advance(a_stages);
+    };
+    if (kPipeProducers && MAXT <= 10) {
+      // Two register buffers: the loads of the NEXT stage are in flight while this one is converted and
+      // stored.  (With one buffer a stage cost a full DRAM round trip plus the stores, ~6K cycles, and the
+      // producers -- not the tensor core -- set the pace of the kernel.)
+      float4 v0[MAXT], v1[MAXT];
+      int tile = blockIdx.x;
+      if (tile < h.tiles_total) load_stage(tile, 0, v0);
+      for (; tile < h.tiles_total; tile += gridDim.x) {
+        load_stage(tile, 1, v1);
+        store_stage(v0);
+        if (tile + (int)gridDim.x < h.tiles_total) load_stage(tile + gridDim.x, 0, v0);
+        store_stage(v1);
+      }
+    } else {
+      float4 v[MAXT];
+      for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x)
+        for (int half = 0; half < 2; ++half) {
+          load_stage(tile, half, v);
+          store_stage(v);
+        }
     }
-    if (h.dbg && tid == 0) { h.dbg[blockIdx.x * 8 + 0] = dbg_a; h.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
+    if (dbgp && tid == 0) { dbgp[blockIdx.x * 8 + 0] = dbg_a; dbgp[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
   } else if (warp == kWeightWarp) {
     // ===================== weight producer =====================
     // (all lanes run the loop, the elected one issues: the bulk copy also takes uniform-register operands)
@@ -221,16 +249,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           for (int t = 0; t < ntaps; ++t) {
             const Tap tp = a.taps[t];
             const float* src = h.bp[tp.src] + ((long long)half * h.nslabs[tp.src] + tp.slab) * (kBSlotBytes / 4);
-            mbar_wait_timed(b_empty + bs.idx, bs.phase ^ 1, dbg_b, h.dbg != nullptr);
-            if (leader) {
-              mbar_expect_tx(b_full + bs.idx, kBSlot);
-              bulk_g2s(smem + h.b_off + bs.idx * kBSlot, src, kBSlot, b_full + bs.idx);
+            if (!(dflags & 32)) mbar_wait_timed(b_empty + bs.idx, bs.phase ^ 1, dbg_b, dbgp != nullptr);
+            if (leader && !(dflags & 64)) {
+              if (dflags & 1) {
+                mbar_arrive(b_full + bs.idx);
+              } else {
+                mbar_expect_tx(b_full + bs.idx, kBSlot);
+                bulk_g2s(smem + h.b_off + bs.idx * kBSlot, src, kBSlot, b_full + bs.idx);
+              }
             }
             bs.advance(nb);
           }
         }
       }
-      if (h.dbg && leader) h.dbg[blockIdx.x * 8 + 2] = dbg_b;
+      if (dbgp && leader) dbgp[blockIdx.x * 8 + 2] = dbg_b;
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
@@ -245,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       int acc_set = 0;
       uint32_t acc_phase = 0;
       long long w_acc = 0, w_a = 0, w_b = 0;
-      const bool timed = h.dbg != nullptr;
+      const bool timed = dbgp != nullptr;
       const long long t_start = clock64();
       const uint32_t plane16 = h.plane_bytes >> 4;
       const uint32_t lbo_bits = 1u << 16;                 // LBO field (ignored for swizzled K-major; 1 by convention)
@@ -270,28 +302,32 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
         int kb = 0;
         for (int half = 0; half < 2; ++half) {
           mbar_wait_timed(a_full + st.idx, st.phase, w_a, timed);
-          tc_fence_after();
+          if (dflags & 128) tc_fence_after();  // not needed: the planes were published with fence.proxy.async
           const uint32_t stage16 = (smem_u32(smem + st.idx * h.stage_bytes) & 0x3FFFFu) >> 4;
           for (int t = 0; t < ntaps; ++t, ++kb) {
             const uint32_t a16 = stage16 + (uint32_t)h.tap_off[t] * 8u;  // slots -> 16-byte units
             const uint32_t a_hi_word = (((uint32_t)h.tap_hc[t] * 128u) >> 4) | (1u << 14) | (2u << 29);  // SBO, v1, SW128
             const uint32_t ah = a16 | lbo_bits, al = (a16 + plane16) | lbo_bits;
             const uint32_t bh = (b_base16 + bs.idx * (kBSlot >> 4)) | lbo_bits;
-            mbar_wait_timed(b_full + bs.idx, bs.phase, w_b, timed);
-            tc_fence_after();
+            if (!(dflags & 64)) mbar_wait_timed(b_full + bs.idx, bs.phase, w_b, timed);
+            if (dflags & 128) tc_fence_after();  // not needed: bulk-copy (async proxy) data
             const uint32_t d_blk = d0 + rot * (X3 ? 128u : 64u);
             const uint32_t acc_first = kb >= kRot;
             if (leader) {
               if (X3) {
+                if (!(dflags & 16)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescN128);
+                  for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescN128);
+                }
+                if (!(dflags & 24)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma(d_blk + 64, al + 2 * k, a_hi_word, bh + 2 * k, 1u, kIdescTf32_128x64);
+                  for (int k = 0; k < 4; ++k) mma(d_blk + 64, al + 2 * k, a_hi_word, bh + 2 * k, 1u, kIdescTf32_128x64);
+                }
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescTf32_128x64);
               }
-              umma_commit(b_empty + bs.idx);
+              if (!(dflags & 32)) umma_commit(b_empty + bs.idx);
             }
             bs.advance(nb);
             if (++rot == kRot) rot = 0;
@@ -303,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
         if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
       }
       if (timed && leader) {
-        long long* o = h.dbg + blockIdx.x * 8;
+        long long* o = dbgp + blockIdx.x * 8;
         o[3] = w_acc; o[4] = w_a; o[5] = w_b; o[6] = clock64() - t_start;
       }
     }
@@ -322,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       const int n = r0 / a.OH, oy = r0 - n * a.OH + (m >> 3), ox = xt * kTileCols + (m & 7);
       const long long off =
           (((long long)n * a.dstH + (long long)oy * a.dst_s + a.dst_oy) * a.dstW + (long long)ox * a.dst_s + a.dst_ox) * 64;
-      mbar_wait_timed(acc_full + acc_set, acc_phase, w_e, h.dbg != nullptr);
+      mbar_wait_timed(acc_full + acc_set, acc_phase, w_e, dbgp != nullptr);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc_set * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
@@ -365,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             const float4 b = ldg4(a.bias2 + c);
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
-          if (a.mask) {
+          if (a.mask && !(dflags & 4)) {
             const float4 mk = ldg4(a.mask + off + c);
             o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
             o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
@@ -373,12 +409,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           if (a.act == B200NP_ACT_RELU) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
           }
-          *reinterpret_cast<float4*>(a.dst + off + c) = o;
+          if (!(dflags & 4) || o.x == 12345.678f) *reinterpret_cast<float4*>(a.dst + off + c) = o;
         }
       }
       if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
     }
-    if (h.dbg && warp == kEpiWarp0 && lane == 0) h.dbg[blockIdx.x * 8 + 7] = w_e;
+    if (dbgp && warp == kEpiWarp0 && lane == 0) dbgp[blockIdx.x * 8 + 7] = w_e;
   }
 
   tc_fence_before();
@@ -392,13 +428,16 @@ template <bool X3, int MAXT>
 int launch_halo_t(const HaloArgs& h, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
-    if (cudaFuncSetAttribute(tapconv_halo_kernel<X3, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(tapconv_halo_kernel<X3, MAXT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(tapconv_halo_kernel<X3, MAXT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
       return B200NP_E_LAUNCH;
     configured = smem;
   }
   int grid = h.tiles_total < kNumSMs ? h.tiles_total : kNumSMs;
-  tapconv_halo_kernel<X3, MAXT><<<grid, kThreads, smem, st>>>(h);
+  if (h.dbg || h.dbg_flags) tapconv_halo_kernel<X3, MAXT, true><<<grid, kThreads, smem, st>>>(h);
+  else tapconv_halo_kernel<X3, MAXT, false><<<grid, kThreads, smem, st>>>(h);
   return launch_status();
 }
 
@@ -408,7 +447,7 @@ int launch_halo(HaloArgs& h, cudaStream_t st) {
   const uint32_t planes = X3 ? 2u : 1u;
   h.plane_bytes = (uint32_t)h.total_slots * 128u;
   h.stage_bytes = planes * h.plane_bytes;
-  const uint32_t tail = 1024 /*alignment slack*/ + 512 /*barriers + tap table*/;
+  const uint32_t tail = 1024 /*alignment slack*/ + 1024 /*barriers + plane table*/;
   const uint32_t bslot = b_slot_bytes<X3>();
   h.a_stages = (2 * h.stage_bytes + 2 * bslot + tail <= kSmemBudget) ? 2 : 1;
   if (h.a_stages * h.stage_bytes + 2 * bslot + tail > kSmemBudget) return B200NP_E_UNSUPPORTED;
@@ -437,6 +476,7 @@ int launch_tapconv_halo(const TapConvArgs& a, const float* bp0, int nslabs0, con
   HaloArgs h{};
   h.t = a;
   h.dbg = g_halo_dbg;
+  h.dbg_flags = g_halo_flags;
   h.bp[0] = bp0; h.bp[1] = bp1; h.nslabs[0] = nslabs0; h.nslabs[1] = nslabs1;
   // group the taps into planes: (source, row parity, column parity) for a stride-2 source, one plane otherwise
   struct Key { int src, py, px; } keys[kMaxPlanes];
