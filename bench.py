@@ -270,13 +270,34 @@ def run_b200_arm(args, rank, world, local_rank):
     finish()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at exactly the size
+# timed below, from `ncu --set full` (profiles/ncu_tapwgrad_r1.txt); None until captured for this size.
+NCU_TRAFFIC_BYTES = {"tapwgrad": None, "tapconv_halo": None}
+
+
+def _time_kernel(run, reps=10):
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 1e3 / reps
+
+
 def dominant_kernel_roofline(args, dev):
-    """Times the dominant kernel of the step alone, with CUDA events on the launching stream: the
-    fused `conv2 3x3 s1 + 1x1 s2 skip projection + bias + ReLU` implicit GEMM of layer1 at the step's
-    own size (all 1140 images of a 20-task ANP step: M = 1140*32*32 pixels, N = 64, K = 640).
+    """Times the dominant kernel of the step alone, with CUDA events on the launching stream (torch's current
+    stream, which is the one the C ABI is given).  By CUPTI kernel time (profiles/profile_step_r1.txt) the
+    dominant kernel is the tcgen05 weight gradient `tapwgrad_umma_kernel` (28% of the step); it is timed on its
+    largest instance, the fused `conv2 3x3 + 1x1 s2 skip` weight gradient of layer1 at the step's own size
+    (all 1140 images of a 20-task ANP step: contraction over M = 1140*32*32 pixels, 64 x 640 outputs).
     Algorithmic FLOPs = 2*M*64*640 per launch (75.5 + 8.4 MFLOP/image).
-    Peak = measured dense bf16 / 2 (tf32 issues at half the bf16 rate); the 3-pass fp32-grade split
-    spends 3 MMAs per algorithmic MAC, so its ceiling on this scale is 1/3."""
+    Peak = measured dense bf16 / 2 (tf32 issues at half the bf16 rate); the fp32-grade 3xTF32 split spends
+    3 MMAs per algorithmic MAC, so its ceiling on this scale is 1/3.  The forward kernel of the same layer
+    (`tapconv_halo_kernel`, second by time) is reported beside it."""
     from b200np import ops
     from b200np.lib import PREC_FP32_SIMT, PREC_TF32, PREC_TF32X3
     prec = {"tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "fp32": PREC_FP32_SIMT}[args.precision]
@@ -284,34 +305,35 @@ def dominant_kernel_roofline(args, dev):
     g = torch.Generator(device="cpu").manual_seed(0)
     x = torch.rand(N, 64, 64, 64, generator=g).to(dev)          # block input  (NHWC)
     h = torch.rand(N, 32, 32, 64, generator=g).to(dev)          # conv1 output (NHWC)
+    dy = torch.randn(N, 32, 32, 64, generator=g).to(dev)        # gradient of the block output
     w2 = (torch.randn(64, 64, 3, 3, generator=g) * 0.04).to(dev)
     ws = (torch.randn(64, 64, 1, 1, generator=g) * 0.1).to(dev)
     b = torch.zeros(64, device=dev)
     wf2 = ops.pack_conv_weight(w2)
     wfs = ops.pack_conv_weight(ws)
-    run = lambda: ops.conv_fwd(h, wf2, b, 1, 1, prec, skip=(x, wfs, b, 2))
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    reps = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) / 1e3 / reps
     flops = 2.0 * N * 32 * 32 * 64 * 640
+    alg_bytes = (h.numel() + x.numel() + N * 32 * 32 * 64) * 4   # both kernels: h, x and one 32x32x64 tensor
     pk = peaks()
     peak = pk["bf16"] / 2.0
-    ach = flops / sec / 1e12
-    alg_bytes = (h.numel() + x.numel() + N * 32 * 32 * 64) * 4
-    return {"kernel": "tapconv (layer1 conv2 3x3 + 1x1 skip + bias + ReLU, implicit GEMM on tcgen05)",
-            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "peak_source": f"{pk['src']} bf16 burst {pk['bf16']} TFLOP/s / 2 (tf32 rate)",
-            "traffic": None, "launch_ms": sec * 1e3,
-            "hbm_view": {"algorithmic_GB": alg_bytes / 1e9, "achieved_GBps": alg_bytes / sec / 1e9,
-                         "peak_GBps": pk["hbm"], "frac": alg_bytes / sec / 1e9 / pk["hbm"]}}
+
+    def entry(name, key, sec):
+        ach = flops / sec / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "peak_source": f"{pk['src']} bf16 burst {pk['bf16']} TFLOP/s / 2 (tf32 rate)",
+                "traffic": NCU_TRAFFIC_BYTES[key], "launch_ms": sec * 1e3,
+                "hbm_view": {"algorithmic_GB": alg_bytes / 1e9, "achieved_GBps": alg_bytes / sec / 1e9,
+                             "peak_GBps": pk["hbm"], "frac": alg_bytes / sec / 1e9 / pk["hbm"]}}
+
+    if prec == PREC_FP32_SIMT:
+        t_w = _time_kernel(lambda: ops.conv_wgrad(h, dy, 3, 1, prec))
+    else:
+        t_w = _time_kernel(lambda: ops.conv_wgrad(h, dy, 3, 1, prec, skip=(x, 2)))
+    t_f = _time_kernel(lambda: ops.conv_fwd(h, wf2, b, 1, 1, prec, skip=(x, wfs, b, 2)))
+    out = entry("tapwgrad_umma (layer1 conv2 3x3 + 1x1 skip weight gradient, pixel contraction on tcgen05)",
+                "tapwgrad", t_w)
+    out["second_kernel"] = entry("tapconv_halo (layer1 conv2 3x3 + 1x1 skip + bias + ReLU forward, implicit GEMM "
+                                 "on tcgen05)", "tapconv_halo", t_f)
+    return out
 
 
 def main():
@@ -325,6 +347,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel from Python each step instead of replaying the captured CUDA graph")
+    ap.add_argument("--roofline-only", action="store_true",
+                    help="run only the dominant-kernel timing (the command captured by `ncu --set full`)")
     ap.add_argument("--profile", action="store_true",
                     help="only the resident-input timed loop (for ncu launch lists); skips e2e / roofline / CPU legs")
     args = ap.parse_args()
@@ -333,6 +357,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.roofline_only:
+        print(json.dumps(dominant_kernel_roofline(args, torch.device("cuda:0"))))
         return
     if args.profile:
         args.graph = False  # ncu needs the individual launches

@@ -265,21 +265,18 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  // A gather role: (tap_local, pixel k, channel half) -> 128 contiguous bytes
-  const int a_tl = tid >> 6, a_k = (tid >> 1) & 31, a_half = tid & 1;
-  const int a_tap = pair * 2 + a_tl;
-  const bool a_tap_ok = a_tap < a.ntaps;
-  const Tap tp = a.taps[a_tap_ok ? a_tap : 0];
-  // B gather role: (pixel k, channel half, 64-byte sub-half)
-  const int b_k = tid >> 2, b_half = (tid >> 1) & 1, b_sub = tid & 1;
-
+  // Gather roles.  The 16 lanes of a half-warp walk the 16 consecutive 16-byte chunks of ONE pixel (256 B),
+  // so a warp-wide load touches 4 full 128-byte lines.  (With a thread per 128-byte half-pixel every load
+  // touched 32 different lines = 32 wavefronts of the L1 data pipe, and that pipe -- shared with the
+  // shared-memory stores and the tensor core's operand reads -- was 92% busy: the kernel's bound.)
+  // thread = (chunk g_c of pixels g_k + 8 i, i = 0..3); A: both taps of the pair, B: dY.
+  const int g_c = tid & 15, g_k = tid >> 4;
+  const int t0 = pair * 2, t1 = pair * 2 + 1;
+  const bool t1_ok = t1 < a.ntaps;
+  const Tap tpa = a.taps[t0], tpb = a.taps[t1_ok ? t1 : t0];
   const long long KB = p_begin < p_end ? ((p_end - p_begin + kWgK - 1) / kWgK) : 0;
-  // source of this thread's tap (the fused skip projection reads a second tensor at its own stride)
-  const float* a_src = tp.src ? a.src2 : a.src;
-  const int a_H = tp.src ? a.src2H : a.srcH, a_W = tp.src ? a.src2W : a.srcW, a_s = tp.src ? a.in_s2 : a.in_s;
-  // fetches run over consecutive K-blocks: walk (n, oy, ox) of this thread's pixel incrementally
-  // (two 64-bit divisions per K-block were a large share of the producers' instructions)
-  long long f_p = p_begin + a_k, f_n;
+  // fetches run over consecutive K-blocks: walk (n, oy, ox) of pixel g_k incrementally (no divisions)
+  long long f_p = p_begin + g_k, f_n;
   int f_ox, f_oy;
   {
     f_ox = (int)(f_p % a.OW);
@@ -287,39 +284,34 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
     f_oy = (int)(q % a.OH);
     f_n = q / a.OH;
   }
-  long long f_pb = p_begin + b_k;
   float4 av0[8], bv0[4], av1[8], bv1[4];
+  auto gather = [&](const Tap& tp, bool tap_ok, bool pix_ok, int oy, int ox, long long n) -> float4 {
+    // source of the tap (the fused skip projection reads a second tensor at its own stride)
+    const float* src = tp.src ? a.src2 : a.src;
+    const int sH = tp.src ? a.src2H : a.srcH, sW = tp.src ? a.src2W : a.srcW, ss = tp.src ? a.in_s2 : a.in_s;
+    const int iy = oy * ss + tp.dy, ix = ox * ss + tp.dx;
+    if (tap_ok && pix_ok && iy >= 0 && iy < sH && ix >= 0 && ix < sW)
+      return ldg4(src + ((n * sH + iy) * sW + ix) * 64 + g_c * 4);
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  };
   auto fetch = [&](long long, float4 (&av)[8], float4 (&bv)[4]) {
-    {
-      bool ok = a_tap_ok && f_p < p_end;
-      const int iy = f_oy * a_s + tp.dy, ix = f_ox * a_s + tp.dx;
-      ok = ok && iy >= 0 && iy < a_H && ix >= 0 && ix < a_W;
-      if (ok) {
-        const float* ap = a_src + ((f_n * a_H + iy) * a_W + ix) * 64 + a_half * 32;
+    int ox = f_ox, oy = f_oy;
+    long long n = f_n;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) av[c] = ldg4(ap + 4 * c);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      f_p += kWgK;
-      f_ox += kWgK;
-      while (f_ox >= a.OW) {
-        f_ox -= a.OW;
-        if (++f_oy == a.OH) { f_oy = 0; ++f_n; }
+    for (int i = 0; i < 4; ++i) {
+      const long long p = f_p + 8 * i;
+      const bool pix_ok = p < p_end;
+      av[i] = gather(tpa, true, pix_ok, oy, ox, n);
+      av[4 + i] = gather(tpb, t1_ok, pix_ok, oy, ox, n);
+      bv[i] = pix_ok ? ldg4(a.dy + p * 64 + g_c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ox += 8;
+      while (ox >= a.OW) {
+        ox -= a.OW;
+        if (++oy == a.OH) { oy = 0; ++n; }
       }
     }
-    {
-      if (f_pb < p_end) {
-        const float* bp = a.dy + f_pb * 64 + b_half * 32 + b_sub * 16;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) bv[c] = ldg4(bp + 4 * c);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) bv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      f_pb += kWgK;
-    }
+    f_p += kWgK;  // after four steps of 8 the walk stands at pixel g_k of the next K-block
+    f_ox = ox; f_oy = oy; f_n = n;
   };
 
   if (KB > 0) fetch(0, av0, bv0);
@@ -333,18 +325,13 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
     uint8_t* a_lo = st + kWgABytes;
     uint8_t* b_hi = st + (X3 ? 2 : 1) * kWgABytes;
     uint8_t* b_lo = b_hi + kWgBBytes;
-    // The eight threads of a quarter-warp cover four pixel rows (four 32-byte swizzle units) and both channel
-    // halves; the halves are 4096 B apart, i.e. the same banks.  The odd half therefore walks its 16-byte chunks
-    // in swapped order (c ^ 1), which makes every quarter-warp store hit all 32 banks.
+    // a quarter-warp holds the eight chunks of one 32-channel block of one pixel: all 32 banks, no conflicts
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 v = a_half ? av[c ^ 1] : av[c];
-      split_store(a_hi, a_lo, mn_offset(a_tl * 2 + a_half, a_k, c) ^ (uint32_t)(a_half << 4), v, X3);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float4 v = b_half ? bv[c ^ 1] : bv[c];
-      split_store(b_hi, b_lo, mn_offset(b_half, b_k, b_sub * 4 + c) ^ (uint32_t)(b_half << 4), v, X3);
+    for (int i = 0; i < 4; ++i) {
+      const int k = g_k + 8 * i;
+      split_store(a_hi, a_lo, mn_offset((g_c >> 3), k, g_c & 7), av[i], X3);
+      split_store(a_hi, a_lo, mn_offset(2 + (g_c >> 3), k, g_c & 7), av[4 + i], X3);
+      split_store(b_hi, b_lo, mn_offset((g_c >> 3), k, g_c & 7), bv[i], X3);
     }
     fence_proxy_async();
     __syncthreads();
