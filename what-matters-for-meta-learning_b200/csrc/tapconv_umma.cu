@@ -213,6 +213,7 @@ int launch(const TapConvArgs& a, cudaStream_t st) {
 // descriptor start advances by 1024 B per k-step.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgK = 32;                             // pixels per K-block
+constexpr int kWgThreads = 256;
 constexpr uint32_t kWgABytes = 128 * kWgK * 4;        // 16 KB : 4 channel blocks x 4 pixel groups x 1 KB
 constexpr uint32_t kWgBBytes = 64 * kWgK * 4;         //  8 KB : 2 channel blocks x 4 pixel groups x 1 KB
 constexpr uint32_t kIdescTf32_128x64_MN = kIdescTf32_128x64 | (1u << 15) | (1u << 16);  // a_major = b_major = MN
@@ -235,7 +236,7 @@ __device__ __forceinline__ uint32_t mn_offset(int cblock, int k, int chunk) {
 }
 
 template <bool X3>
-__global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArgs a) {
+__global__ void __launch_bounds__(kWgThreads, 2) tapwgrad_umma_kernel(const TapWgradArgs a) {
   constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kWgABytes + kWgBBytes);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -269,8 +270,14 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
   // so a warp-wide load touches 4 full 128-byte lines.  (With a thread per 128-byte half-pixel every load
   // touched 32 different lines = 32 wavefronts of the L1 data pipe, and that pipe -- shared with the
   // shared-memory stores and the tensor core's operand reads -- was 92% busy: the kernel's bound.)
-  // thread = (chunk g_c of pixels g_k + 8 i, i = 0..3); A: both taps of the pair, B: dY.
+  // thread = (chunk g_c of pixels g_k + 16 i, i = 0..1); A: both taps of the pair, B: dY.  256 threads: the
+  // gather is a chain of dependent address arithmetic, so it is the number of warps per scheduler (4 with
+  // two CTAs per SM) that hides it.
   const int g_c = tid & 15, g_k = tid >> 4;
+  // shared-memory offsets of this thread's chunks do not depend on the K-block
+  uint32_t g_off[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) g_off[i] = mn_offset(g_c >> 3, g_k + 16 * i, g_c & 7);
   const int t0 = pair * 2, t1 = pair * 2 + 1;
   const bool t1_ok = t1 < a.ntaps;
   const Tap tpa = a.taps[t0], tpb = a.taps[t1_ok ? t1 : t0];
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
     f_oy = (int)(q % a.OH);
     f_n = q / a.OH;
   }
-  float4 av0[8], bv0[4], av1[8], bv1[4];
+  float4 av0[4], bv0[2], av1[4], bv1[2];
   auto gather = [&](const Tap& tp, bool tap_ok, bool pix_ok, int oy, int ox, long long n) -> float4 {
     // source of the tap (the fused skip projection reads a second tensor at its own stride)
     const float* src = tp.src ? a.src2 : a.src;
@@ -294,29 +301,29 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
       return ldg4(src + ((n * sH + iy) * sW + ix) * 64 + g_c * 4);
     return make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  auto fetch = [&](long long, float4 (&av)[8], float4 (&bv)[4]) {
+  auto fetch = [&](long long, float4 (&av)[4], float4 (&bv)[2]) {
     int ox = f_ox, oy = f_oy;
     long long n = f_n;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long p = f_p + 8 * i;
+    for (int i = 0; i < 2; ++i) {
+      const long long p = f_p + 16 * i;
       const bool pix_ok = p < p_end;
       av[i] = gather(tpa, true, pix_ok, oy, ox, n);
-      av[4 + i] = gather(tpb, t1_ok, pix_ok, oy, ox, n);
+      av[2 + i] = gather(tpb, t1_ok, pix_ok, oy, ox, n);
       bv[i] = pix_ok ? ldg4(a.dy + p * 64 + g_c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      ox += 8;
+      ox += 16;
       while (ox >= a.OW) {
         ox -= a.OW;
         if (++oy == a.OH) { oy = 0; ++n; }
       }
     }
-    f_p += kWgK;  // after four steps of 8 the walk stands at pixel g_k of the next K-block
+    f_p += kWgK;  // after two steps of 16 the walk stands at pixel g_k of the next K-block
     f_ox = ox; f_oy = oy; f_n = n;
   };
 
   if (KB > 0) fetch(0, av0, bv0);
   if (KB > 1) fetch(1, av1, bv1);
-  auto step = [&](long long kb, float4 (&av)[8], float4 (&bv)[4]) {
+  auto step = [&](long long kb, float4 (&av)[4], float4 (&bv)[2]) {
     const int s = (int)(kb % kStages);
     const long long use = kb / kStages;
     if (use >= 1) mbar_wait(bars + s, (uint32_t)((use - 1) & 1));
@@ -327,11 +334,10 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
     uint8_t* b_lo = b_hi + kWgBBytes;
     // a quarter-warp holds the eight chunks of one 32-channel block of one pixel: all 32 banks, no conflicts
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = g_k + 8 * i;
-      split_store(a_hi, a_lo, mn_offset((g_c >> 3), k, g_c & 7), av[i], X3);
-      split_store(a_hi, a_lo, mn_offset(2 + (g_c >> 3), k, g_c & 7), av[4 + i], X3);
-      split_store(b_hi, b_lo, mn_offset((g_c >> 3), k, g_c & 7), bv[i], X3);
+    for (int i = 0; i < 2; ++i) {
+      split_store(a_hi, a_lo, g_off[i], av[i], X3);
+      split_store(a_hi, a_lo, g_off[i] + 2 * 4096, av[2 + i], X3);  // second tap: channel blocks 2, 3
+      split_store(b_hi, b_lo, g_off[i], bv[i], X3);
     }
     fence_proxy_async();
     __syncthreads();
@@ -363,18 +369,19 @@ __global__ void __launch_bounds__(128, 2) tapwgrad_umma_kernel(const TapWgradArg
     if (kb + 1 < KB) step(kb + 1, av1, bv1);
   }
 
-  // epilogue: thread (warp w, lane l) holds row m = 32w + l = tap_local*64 + ci, 64 couts
-  const int tl = warp >> 1, ci = (warp & 1) * 32 + lane;
+  // epilogue: warps w and w + 4 share TMEM lane quarter w % 4 (rows m = 32 (w % 4) + l = tap_local*64 + ci)
+  // and take 32 of the 64 cout columns each
+  const int q4 = warp & 3, half = warp >> 2;
+  const int tl = q4 >> 1, ci = (q4 & 1) * 32 + lane;
   const int tap = pair * 2 + tl;
   if (KB > 0) {
     mbar_wait(bars + kStages, 0);
     tc_fence_after();
   }
   {
-    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q4 * 32) << 16);
     float* po = a.part + ((long long)chunk * a.ntaps + (tap < a.ntaps ? tap : 0)) * 64 * 64 + ci;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    {
       float acc[32];
       if (KB > 0) {
         if (X3) {  // cross-term columns first (smallest magnitude), then the main products, both blocks
@@ -422,7 +429,7 @@ int launch_wgrad(const TapWgradArgs& a, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((a.ntaps + 1) / 2, a.chunks);  // pair fastest: the CTAs that share a pixel chunk run together and share it in L2
-  tapwgrad_umma_kernel<X3><<<grid, 128, smem, st>>>(a);
+  tapwgrad_umma_kernel<X3><<<grid, kWgThreads, smem, st>>>(a);
   return launch_status();
 }
 
