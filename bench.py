@@ -271,8 +271,9 @@ def run_b200_arm(args, rank, world, local_rank):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at exactly the size
-# timed below, from `ncu --set full` (profiles/ncu_tapwgrad_r1.txt); None until captured for this size.
-NCU_TRAFFIC_BYTES = {"tapwgrad": None, "tapconv_halo": None}
+# timed below, from `ncu --set full` of `bench.py --roofline-only` (profiles/ncu_tapwgrad_r1.txt,
+# profiles/ncu_tapconv_halo_r1.txt).
+NCU_TRAFFIC_BYTES = {"tapwgrad": 941.2e6, "tapconv_halo": 863.2e6}
 
 
 def _time_kernel(run, reps=10):
@@ -312,7 +313,9 @@ def dominant_kernel_roofline(args, dev):
     wf2 = ops.pack_conv_weight(w2)
     wfs = ops.pack_conv_weight(ws)
     flops = 2.0 * N * 32 * 32 * 64 * 640
-    alg_bytes = (h.numel() + x.numel() + N * 32 * 32 * 64) * 4   # both kernels: h, x and one 32x32x64 tensor
+    # both kernels touch h, every second pixel of every second row of x (the stride-2 skip) and one more
+    # 32x32x64 tensor (dY or the output): 3 x 299 MB
+    alg_bytes = (h.numel() + x.numel() // 4 + N * 32 * 32 * 64) * 4
     pk = peaks()
     peak = pk["bf16"] / 2.0
 
