@@ -163,6 +163,8 @@ typedef struct b200np_gemm_desc {
   int precision;
   void* workspace;        /* optional split-K scratch (b200np_gemm_workspace bytes); NULL: single pass */
   size_t workspace_bytes;
+  int sum_groups;         /* nonzero: the groups are concatenated along K into ONE product,
+                             C_0 = act(alpha * sum_g sum_k A_g(m,k) B_g(k,n) + ...)  (K % 32 == 0) */
 } b200np_gemm_desc;
 /* bytes of scratch with which b200np_gemm spreads the K range of a GEMM with few output tiles over the idle
  * SMs (deterministic: partial tiles are reduced in a fixed order); 0 when the shape does not profit */

@@ -312,3 +312,22 @@ def test_favor_attention_fwd_bwd(prec, T, H, nt, nc, d):
     assert rel(from_rows(v_g.grad, nc), dv_ref) < 2e-5
     assert rel(from_rows(k_g.grad, nc), dk_ref) < 2e-3
     assert rel(from_rows(q_g.grad, nt), dq_ref) < 2e-2
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("rows,H,d,K", [(300, 8, 256, 256), (37, 3, 64, 96)])
+def test_gemm_sum_groups(prec, rows, H, d, K):
+    """dX = sum_h dY[:, h*d:(h+1)*d] @ W_h (the per-head AttnLinear data gradient, ANPDistractor.py:83-96) as ONE
+    product whose K dimension runs over the groups."""
+    ops = _ops()
+    from b200np import lib
+    P = {"fp32": lib.PREC_FP32_SIMT, "tf32x3": lib.PREC_TF32X3, "tf32": lib.PREC_TF32}[prec]
+    dy = rnd(rows, H * d, seed=11)
+    ws = [rnd(d, K, seed=20 + h, scale=0.1) for h in range(H)]
+    ref = sum(dy[:, h * d:(h + 1) * d] @ ws[h] for h in range(H))
+    dyc = dy.float().cuda()
+    wc = [w.float().cuda() for w in ws]
+    dx = torch.full((rows, K), float("nan"), device="cuda")
+    ops.gemm([dyc.data_ptr() + 4 * h * d for h in range(H)], [w.data_ptr() for w in wc], [dx.data_ptr()] * H,
+             rows, K, d, H * d, 1, K, 1, K, prec=P, sum_groups=True)
+    assert rel(dx, ref) < (2e-3 if prec == "tf32" else 3e-6)

@@ -257,10 +257,9 @@ class HeadsLinearFn(Function):
         db = ops.colsum(dy, rows, H * d, H * d)
         dx = None
         if ctx.needs_input_grad[1]:
-            dx = torch.empty_like(x)
-            for h in range(H):
-                ops.gemm(_p(dy, h * d), _p(ws[h]), _p(dx), rows, K, d, H * d, 1, K, 1, K, beta=0.0 if h == 0 else 1.0,
-                         prec=prec)
+            dx = torch.empty_like(x)  # dX = sum_h dY_h W_h: the heads are K-slices of one product
+            ops.gemm([_p(dy, h * d) for h in range(H)], [_p(w) for w in ws], [_p(dx)] * H, rows, K, d, H * d, 1, K, 1, K,
+                     prec=prec, sum_groups=True)
         return (None, dx) + tuple(dw[h] for h in range(H)) + tuple(db[h * d:(h + 1) * d] for h in range(H))
 
 

@@ -21,7 +21,7 @@ class GemmDesc(C.Structure):
                 ("M", _i), ("N", _i), ("K", _i), ("a_rs", _ll), ("a_cs", _ll), ("b_rs", _ll),
                 ("b_cs", _ll), ("ldc", _ll), ("alpha", _f), ("beta", _f), ("act", _i),
                 ("row_scale", _p), ("addend", _p), ("ld_add", _ll), ("precision", _i),
-                ("workspace", _p), ("workspace_bytes", _sz)]
+                ("workspace", _p), ("workspace_bytes", _sz), ("sum_groups", _i)]
 
 
 # name: (restype, [argtypes])  -- one entry per symbol in include/b200np.h

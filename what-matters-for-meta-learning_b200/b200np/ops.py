@@ -198,8 +198,9 @@ def maxpool2x2_bwd(dy, idx, x_saved):
 # GEMM and friends
 # ----------------------------------------------------------------------------------------------
 def gemm(A, B, Cmat, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, bias=None, alpha=1.0, beta=0.0, act=lib.ACT_NONE,
-         row_scale=None, addend=None, ld_add=0, prec=lib.PREC_FP32_SIMT):
-    """A, B, Cmat, bias: device pointers (ints) or lists of up to 8 of them (grouped)."""
+         row_scale=None, addend=None, ld_add=0, prec=lib.PREC_FP32_SIMT, sum_groups=False):
+    """A, B, Cmat, bias: device pointers (ints) or lists of up to 8 of them (grouped).  sum_groups: the groups
+    are K-slices of one product written to Cmat[0]."""
     d = GemmDesc()
     As = A if isinstance(A, (list, tuple)) else [A]
     Bs = B if isinstance(B, (list, tuple)) else [B]
@@ -215,7 +216,7 @@ def gemm(A, B, Cmat, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, bias=None, alpha=1.0,
     d.row_scale = 0 if row_scale is None else row_scale.data_ptr()
     d.addend = 0 if addend is None else addend.data_ptr()
     d.ld_add, d.precision = ld_add, prec
-    d.workspace, d.workspace_bytes = 0, 0
+    d.workspace, d.workspace_bytes, d.sum_groups = 0, 0, int(sum_groups)
     ws_bytes = LIB.b200np_gemm_workspace(C.byref(d))
     if ws_bytes:  # split-K scratch for the GEMMs with too few output tiles to fill the chip
         ws = torch.empty(ws_bytes // 4, device="cuda", dtype=F32)

@@ -195,6 +195,24 @@ extern "C" int b200np_gemm(const b200np_gemm_desc* dp, void* stream) {
     int rc = launch_gemm_umma(g.d, g.a_vec, g.b_vec, as_stream(stream));
     if (rc != B200NP_E_UNSUPPORTED) return rc;
   }
+  if (d.sum_groups) {  // CUDA-core path: one accumulating launch per K-slice, epilogue on the last
+    for (int i = 0; i < d.groups; ++i) {
+      GemmArgs gi = g;
+      const bool last = i == d.groups - 1;
+      gi.d.groups = 1;
+      gi.d.sum_groups = 0;
+      gi.d.A[0] = d.A[i]; gi.d.B[0] = d.B[i]; gi.d.C[0] = d.C[0];
+      gi.d.bias[0] = last ? d.bias[0] : nullptr;
+      gi.d.act = last ? d.act : B200NP_ACT_NONE;
+      gi.d.row_scale = last ? d.row_scale : nullptr;
+      gi.d.beta = i == 0 ? d.beta : 1.f;
+      dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, 1);
+      gemm_kernel<<<grid, 128, 0, as_stream(stream)>>>(gi);
+      int rc = launch_status();
+      if (rc != B200NP_OK) return rc;
+    }
+    return B200NP_OK;
+  }
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.groups);
   gemm_kernel<<<grid, 128, 0, as_stream(stream)>>>(g);
   return launch_status();

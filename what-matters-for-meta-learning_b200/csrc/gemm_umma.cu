@@ -63,9 +63,9 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
   const b200np_gemm_desc& d = g.d;
-  const int grp = blockIdx.z / g.splits, sp = blockIdx.z - grp * g.splits;
-  const float* __restrict__ A = d.A[grp];
-  const float* __restrict__ B = d.B[grp];
+  // sum_groups: the groups are K-slices of one product (group pointers switch inside the K loop)
+  const int grp = d.sum_groups ? 0 : blockIdx.z / g.splits;
+  const int sp = d.sum_groups ? blockIdx.z : blockIdx.z - grp * g.splits;
   float* __restrict__ C = d.C[grp];
   const float* __restrict__ bias = d.bias[grp];
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -90,13 +90,18 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
   const uint32_t tmem_d = *tmem_slot;
 
   // this CTA's K-block range (split-K: the small dense layers have 16 output tiles for 148 SMs)
-  const int KB_all = (K + 31) / 32;
+  const int KB_grp = (K + 31) / 32;                       // K-blocks per group
+  const int KB_all = d.sum_groups ? KB_grp * d.groups : KB_grp;
   const int kb_per = (KB_all + g.splits - 1) / g.splits;
   const int kb_lo = sp * kb_per;
   const int KB = KB_all - kb_lo < kb_per ? (KB_all - kb_lo > 0 ? KB_all - kb_lo : 0) : kb_per;
   float4 av0[8], bv0[4], av1[8], bv1[4];
   auto fetch = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
-    const int k0 = (kb_lo + kb) * 32;
+    const int kbt = kb_lo + kb;
+    const int gsel = d.sum_groups ? kbt / KB_grp : grp;
+    const int k0 = (kbt - (d.sum_groups ? gsel * KB_grp : 0)) * 32;
+    const float* __restrict__ A = d.A[gsel];
+    const float* __restrict__ B = d.B[gsel];
     if (AK) {  // thread = row m0+tid, 32 consecutive k
       const int m = m0 + tid;
       const float* p = A + (long long)m * d.a_rs + k0;
@@ -230,7 +235,7 @@ int launch(const GemmUArgs& g, cudaStream_t st) {
       return B200NP_E_LAUNCH;
     configured = true;
   }
-  dim3 grid((g.d.M + 127) / 128, (g.d.N + 63) / 64, g.d.groups * g.splits);
+  dim3 grid((g.d.M + 127) / 128, (g.d.N + 63) / 64, (g.d.sum_groups ? 1 : g.d.groups) * g.splits);
   gemm_umma_kernel<X3, AK, BK><<<grid, 128, smem, st>>>(g);
   return launch_status();
 }
@@ -260,9 +265,9 @@ __global__ void splitk_epilogue_kernel(const b200np_gemm_desc d, int splits) {
 // Split-K factor: the dense layers of the path have a few hundred rows, i.e. ~16 output tiles for 148 SMs;
 // their K range is spread over the idle SMs and the partial tiles are reduced from the caller's workspace.
 int gemm_umma_splits(const b200np_gemm_desc& d) {
-  if (d.precision == B200NP_PREC_FP32_SIMT || d.groups != 1) return 1;
+  if (d.precision == B200NP_PREC_FP32_SIMT || (d.groups != 1 && !d.sum_groups)) return 1;
   const int tiles = ((d.M + 127) / 128) * ((d.N + 63) / 64);
-  const int KB = (d.K + 31) / 32;
+  const int KB = ((d.K + 31) / 32) * (d.sum_groups ? d.groups : 1);
   if (tiles * 2 > kNumSMs || KB < 8) return 1;
   int s = kNumSMs / tiles;
   if (s > KB / 4) s = KB / 4;
@@ -274,7 +279,8 @@ int launch_gemm_umma(const b200np_gemm_desc& d, int a_vec, int b_vec, cudaStream
   if (d.precision == B200NP_PREC_FP32_SIMT) return B200NP_E_UNSUPPORTED;
   if (d.K < 32 || d.N < 16 || (long long)d.M * d.N < 64 * 64) return B200NP_E_UNSUPPORTED;  // tiny: not worth a tile
   const bool AK = d.a_cs == 1, BK = d.b_rs == 1;
-  if (!AK && BK) return B200NP_E_UNSUPPORTED;  // (A m-contiguous, B k-contiguous) never occurs on the path
+  if (!AK && BK) return B200NP_E_UNSUPPORTED;
+  if (d.sum_groups && d.K % 32 != 0) return B200NP_E_UNSUPPORTED;  // (A m-contiguous, B k-contiguous) never occurs on the path
   GemmUArgs g;
   g.d = d;
   g.a_vec = a_vec;
