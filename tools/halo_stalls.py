@@ -24,7 +24,8 @@ def report(name, fl):
           f"| weight warp blocked on b_empty {d[2]/tiles:.0f} | epilogue blocked on acc_full {d[7]/tiles:.0f}")
 
 
-for name, fn in (("fwd conv2+skip", lambda: ops.conv_fwd(h, w2, b, 1, 1, prec, skip=(x, ws, b, 2))),
+for name, fn in (("fwd conv1 s2", lambda: ops.conv_fwd(x, w2, b, 2, 1, prec)),
+                 ("fwd conv2+skip", lambda: ops.conv_fwd(h, w2, b, 1, 1, prec, skip=(x, ws, b, 2))),
                  ("dgrad s1", lambda: ops.conv_dgrad(h, w2, h.shape, 1, prec, mask_src=h))):
     for fl in flag_list:  # diagnostic flags, see tapconv_halo.cu (1 weights, 2 planes, 4 epilogue, 8 cross MMAs, 16 MMAs)
         LIB.b200np_debug_set_halo_flags(fl)
