@@ -23,7 +23,7 @@ inline int launch_status(int kernels = 1) {
   return e == cudaSuccess ? B200NP_OK : B200NP_E_LAUNCH;
 }
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -54,10 +54,20 @@ __device__ __forceinline__ float4 load4_guarded(const float* p, int valid, bool 
   return v;
 }
 
-// AK / BK: operand is k-contiguous (K-major) or m|n-contiguous (MN-major)
+constexpr int kGemmThreads = 256;
+constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// AK / BK: operand is k-contiguous (K-major) or m|n-contiguous (MN-major).
+// 256 threads.  Every global access of a warp covers whole 128-byte lines: operand loads put consecutive lanes
+// on consecutive 16-byte chunks of a row (a "thread = row" mapping makes each warp load touch 32 lines, i.e. 32
+// wavefronts of the L1 data pipe), and the epilogue transposes the accumulator tile through shared memory so
+// that bias / beta*C / row_scale*addend / activation and the store all run on coalesced float4 rows.
+// 3xTF32: the B tile's hi and lo halves are adjacent, so one N = 128 MMA forms A_hi*[B_hi|B_lo] and an N = 64
+// MMA adds A_lo*B_hi to the cross-term columns; two rotating 128-column accumulator blocks (see umma.cuh).
 template <bool X3, bool AK, bool BK>
-__global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_umma_kernel(const GemmUArgs g) {
   constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kGA + kGB);
+  constexpr uint32_t kCols = X3 ? 256u : 64u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -66,9 +76,7 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
   // sum_groups: the groups are K-slices of one product (group pointers switch inside the K loop)
   const int grp = d.sum_groups ? 0 : blockIdx.z / g.splits;
   const int sp = d.sum_groups ? blockIdx.z : blockIdx.z - grp * g.splits;
-  float* __restrict__ C = d.C[grp];
-  const float* __restrict__ bias = d.bias[grp];
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const uint32_t leader = elect_one_sync();
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(AccCfg<X3>::kCols)
+                 "r"(kCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -95,41 +103,51 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
   const int kb_per = (KB_all + g.splits - 1) / g.splits;
   const int kb_lo = sp * kb_per;
   const int KB = KB_all - kb_lo < kb_per ? (KB_all - kb_lo > 0 ? KB_all - kb_lo : 0) : kb_per;
-  float4 av0[8], bv0[4], av1[8], bv1[4];
-  auto fetch = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
+
+  // shared-memory offsets of this thread's chunks (K-block invariant)
+  //   A K-major : rows (tid >> 3) + 32 i, chunk tid & 7        A MN-major: k rows (tid >> 5) + 8 i, m chunk tid & 31
+  //   B K-major : rows (tid >> 3) + 32 j, chunk tid & 7        B MN-major: k rows (tid >> 4) + 16 j, n chunk tid & 15
+  uint32_t a_off[4], b_off[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    a_off[i] = AK ? sw128_offset((tid >> 3) + 32 * i, tid & 7) : mn_off((tid & 31) >> 3, (tid >> 5) + 8 * i, tid & 7);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    b_off[j] = BK ? sw128_offset((tid >> 3) + 32 * j, tid & 7) : mn_off((tid & 15) >> 3, (tid >> 4) + 16 * j, tid & 7);
+
+  float4 av0[4], bv0[2], av1[4], bv1[2];
+  auto fetch = [&](int kb, float4 (&av)[4], float4 (&bv)[2]) {
     const int kbt = kb_lo + kb;
     const int gsel = d.sum_groups ? kbt / KB_grp : grp;
     const int k0 = (kbt - (d.sum_groups ? gsel * KB_grp : 0)) * 32;
     const float* __restrict__ A = d.A[gsel];
     const float* __restrict__ B = d.B[gsel];
-    if (AK) {  // thread = row m0+tid, 32 consecutive k
-      const int m = m0 + tid;
-      const float* p = A + (long long)m * d.a_rs + k0;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) av[c] = load4_guarded(p + 4 * c, m < M ? K - k0 - 4 * c : 0, g.a_vec);
-    } else {   // thread = (k row tid>>2, 32-wide m block tid&3)
-      const int k = k0 + (tid >> 2), mb = m0 + (tid & 3) * 32;
-      const float* p = A + (long long)k * d.a_cs + mb;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) av[c] = load4_guarded(p + 4 * c, k < K ? M - mb - 4 * c : 0, g.a_vec);
+    for (int i = 0; i < 4; ++i) {
+      if (AK) {
+        const int m = m0 + (tid >> 3) + 32 * i, k = k0 + (tid & 7) * 4;
+        av[i] = load4_guarded(A + (long long)m * d.a_rs + k, m < M ? K - k : 0, g.a_vec);
+      } else {
+        const int k = k0 + (tid >> 5) + 8 * i, m = m0 + (tid & 31) * 4;
+        av[i] = load4_guarded(A + (long long)k * d.a_cs + m, k < K ? M - m : 0, g.a_vec);
+      }
     }
-    if (BK) {  // thread = (row n0 + tid>>1, 16 consecutive k at (tid&1)*16)
-      const int n = n0 + (tid >> 1), kb0 = k0 + (tid & 1) * 16;
-      const float* p = B + (long long)n * d.b_cs + kb0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) bv[c] = load4_guarded(p + 4 * c, n < N ? K - kb0 - 4 * c : 0, g.b_vec);
-    } else {   // thread = (k row tid>>2, 16 consecutive n at (tid&3)*16)
-      const int k = k0 + (tid >> 2), nb = n0 + (tid & 3) * 16;
-      const float* p = B + (long long)k * d.b_rs + nb;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) bv[c] = load4_guarded(p + 4 * c, k < K ? N - nb - 4 * c : 0, g.b_vec);
+    for (int j = 0; j < 2; ++j) {
+      if (BK) {
+        const int n = n0 + (tid >> 3) + 32 * j, k = k0 + (tid & 7) * 4;
+        bv[j] = load4_guarded(B + (long long)n * d.b_cs + k, n < N ? K - k : 0, g.b_vec);
+      } else {
+        const int k = k0 + (tid >> 4) + 16 * j, n = n0 + (tid & 15) * 4;
+        bv[j] = load4_guarded(B + (long long)k * d.b_rs + n, k < K ? N - n : 0, g.b_vec);
+      }
     }
   };
-  constexpr uint32_t kIdesc = kIdescTf32_128x64 | (AK ? 0u : (1u << 15)) | (BK ? 0u : (1u << 16));
+  constexpr uint32_t kMajorBits = (AK ? 0u : (1u << 15)) | (BK ? 0u : (1u << 16));
 
   if (KB > 0) fetch(0, av0, bv0);
   if (KB > 1) fetch(1, av1, bv1);
-  auto step = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
+  auto step = [&](int kb, float4 (&av)[4], float4 (&bv)[2]) {
     const int s = kb % kStages;
     const int use = kb / kStages;
     if (use >= 1) mbar_wait(bars + s, (use - 1) & 1);
@@ -137,15 +155,11 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
     uint8_t* a_hi = st;
     uint8_t* a_lo = st + kGA;
     uint8_t* b_hi = st + (X3 ? 2 : 1) * kGA;
-    uint8_t* b_lo = b_hi + kGB;
+    uint8_t* b_lo = b_hi + kGB;   // adjacent to b_hi: [B_hi ; B_lo] is one 128-row (K-major) / 4-block (MN-major) tile
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      split_store(a_hi, a_lo, AK ? sw128_offset(tid, c) : mn_off(tid & 3, tid >> 2, c), av[c], X3);
+    for (int i = 0; i < 4; ++i) split_store(a_hi, a_lo, a_off[i], av[i], X3);
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      split_store(b_hi, b_lo,
-                  BK ? sw128_offset(tid >> 1, (tid & 1) * 4 + c) : mn_off((tid & 3) >> 1, tid >> 2, ((tid & 1) * 4) + c),
-                  bv[c], X3);
+    for (int j = 0; j < 2; ++j) split_store(b_hi, b_lo, b_off[j], bv[j], X3);
     fence_proxy_async();
     __syncthreads();
     if (warp_u == 0) {  // all 32 lanes: descriptors stay in uniform registers, the elected lane issues
@@ -153,18 +167,19 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
       const uint64_t ah = AK ? make_kmajor_sw128_desc(smem_u32(a_hi)) : mn_desc(smem_u32(a_hi));
       const uint64_t bh = BK ? make_kmajor_sw128_desc(smem_u32(b_hi)) : mn_desc(smem_u32(b_hi));
       constexpr uint64_t ka = AK ? 2 : 64, kbs = BK ? 2 : 64;  // descriptor advance per k-step of 8
-      const uint32_t d_hi = tmem_d + (kb % AccCfg<X3>::kHi) * 64;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_tf32(d_hi, ah + ka * k, bh + kbs * k, kIdesc, (kb >= AccCfg<X3>::kHi) | (k != 0), leader);
       if (X3) {
         const uint64_t al = AK ? make_kmajor_sw128_desc(smem_u32(a_lo)) : mn_desc(smem_u32(a_lo));
-        const uint64_t bl = BK ? make_kmajor_sw128_desc(smem_u32(b_lo)) : mn_desc(smem_u32(b_lo));
-        const uint32_t d_lo = tmem_d + AccCfg<X3>::kHi * 64;
+        const uint32_t d_blk = tmem_d + (uint32_t)(kb & 1) * 128;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + ka * k, bh + kbs * k, kIdesc, (kb | k) != 0, leader);
+        for (int k = 0; k < 4; ++k)
+          umma_tf32(d_blk, ah + ka * k, bh + kbs * k, kIdescN128 | kMajorBits, (kb >= 2) | (k != 0), leader);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + ka * k, bl + kbs * k, kIdesc, 1u, leader);
+        for (int k = 0; k < 4; ++k)
+          umma_tf32(d_blk + 64, al + ka * k, bh + kbs * k, kIdescTf32_128x64 | kMajorBits, 1u, leader);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_tf32(tmem_d, ah + ka * k, bh + kbs * k, kIdescTf32_128x64 | kMajorBits, (kb | k) != 0, leader);
       }
       umma_commit(bars + s, leader);
       if (kb == KB - 1) umma_commit(bars + kStages, leader);
@@ -176,51 +191,106 @@ __global__ void __launch_bounds__(128, 2) gemm_umma_kernel(const GemmUArgs g) {
     if (kb + 1 < KB) step(kb + 1, av1, bv1);
   }
 
-  // epilogue: thread = row m0 + 32*warp + lane, 64 columns
+  // ---- epilogue.  warps w and w + 4 share TMEM lane quarter w % 4 and take 32 of the 64 columns each ----
   if (KB > 0) {
-    mbar_wait(bars + kStages, 0);
+    mbar_wait(bars + kStages, 0);   // all MMAs retired: the stages are free and serve as transpose staging
     tc_fence_after();
   }
-  const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-  const int hi_used = KB < AccCfg<X3>::kHi ? KB : AccCfg<X3>::kHi;
-  const int m = m0 + tid;
-  const bool use_rs = d.row_scale != nullptr && grp == 0;
-  const float rs = (use_rs && m < M) ? __ldg(d.row_scale + m) : 0.f;
+  const int q4 = warp & 3, half = warp >> 2;
+  float acc[32];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float acc[32];
-    if (KB > 0) {
-      gather_acc<X3>(taddr, half * 32, hi_used, acc);
-    } else {
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  if (KB > 0) {
+    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q4 * 32) << 16);
+    uint32_t r[32];
+    if (X3) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    }
-    if (m < M) {
+      for (int q = 0; q < 4; ++q) {  // cross-term columns first (smallest magnitude), then the main products
+        const int blk = q & 1, cross = q < 2;
+        if (blk < KB) {
+          tmem_ld32(taddr + blk * 128 + cross * 64 + half * 32, r);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + half * 32 + j;
-        if (n < N) {
-          if (g.splits > 1) {  // raw partial sum; splitk_epilogue_kernel reduces the splits in a fixed order
-            static_cast<float*>(d.workspace)[((long long)sp * M + m) * N + n] = acc[j];
-            continue;
-          }
-          float v = d.alpha * acc[j];
-          float* cp = C + (long long)m * d.ldc + n;
-          if (bias) v += __ldg(bias + n);
-          if (d.beta != 0.f) v = fmaf(d.beta, *cp, v);
-          if (use_rs) v = fmaf(rs, __ldg(d.addend + (long long)m * d.ld_add + n), v);
-          if (d.act == B200NP_ACT_RELU) v = fmaxf(v, 0.f);
-          else if (d.act == B200NP_ACT_TANH) v = tanhf(v);
-          *cp = v;
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
         }
       }
+    } else {
+      tmem_ld32(taddr + half * 32, r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+    }
+  }
+  // stage this warp's 32 rows x 32 columns (row pitch 128 B, chunk index XOR row: conflict-free both ways)
+  uint8_t* stg = smem + warp * 4096;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  __syncwarp();
+  {
+    const int cj = lane & 7;                         // 16-byte column chunk of this lane
+    const int n = n0 + half * 32 + cj * 4;
+    const bool split = g.splits > 1;
+    float* __restrict__ C = split ? static_cast<float*>(d.workspace) + (long long)sp * M * N : d.C[grp];
+    const long long ldc = split ? N : d.ldc;
+    const bool vec = n + 3 < N && (ldc & 3) == 0 && aligned16(C) &&
+                     (split || ((!d.row_scale || ((d.ld_add & 3) == 0 && aligned16(d.addend)))));
+    const float* __restrict__ bias = d.bias[grp];
+    const bool use_rs = d.row_scale != nullptr && grp == 0 && !split;
+    float bv4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bias && !split) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n + e < N) bv4[e] = __ldg(bias + n + e);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      const int m = m0 + q4 * 32 + rr;
+      const float4 t = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4));
+      if (m >= M || n >= N) continue;
+      float v[4] = {t.x, t.y, t.z, t.w};
+      float* cp = C + (long long)m * ldc + n;
+      if (split) {  // raw partial sums; splitk_epilogue_kernel reduces the splits in a fixed order
+        if (vec) *reinterpret_cast<float4*>(cp) = t;
+        else
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < N) cp[e] = v[e];
+        continue;
+      }
+      float old[4] = {0.f, 0.f, 0.f, 0.f}, add[4] = {0.f, 0.f, 0.f, 0.f};
+      const float rs = use_rs ? __ldg(d.row_scale + m) : 0.f;
+      if (vec) {
+        if (d.beta != 0.f) { const float4 o = *reinterpret_cast<const float4*>(cp); old[0] = o.x; old[1] = o.y; old[2] = o.z; old[3] = o.w; }
+        if (use_rs) { const float4 o = ldg4(d.addend + (long long)m * d.ld_add + n); add[0] = o.x; add[1] = o.y; add[2] = o.z; add[3] = o.w; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < N) {
+            if (d.beta != 0.f) old[e] = cp[e];
+            if (use_rs) add[e] = __ldg(d.addend + (long long)m * d.ld_add + n + e);
+          }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x = d.alpha * v[e] + bv4[e];
+        if (d.beta != 0.f) x = fmaf(d.beta, old[e], x);
+        if (use_rs) x = fmaf(rs, add[e], x);
+        if (d.act == B200NP_ACT_RELU) x = fmaxf(x, 0.f);
+        else if (d.act == B200NP_ACT_TANH) x = tanhf(x);
+        v[e] = x;
+      }
+      if (vec) *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+      else
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < N) cp[e] = v[e];
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(AccCfg<X3>::kCols)
-                 : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kCols) : "memory");
   }
 }
 
@@ -236,7 +306,7 @@ int launch(const GemmUArgs& g, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((g.d.M + 127) / 128, (g.d.N + 63) / 64, (g.d.sum_groups ? 1 : g.d.groups) * g.splits);
-  gemm_umma_kernel<X3, AK, BK><<<grid, 128, smem, st>>>(g);
+  gemm_umma_kernel<X3, AK, BK><<<grid, kGemmThreads, smem, st>>>(g);
   return launch_status();
 }
 
