@@ -27,15 +27,25 @@ namespace {
 using namespace umma;
 
 
+constexpr int kConvThreads = 256;
+constexpr uint32_t kIdescTf32_128x128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// One 128-pixel tile per CTA, K-blocks = (tap, channel half).  256 threads: eight consecutive lanes hold the
+// eight 16-byte chunks of one 128-byte row (pixel x 32 channels, or weight row), so every warp load covers four
+// whole lines; the epilogue goes through a shared-memory transpose for the same reason (see gemm_umma.cu).
+// 3xTF32 uses the stacked [W_hi ; W_lo] operand: an N = 128 and an N = 64 MMA per k-step, two rotating
+// 128-column accumulator blocks.
 template <bool X3>
-__global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs a) {
+__global__ void __launch_bounds__(kConvThreads, 2) tapconv_umma_kernel(const TapConvArgs a) {
   constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kABytes + kBBytes);
+  constexpr uint32_t kCols = X3 ? 256u : 64u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);  // [kStages] stage free, [1] accum done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kStages + 1);
+  long long* off_s = reinterpret_cast<long long*>(bars + kStages + 2);         // [128] output offset per tile pixel, -1: none
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const uint32_t leader = elect_one_sync();
   const long long M = (long long)a.N * a.OH * a.OW;
@@ -47,52 +57,70 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(AccCfg<X3>::kCols)
+                 "r"(kCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < kBM) {  // output offsets of the tile's pixels, for the transposed epilogue
+    const long long p = m0 + tid;
+    long long off = -1;
+    if (p < M) {
+      const int ox = (int)(p % a.OW);
+      const long long q = p / a.OW;
+      const int oy = (int)(q % a.OH);
+      const long long n = q / a.OH;
+      off = ((n * a.dstH + (long long)oy * a.dst_s + a.dst_oy) * a.dstW + (long long)ox * a.dst_s + a.dst_ox) * 64;
+    }
+    off_s[tid] = off;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
-  // pixel gathered by this thread (row `tid` of the A tile)
-  const long long p = m0 + tid;
-  const bool pvalid = p < M;
-  int ox = 0, oy = 0, n = 0;
-  if (pvalid) {
-    ox = (int)(p % a.OW);
-    long long q = p / a.OW;
-    oy = (int)(q % a.OH);
-    n = (int)(q / a.OH);
+  // gather roles: chunk g_c of rows g_r + 32 i (A: i = 0..3 pixels of the tile, B: i = 0..1 weight rows)
+  const int g_c = tid & 7, g_r = tid >> 3;
+  int pn[4], poy[4], pox[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long p = m0 + g_r + 32 * i;
+    pn[i] = -1; poy[i] = 0; pox[i] = 0;
+    if (p < M) {
+      pox[i] = (int)(p % a.OW);
+      const long long q = p / a.OW;
+      poy[i] = (int)(q % a.OH);
+      pn[i] = (int)(q / a.OH);
+    }
   }
-  const int brow = tid >> 1, bhalf = tid & 1;  // B: cout row, 64-byte half of the 128 B K-block row
+  uint32_t a_off[4], b_off[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a_off[i] = sw128_offset(g_r + 32 * i, g_c);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) b_off[j] = sw128_offset(g_r + 32 * j, g_c);
 
   const int KB = a.ntaps * 2;
   // two register buffers: the loads of K-block kb+2 are in flight while kb+1 is staged and kb runs
-  float4 av0[8], bv0[4], av1[8], bv1[4];
-  auto fetch = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
-    const int t = kb >> 1, c0 = (kb & 1) * kBK;
+  float4 av0[4], bv0[2], av1[4], bv1[2];
+  auto fetch = [&](int kb, float4 (&av)[4], float4 (&bv)[2]) {
+    const int t = kb >> 1, c0 = (kb & 1) * kBK + g_c * 4;
     const Tap tp = a.taps[t];
     const int s = tp.src;
-    const int iy = oy * a.in_s[s] + tp.dy, ix = ox * a.in_s[s] + tp.dx;
-    const bool ok = pvalid && iy >= 0 && iy < a.srcH[s] && ix >= 0 && ix < a.srcW[s];
-    if (ok) {
-      const float* ap = a.src[s] + (((long long)n * a.srcH[s] + iy) * a.srcW[s] + ix) * 64 + c0;
+    const float* src = a.src[s];
+    const int sH = a.srcH[s], sW = a.srcW[s], ss = a.in_s[s];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) av[c] = ldg4(ap + 4 * c);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i) {
+      const int iy = poy[i] * ss + tp.dy, ix = pox[i] * ss + tp.dx;
+      const bool ok = pn[i] >= 0 && iy >= 0 && iy < sH && ix >= 0 && ix < sW;
+      av[i] = ok ? ldg4(src + (((long long)pn[i] * sH + iy) * sW + ix) * 64 + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float* bp = a.w[s] + ((long long)tp.slab * 64 + brow) * 64 + c0 + bhalf * 16;
+    const float* bp = a.w[s] + ((long long)tp.slab * 64 + g_r) * 64 + c0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) bv[c] = ldg4(bp + 4 * c);
+    for (int j = 0; j < 2; ++j) bv[j] = ldg4(bp + 32 * 64 * j);
   };
 
   if (KB > 0) fetch(0, av0, bv0);
   if (KB > 1) fetch(1, av1, bv1);
-  auto step = [&](int kb, float4 (&av)[8], float4 (&bv)[4]) {
+  auto step = [&](int kb, float4 (&av)[4], float4 (&bv)[2]) {
     const int s = kb % kStages;
     const int use = kb / kStages;
     if (use >= 1) mbar_wait(bars + s, (use - 1) & 1);  // MMAs that read this stage have retired
@@ -100,27 +128,27 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
     uint8_t* a_hi = st;
     uint8_t* a_lo = st + kABytes;                       // only in X3
     uint8_t* b_hi = st + (X3 ? 2 : 1) * kABytes;
-    uint8_t* b_lo = b_hi + kBBytes;                     // only in X3
+    uint8_t* b_lo = b_hi + kBBytes;                     // only in X3; [W_hi ; W_lo] = one 128-row K-major tile
 #pragma unroll
-    for (int c = 0; c < 8; ++c) split_store(a_hi, a_lo, sw128_offset(tid, c), av[c], X3);
+    for (int i = 0; i < 4; ++i) split_store(a_hi, a_lo, a_off[i], av[i], X3);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) split_store(b_hi, b_lo, sw128_offset(brow, bhalf * 4 + c), bv[c], X3);
+    for (int j = 0; j < 2; ++j) split_store(b_hi, b_lo, b_off[j], bv[j], X3);
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (warp_u == 0) {  // all 32 lanes: descriptors stay in uniform registers, the elected lane issues
       tc_fence_after();
       const uint64_t ah = make_kmajor_sw128_desc(smem_u32(a_hi)), bh = make_kmajor_sw128_desc(smem_u32(b_hi));
-      const uint32_t d_hi = tmem_d + (kb % AccCfg<X3>::kHi) * 64;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)  // +32 B (8 tf32) along K inside the swizzle atom = +2 in the address field
-        umma_tf32(d_hi, ah + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb >= AccCfg<X3>::kHi) | (k != 0), leader);
       if (X3) {
-        const uint64_t al = make_kmajor_sw128_desc(smem_u32(a_lo)), bl = make_kmajor_sw128_desc(smem_u32(b_lo));
-        const uint32_t d_lo = tmem_d + AccCfg<X3>::kHi * 64;
+        const uint64_t al = make_kmajor_sw128_desc(smem_u32(a_lo));
+        const uint32_t d_blk = tmem_d + (uint32_t)(kb & 1) * 128;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, al + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb | k) != 0, leader);
+        for (int k = 0; k < 4; ++k)  // +32 B (8 tf32) along K inside the swizzle atom = +2 in the address field
+          umma_tf32(d_blk, ah + 2 * k, bh + 2 * k, kIdescTf32_128x128, (kb >= 2) | (k != 0), leader);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(d_lo, ah + 2 * k, bl + 2 * k, kIdescTf32_128x64, 1u, leader);
+        for (int k = 0; k < 4; ++k) umma_tf32(d_blk + 64, al + 2 * k, bh + 2 * k, kIdescTf32_128x64, 1u, leader);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, ah + 2 * k, bh + 2 * k, kIdescTf32_128x64, (kb | k) != 0, leader);
       }
       umma_commit(bars + s, leader);                       // stage reusable once these MMAs retire
       if (kb == KB - 1) umma_commit(bars + kStages, leader);  // accumulator complete
@@ -132,38 +160,56 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
     if (kb + 1 < KB) step(kb + 1, av1, bv1);
   }
 
-  // ---- epilogue: TMEM -> registers -> bias / ReLU-mask / activation -> NHWC global ----
+  // ---- epilogue: TMEM -> registers -> shared-memory transpose -> bias / ReLU-mask / activation -> NHWC global.
+  // warps w and w + 4 share TMEM lane quarter w % 4 and take 32 of the 64 output channels each ----
   if (KB > 0) {
-    mbar_wait(bars + kStages, 0);
+    mbar_wait(bars + kStages, 0);   // all MMAs retired: the stages are free and serve as staging
     tc_fence_after();
   }
-  const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-  const int hi_used = KB < AccCfg<X3>::kHi ? KB : AccCfg<X3>::kHi;
-  const long long off = pvalid ? (((long long)n * a.dstH + (long long)oy * a.dst_s + a.dst_oy) * a.dstW +
-                                  (long long)ox * a.dst_s + a.dst_ox) * 64
-                               : 0;
+  const int q4 = warp & 3, half = warp >> 2;
+  float acc[32];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float acc[32];
-    if (KB > 0) {
-      gather_acc<X3>(taddr, half * 32, hi_used, acc);  // warp-collective: every lane takes part
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  if (KB > 0) {
+    const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q4 * 32) << 16);
+    uint32_t r[32];
+    if (X3) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // cross-term columns first (smallest magnitude), then the main products
+        const int blk = q & 1, cross = q < 2;
+        if (blk < KB) {
+          tmem_ld32(taddr + blk * 128 + cross * 64 + half * 32, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+        }
+      }
     } else {
+      tmem_ld32(taddr + half * 32, r);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
     }
-    if (!pvalid) continue;
+  }
+  uint8_t* stg = smem + warp * 4096;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int c = half * 32 + 4 * q;
-      float4 o = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-      if (a.bias) {
-        const float4 b = ldg4(a.bias + c);
-        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-      }
-      if (a.bias2) {
-        const float4 b = ldg4(a.bias2 + c);
-        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-      }
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  __syncwarp();
+  {
+    const int cj = lane & 7, c = half * 32 + cj * 4;   // this lane's four output channels
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias) bsum = ldg4(a.bias + c);
+    if (a.bias2) {
+      const float4 b = ldg4(a.bias2 + c);
+      bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w;
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      const long long off = off_s[q4 * 32 + rr];
+      float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4));
+      if (off < 0) continue;
+      o.x += bsum.x; o.y += bsum.y; o.z += bsum.z; o.w += bsum.w;
       if (a.mask) {
         const float4 mk = ldg4(a.mask + off + c);
         o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
@@ -178,14 +224,14 @@ __global__ void __launch_bounds__(128, 2) tapconv_umma_kernel(const TapConvArgs 
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(AccCfg<X3>::kCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kCols) : "memory");
   }
 }
 
 template <bool X3>
 int launch(const TapConvArgs& a, cudaStream_t st) {
   constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kABytes + kBBytes);
-  const size_t smem = kStages * kStageBytes + 1024 + 64;
+  const size_t smem = kStages * kStageBytes + 1024 + 64 + 1024;  // + per-pixel output offsets
   static bool configured = false;  // idempotent attribute; benign if two threads race
   if (!configured) {
     if (cudaFuncSetAttribute(tapconv_umma_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
@@ -195,7 +241,7 @@ int launch(const TapConvArgs& a, cudaStream_t st) {
   }
   const long long M = (long long)a.N * a.OH * a.OW;
   if (M <= 0) return B200NP_OK;
-  tapconv_umma_kernel<X3><<<(unsigned)ceil_div(M, kBM), 128, smem, st>>>(a);
+  tapconv_umma_kernel<X3><<<(unsigned)ceil_div(M, kBM), kConvThreads, smem, st>>>(a);
   return launch_status();
 }
 
