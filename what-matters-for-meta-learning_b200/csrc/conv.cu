@@ -149,6 +149,33 @@ extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, co
   // stride 2: one launch per parity class of the input pixel (iy,ix) = (2*oy+py, 2*ox+px).
   // y[o] = sum_r x[2o + r - pad] w[r]  =>  dx[i] = sum_{r : (i + pad - r) even} dy[(i + pad - r)/2] w[r]
   a.OH = OHc; a.OW = OWc; a.dst_s = 2;
+  if (img && use_umma(precision, a.Cin, a.Cout)) {
+    // all four classes from one staged dY halo (one launch, one accumulator set per class)
+    TapConvArgs f = a;
+    TapClasses cls{};
+    cls.ncls = 4;
+    int nt = 0;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const int c = py * 2 + px;
+        cls.oy[c] = py; cls.ox[c] = px;
+        for (int r = 0; r < R; ++r) {
+          if ((py + pad - r) & 1) continue;
+          for (int s = 0; s < R; ++s) {
+            if ((px + pad - s) & 1) continue;
+            cls.tap_cls[nt] = c;
+            f.taps[nt++] = Tap{0, (int8_t)((py + pad - r) / 2), (int8_t)((px + pad - s) / 2), (int8_t)(r * R + s)};
+          }
+        }
+        if (dys && c == 0) { cls.tap_cls[nt] = c; f.taps[nt++] = Tap{1, 0, 0, 0}; }
+      }
+    f.ntaps = nt;
+    f.dst_oy = f.dst_ox = 0;
+    if (R == 3) {
+      int rc = launch_tapconv_halo(f, wd + (size_t)R * R * 4096, R * R, dys ? wsd + 4096 : nullptr, 1, precision, st, &cls);
+      if (rc != B200NP_E_UNSUPPORTED) return rc;
+    }
+  }
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       int nt = 0;

@@ -62,8 +62,16 @@ int launch_tapwgrad_simt(const TapWgradArgs& a, cudaStream_t st);
 // tcgen05 path (tapconv_umma.cu); returns B200NP_E_UNSUPPORTED when the shape does not fit
 int launch_tapconv_umma(const TapConvArgs& a, int precision, cudaStream_t st);
 int launch_tapwgrad_umma(const TapWgradArgs& a, int precision, cudaStream_t st);
+// Several outputs from one staged input ("classes"): tap t accumulates into output class tap_cls[t] (taps sorted
+// by class), class c is written at dst pixel (oy*dst_s + oy_c, ox*dst_s + ox_c).  The four input-parity classes
+// of a stride-2 data gradient read the same dY halo, so one launch stages it once for all four.
+struct TapClasses {
+  int ncls;              // 2..4
+  int tap_cls[kMaxTaps];
+  int oy[4], ox[4];
+};
 // halo-tile tcgen05 path for unit-input-stride stencils (tapconv_halo.cu); bp = tensor-core weight images
 int launch_tapconv_halo(const TapConvArgs& a, const float* bp0, int nslabs0, const float* bp1, int nslabs1,
-                        int precision, cudaStream_t st);
+                        int precision, cudaStream_t st, const TapClasses* cls = nullptr);
 
 }  // namespace b200np

@@ -82,6 +82,9 @@ struct HaloArgs {
   int tap_off[kMaxTaps];   // first slot of the tap's window inside the stage
   int tap_hc[kMaxTaps];    // pitch (slots per plane row) of the tap's plane
   int total_slots;         // per stage plane
+  int ncls;                // 1, or the number of output classes (TapClasses): one accumulator set per class
+  int tap_cls[kMaxTaps];
+  int cls_oy[4], cls_ox[4];
   int a_stages;            // 1 or 2 plane stages
   int tiles_x, tiles_total;
   uint32_t plane_bytes, stage_bytes, b_off, bar_off;
@@ -130,9 +133,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + h.bar_off);
   uint64_t* a_full = bars;                  // [a_stages] producers -> MMA            (count 256)
   uint64_t* a_empty = bars + 2;             // [a_stages] MMA commit -> producers     (count 1)
-  uint64_t* acc_full = bars + 4;            // [2] MMA commit -> epilogue             (count 1)
-  uint64_t* acc_empty = bars + 6;           // [2] epilogue -> MMA                    (count 128)
-  uint64_t* b_full = bars + 8;              // [nb] bulk copy tx -> MMA               (count 1 + tx)
+  uint64_t* acc_full = bars + 4;            // [4] MMA commit -> epilogue             (count 1)
+  uint64_t* acc_empty = bars + 8;           // [4] epilogue -> MMA                    (count 128)
+  uint64_t* b_full = bars + 12;             // [nb] bulk copy tx -> MMA               (count 1 + tx)
   uint64_t* b_empty = b_full + kMaxBStages; // [nb] MMA commit -> weight warp         (count 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMaxBStages);
   const int nb = h.nb, a_stages = h.a_stages;
@@ -143,11 +146,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kAccCols = X3 ? 256u : 128u;       // columns per accumulator set: kRot blocks of 128 | 64
   constexpr uint32_t kTmemCols = 2 * kAccCols;
+  // class mode (h.ncls > 1): one accumulator set per output class, a single block each (K <= 4 taps x 64, no
+  // rotation needed): 4 x 128 | 64 columns = the same TMEM allocation
+  constexpr uint32_t kBlkCols = X3 ? 128u : 64u;
+  const int ncls = h.ncls;
+  const uint32_t set_stride = ncls > 1 ? kBlkCols : kAccCols;
 
   if (tid == 0) {
     for (int s = 0; s < a_stages; ++s) { mbar_init(a_full + s, kProducerThreads); mbar_init(a_empty + s, 1); }
     for (int s = 0; s < nb; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
+    for (int s = 0; s < 4; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWeightWarp) {
@@ -313,9 +321,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi_word), "r"(idesc), "r"(acc)
             : "memory");
       };
+      uint32_t cphase = 0;                                // class mode: every set is used once per tile
       for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
-        mbar_wait_timed(acc_empty + acc_set, acc_phase ^ 1, w_acc, timed);   // epilogue has drained this set
-        tc_fence_after();
+        if (ncls == 1) {
+          mbar_wait_timed(acc_empty + acc_set, acc_phase ^ 1, w_acc, timed);   // epilogue has drained this set
+          tc_fence_after();
+        }
         const uint32_t d0 = tmem_base + acc_set * kAccCols;
         uint32_t rot = 0;                                 // accumulator block rotation (kb % kRot without a division)
         int kb = 0;
@@ -330,8 +341,21 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             const uint32_t bh = (b_base16 + bs.idx * (kBSlot >> 4)) | lbo_bits;
             if (!(dflags & 64)) mbar_wait_timed(b_full + bs.idx, bs.phase, w_b, timed);
             if (dflags & 128) tc_fence_after();  // not needed: bulk-copy (async proxy) data
-            const uint32_t d_blk = d0 + rot * (X3 ? 128u : 64u);
-            const uint32_t acc_first = kb >= kRot;
+            uint32_t d_blk = d0 + rot * kBlkCols;
+            uint32_t acc_first = kb >= kRot;
+            int cls = 0;
+            bool cls_last = false;
+            if (ncls > 1) {
+              cls = h.tap_cls[t];
+              const bool cls_first = t == 0 || h.tap_cls[t - 1] != cls;
+              cls_last = t == ntaps - 1 || h.tap_cls[t + 1] != cls;
+              if (half == 0 && cls_first) {               // the epilogue has drained this class of the previous tile
+                mbar_wait_timed(acc_empty + cls, cphase ^ 1, w_acc, timed);
+                tc_fence_after();
+              }
+              d_blk = tmem_base + cls * kBlkCols;
+              acc_first = !(half == 0 && cls_first);
+            }
             if (leader) {
               if (X3) {
                 if (!(dflags & 16)) {
@@ -347,15 +371,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
                 for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hi_word, bh + 2 * k, k == 0 ? acc_first : 1u, kIdescTf32_128x64);
               }
               if (!(dflags & 32)) umma_commit(b_empty + bs.idx);
+              if (ncls > 1 && half == 1 && cls_last) umma_commit(acc_full + cls);   // class complete
             }
             bs.advance(nb);
-            if (++rot == kRot) rot = 0;
+            if (ncls == 1 && ++rot == kRot) rot = 0;
           }
           if (leader) umma_commit(a_empty + st.idx);
           st.advance(a_stages);
         }
-        if (leader) umma_commit(acc_full + acc_set);
-        if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
+        if (ncls == 1) {
+          if (leader) umma_commit(acc_full + acc_set);
+          if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
+        } else {
+          cphase ^= 1;
+        }
       }
       if (timed && leader) {
         long long* o = dbgp + blockIdx.x * 8;
@@ -364,22 +393,28 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
     }
   } else {
     // ===================== epilogue =====================
+    // (A shared-memory transposed store, which halved the stem kernel's time, was measured here and made this
+    // kernel slower -- 1.16 -> 2.3 ms for the fused stride-2 data gradient: with one epilogue warp per scheduler
+    // the extra STS/LDS/__syncwarp round trip is pure latency.  Direct 16-byte stores per pixel row are kept.)
     const int q = warp & 3;                              // TMEM lane quarter this warp may access (warp id % 4)
     const int m = q * 32 + lane;                         // accumulator row = output pixel of the tile
     int acc_set = 0;
     uint32_t acc_phase = 0;
     long long w_e = 0;
     const int kb_total = 2 * ntaps;
-    const int blocks_used = kb_total < kRot ? kb_total : kRot;
+    const int blocks_used = ncls > 1 ? 1 : (kb_total < kRot ? kb_total : kRot);
     for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
       const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
       const int r0 = rb * kTileRows;
       const int n = r0 / a.OH, oy = r0 - n * a.OH + (m >> 3), ox = xt * kTileCols + (m & 7);
+     for (int cls = 0; cls < ncls; ++cls) {              // class mode: the tile's outputs, one accumulator set each
+      const int set = ncls > 1 ? cls : acc_set;
+      const int d_oy = ncls > 1 ? h.cls_oy[cls] : a.dst_oy, d_ox = ncls > 1 ? h.cls_ox[cls] : a.dst_ox;
       const long long off =
-          (((long long)n * a.dstH + (long long)oy * a.dst_s + a.dst_oy) * a.dstW + (long long)ox * a.dst_s + a.dst_ox) * 64;
-      mbar_wait_timed(acc_full + acc_set, acc_phase, w_e, dbgp != nullptr);
+          (((long long)n * a.dstH + (long long)oy * a.dst_s + d_oy) * a.dstW + (long long)ox * a.dst_s + d_ox) * 64;
+      mbar_wait_timed(acc_full + set, acc_phase, w_e, dbgp != nullptr);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc_set * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr = tmem_base + set * set_stride + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float acc[32];
@@ -406,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
         }
         if (hf == 1) {                                   // all TMEM reads of this set are done
           tc_fence_before();
-          mbar_arrive(acc_empty + acc_set);
+          mbar_arrive(acc_empty + set);
         }
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq) {
@@ -431,7 +466,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           if (!(dflags & 4) || o.x == 12345.678f) *reinterpret_cast<float4*>(a.dst + off + c) = o;
         }
       }
-      if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
+     }
+      if (ncls > 1) acc_phase ^= 1;                      // every class set is used once per tile
+      else if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
     }
     if (dbgp && warp == kEpiWarp0 && lane == 0) dbgp[blockIdx.x * 8 + 7] = w_e;
   }
@@ -486,7 +523,7 @@ int launch_halo(HaloArgs& h, cudaStream_t st) {
 
 // Eligibility + geometry.  `bp0` / `bp1`: pre-split weights of source 0 / 1 (see b200np_pack_conv_weight).
 int launch_tapconv_halo(const TapConvArgs& a, const float* bp0, int nslabs0, const float* bp1, int nslabs1,
-                        int precision, cudaStream_t st) {
+                        int precision, cudaStream_t st, const TapClasses* cls) {
   if (a.Cin != 64 || a.Cout != 64 || a.ntaps < 1 || a.ntaps > kMaxTaps || !bp0) return B200NP_E_UNSUPPORTED;
   if (a.act != B200NP_ACT_NONE && a.act != B200NP_ACT_RELU) return B200NP_E_UNSUPPORTED;
   if (a.OH % kTileRows != 0 || a.OW % kTileCols != 0) return B200NP_E_UNSUPPORTED;
@@ -494,6 +531,22 @@ int launch_tapconv_halo(const TapConvArgs& a, const float* bp0, int nslabs0, con
   if (a.ntaps < g_halo_min_taps) return B200NP_E_UNSUPPORTED;
   HaloArgs h{};
   h.t = a;
+  h.ncls = 1;
+  if (cls) {
+    if (cls->ncls < 2 || cls->ncls > 4) return B200NP_E_UNSUPPORTED;
+    h.ncls = cls->ncls;
+    for (int t = 0; t < a.ntaps; ++t) {
+      if (cls->tap_cls[t] < 0 || cls->tap_cls[t] >= cls->ncls || (t > 0 && cls->tap_cls[t] < cls->tap_cls[t - 1]))
+        return B200NP_E_UNSUPPORTED;           // taps must be sorted by class
+      h.tap_cls[t] = cls->tap_cls[t];
+    }
+    for (int c = 0; c < 4; ++c) { h.cls_oy[c] = cls->oy[c]; h.cls_ox[c] = cls->ox[c]; }
+    for (int c = 0; c < cls->ncls; ++c) {      // every class needs at least one tap (its set is waited on per tile)
+      bool any = false;
+      for (int t = 0; t < a.ntaps; ++t) any |= cls->tap_cls[t] == c;
+      if (!any) return B200NP_E_UNSUPPORTED;
+    }
+  }
   h.dbg = g_halo_dbg;
   h.dbg_flags = g_halo_flags;
   h.bp[0] = bp0; h.bp[1] = bp1; h.nslabs[0] = nslabs0; h.nslabs[1] = nslabs1;
