@@ -180,6 +180,11 @@ int b200np_colsum(const float* x, float* out, long long rows, int cols, long lon
 /* utility elementwise ops used between kernels (no library calls on the hot path) */
 int b200np_fill(float* x, long long n, float value, void* stream);
 int b200np_axpy(float* y, const float* x, long long n, float a, void* stream); /* y += a*x */
+/* dst[dst_off[i] .. +numel[i]) = src[i] (zeros where src[i] is NULL) for nseg segments: the per-parameter
+ * gradients of one backward pass gathered into the flat gradient buffer with one launch per 64 segments
+ * (replaces autograd's per-parameter accumulate kernels).  src / dst_off / numel are HOST arrays. */
+int b200np_multi_copy(const float* const* src, const long long* dst_off, const long long* numel, int nseg,
+                      float* dst, void* stream);
 /* y[r, :] = x[r / rep, :] (rep consecutive copies of each row; the reference's .repeat) */
 int b200np_repeat_rows(const float* x, float* y, long long rows_in, int rep, int cols, void* stream);
 /* x[r,:] = sum over the rep copies of dy (backward of repeat_rows) */

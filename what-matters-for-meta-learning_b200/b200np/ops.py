@@ -249,6 +249,18 @@ def zeros(shape, like):
     return fill(empty(shape, like), 0.0)
 
 
+def multi_copy(dst, segments):
+    """dst[off:off+n] = src (zeros for src None) for every (src, off, n) in segments -- one launch per 64."""
+    k = len(segments)
+    if k == 0:
+        return dst
+    srcs = (C.c_void_p * k)(*[None if s is None else s.data_ptr() for s, _, _ in segments])
+    offs = (C.c_longlong * k)(*[o for _, o, _ in segments])
+    nums = (C.c_longlong * k)(*[n for _, _, n in segments])
+    check(LIB.b200np_multi_copy(srcs, offs, nums, k, _ptr(dst), _stream()), "multi_copy")
+    return dst
+
+
 def axpy(y, x, a=1.0):
     check(LIB.b200np_axpy(_ptr(y), _ptr(x), y.numel(), float(a), _stream()), "axpy")
     return y

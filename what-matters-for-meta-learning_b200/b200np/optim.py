@@ -24,7 +24,7 @@ class FlatParams:
         total = self.n_live + sum(pad(p.numel()) for _, p in rest)
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(self.n_live, device=dev, dtype=torch.float32)
-        self.live, self.views = [], {}
+        self.live, self.views, self._keep = [], {}, []
         off = 0
         for n, p in live + rest:
             k = p.numel()
@@ -41,20 +41,28 @@ class FlatParams:
             p.grad = self.grad[off:off + k].view_as(p)
 
     def gather_grads(self):
-        """After autograd: make sure every .grad lives in the flat buffer (copy only if autograd
-        replaced the view with its own tensor)."""
+        """After autograd: bring every .grad into the flat buffer -- ONE launch per 64 parameters
+        (`b200np_multi_copy`); parameters without a gradient get zeros.  Afterwards .grad is the flat view."""
+        segs = []
         for _, p, off, k in self.live:
             view = self.grad[off:off + k].view_as(p)
             g = p.grad
             if g is None:
-                ops.fill(view, 0.0)
+                segs.append((None, off, k))
             elif g.data_ptr() != view.data_ptr():
-                view.copy_(g)
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                self._keep.append(g)      # keep the source alive until the copy has been enqueued
+                segs.append((g, off, k))
             p.grad = view
+        ops.multi_copy(self.grad, segs)
+        self._keep.clear()
 
     def zero_grad(self):
-        ops.fill(self.grad, 0.0)
-        self.attach_grads()
+        """Drop the gradients: autograd then hands each parameter its gradient tensor by reference (no
+        accumulate kernel per parameter); `gather_grads` collects them."""
+        for _, p, _, _ in self.live:
+            p.grad = None
 
 
 class FusedAdam:

@@ -49,6 +49,44 @@ extern "C" int b200np_axpy(float* y, const float* x, long long n, float a, void*
   return launch_status();
 }
 
+// dst[off_i .. off_i + n_i) = src_i (or 0 where src_i is NULL), up to 64 segments per launch, passed by value
+constexpr int kSegsPerLaunch = 64;
+struct CopySegs {
+  const float* src[kSegsPerLaunch];
+  long long off[kSegsPerLaunch];
+  long long n[kSegsPerLaunch];
+};
+__global__ void multi_copy_kernel(const CopySegs g, float* __restrict__ dst) {
+  const float* __restrict__ s = g.src[blockIdx.y];
+  float* __restrict__ d = dst + g.off[blockIdx.y];
+  const long long n = g.n[blockIdx.y];
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long st = (long long)gridDim.x * blockDim.x;
+  if (s) for (; i < n; i += st) d[i] = s[i];
+  else for (; i < n; i += st) d[i] = 0.f;
+}
+extern "C" int b200np_multi_copy(const float* const* src, const long long* dst_off, const long long* numel, int nseg,
+                                 float* dst, void* stream) {
+  if (nseg <= 0) return B200NP_OK;
+  if (!src || !dst_off || !numel || !dst) return B200NP_E_BADARG;
+  for (int base = 0; base < nseg; base += kSegsPerLaunch) {
+    CopySegs g{};
+    const int cnt = nseg - base < kSegsPerLaunch ? nseg - base : kSegsPerLaunch;
+    long long mx = 1;
+    for (int i = 0; i < cnt; ++i) {
+      if (numel[base + i] < 0 || dst_off[base + i] < 0) return B200NP_E_BADARG;
+      g.src[i] = src[base + i]; g.off[i] = dst_off[base + i]; g.n[i] = numel[base + i];
+      if (g.n[i] > mx) mx = g.n[i];
+    }
+    long long bx = (mx + 1023) / 1024;   // 256 threads x 4 elements
+    if (bx > 64) bx = 64;
+    multi_copy_kernel<<<dim3((unsigned)bx, (unsigned)cnt), 256, 0, as_stream(stream)>>>(g, dst);
+    int rc = launch_status();
+    if (rc != B200NP_OK) return rc;
+  }
+  return B200NP_OK;
+}
+
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                float* __restrict__ dz, long long n, int act) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
