@@ -202,7 +202,8 @@ extern "C" size_t b200np_conv_wgrad_workspace(int N, int H, int W, int Cin, int 
   int nt = R * R + 1;  // room for a fused skip-projection tap
   int chunks = wgrad_chunks(M, nt);
   size_t part = (size_t)chunks * nt * Cout * Cin * sizeof(float);
-  return part + b200np_colsum_workspace(M, Cout);
+  size_t dbw = b200np_colsum_workspace(M, Cout), dbp = (size_t)chunks * Cout * sizeof(float);
+  return part + (dbw > dbp ? dbw : dbp);
 }
 
 extern "C" int b200np_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int Cin,
@@ -230,15 +231,24 @@ extern "C" int b200np_conv_wgrad(const float* x, const float* dy, float* dw, flo
   a.chunks = wgrad_chunks(M, nt);
   a.pix_per_chunk = wgrad_pix_per_chunk(M, a.chunks);
   a.part = (float*)ws;
+  const int per = nt * Cout * Cin;
+  const size_t part_bytes = (size_t)a.chunks * per * sizeof(float);
   int rc = B200NP_E_UNSUPPORTED;
-  if (use_umma(precision, Cin, Cout)) rc = launch_tapwgrad_umma(a, precision, st);
-  if (rc == B200NP_E_UNSUPPORTED) rc = launch_tapwgrad_simt(a, st);
+  bool db_fused = false;
+  if (use_umma(precision, Cin, Cout)) {
+    a.part_db = db ? (float*)((char*)ws + part_bytes) : nullptr;   // bias gradient from the dy tiles the kernel stages
+    rc = launch_tapwgrad_umma(a, precision, st);
+    db_fused = rc == B200NP_OK && db;
+  }
+  if (rc == B200NP_E_UNSUPPORTED) {
+    a.part_db = nullptr;
+    rc = launch_tapwgrad_simt(a, st);
+  }
   if (rc != B200NP_OK) return rc;
-  int per = nt * Cout * Cin;
   rc = launch_reduce_partials(a.part, dw, a.chunks, per, ReduceMap{1, R * R, Cout, Cin, dws}, st);
   if (rc != B200NP_OK) return rc;
+  if (db_fused) return launch_reduce_partials(a.part_db, db, a.chunks, Cout, ReduceMap{0, 0, 0, 0, nullptr}, st);
   if (db) {
-    size_t part_bytes = (size_t)a.chunks * per * sizeof(float);
     rc = b200np_colsum(dy, db, M, Cout, Cout, (char*)ws + part_bytes, ws_bytes - part_bytes, stream);
     if (rc != B200NP_OK) return rc;
   }

@@ -53,6 +53,8 @@ struct TapWgradArgs {
   int ntaps;
   Tap taps[kMaxTaps];  // dy/dx only
   float* part;         // [chunks][ntaps][Cout][Cin]
+  float* part_db;      // nullable, tcgen05 kernel only: [chunks][Cout] column sums of dy (the bias gradient) --
+                       // the kernel stages every dy element anyway, so db costs no second pass over dy
   int chunks;
   long long pix_per_chunk;  // multiple of 16
 };

@@ -338,6 +338,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) tapwgrad_umma_kernel(const TapW
     f_n = q / a.OH;
   }
   float4 av0[4], bv0[2], av1[4], bv1[2];
+  const bool want_db = a.part_db != nullptr && pair == 0;   // one CTA per chunk sums dy for the bias gradient
+  float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
   auto gather = [&](const Tap& tp, bool tap_ok, bool pix_ok, int oy, int ox, long long n) -> float4 {
     // source of the tap (the fused skip projection reads a second tensor at its own stride)
     const float* src = tp.src ? a.src2 : a.src;
@@ -384,6 +386,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) tapwgrad_umma_kernel(const TapW
       split_store(a_hi, a_lo, g_off[i], av[i], X3);
       split_store(a_hi, a_lo, g_off[i] + 2 * 4096, av[2 + i], X3);  // second tap: channel blocks 2, 3
       split_store(b_hi, b_lo, g_off[i], bv[i], X3);
+      if (want_db) { dbs.x += bv[i].x; dbs.y += bv[i].y; dbs.z += bv[i].z; dbs.w += bv[i].w; }
     }
     fence_proxy_async();
     __syncthreads();
@@ -423,6 +426,17 @@ __global__ void __launch_bounds__(kWgThreads, 2) tapwgrad_umma_kernel(const TapW
   if (KB > 0) {
     mbar_wait(bars + kStages, 0);
     tc_fence_after();
+  }
+  if (want_db) {  // CTA-uniform.  All MMAs have retired: the stages are free for the 16-row reduction
+    float* red = reinterpret_cast<float*>(smem);
+    *reinterpret_cast<float4*>(red + g_k * 64 + g_c * 4) = dbs;
+    __syncthreads();
+    if (tid < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t += red[r * 64 + tid];
+      a.part_db[(long long)chunk * 64 + tid] = t;
+    }
   }
   {
     const uint32_t taddr = tmem_d + (static_cast<uint32_t>(q4 * 32) << 16);
