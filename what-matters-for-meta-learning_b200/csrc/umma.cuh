@@ -91,22 +91,30 @@ constexpr uint32_t kIdescTf32_128x64 = (1u << 4) | (2u << 7) | (2u << 10) | ((kB
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
   return static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
-// fp32 -> tf32 with round-to-nearest (the tensor core itself truncates: measured 2.3x the error of
-// cuDNN's RN path).  The result has its low 13 mantissa bits clear, so hardware truncation is a no-op.
+// fp32 -> tf32 with round-to-nearest, ties away from zero (the tensor core itself truncates: measured 2.3x the
+// error of cuDNN's RN path).  The result has its low 13 mantissa bits clear, so hardware truncation is a no-op.
+// Done on the bit pattern: adding half a tf32 ulp to the magnitude and clearing the low bits IS `cvt.rna.tf32.f32`
+// (Inf stays Inf, NaN stays NaN), in 2 integer instructions -- ptxas expands the cvt into ~5 (FADD/FSETP/SEL/LOP3),
+// which made the operand conversion the largest share of every staging loop (SASS: 530 instructions per thread and
+// K-block in the weight-gradient kernel, half of them this).
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 // X3: hi = rn_tf32(x), lo = rn_tf32(x - hi) (x - hi is exact in fp32); single pass: rn_tf32(x).
+// The stores are explicit st.shared with 32-bit addresses: through the 1024-byte alignment arithmetic on the
+// dynamic shared-memory base the compiler loses the address space and emits generic 64-bit ST.E (and splits some
+// of them into scalar stores).
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v, bool x3) {
   float4 h;
   h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-  *reinterpret_cast<float4*>(hi_base + off) = h;
+  sts128(smem_u32(hi_base) + off, h);
   if (x3) {
     float4 l;
     l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-    *reinterpret_cast<float4*>(lo_base + off) = l;
+    sts128(smem_u32(lo_base) + off, l);
   }
 }
 
