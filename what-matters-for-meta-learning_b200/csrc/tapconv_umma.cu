@@ -328,37 +328,45 @@ __global__ void __launch_bounds__(kWgThreads, 2) tapwgrad_umma_kernel(const TapW
   const bool t1_ok = t1 < a.ntaps;
   const Tap tpa = a.taps[t0], tpb = a.taps[t1_ok ? t1 : t0];
   const long long KB = p_begin < p_end ? ((p_end - p_begin + kWgK - 1) / kWgK) : 0;
-  // fetches run over consecutive K-blocks: walk (n, oy, ox) of pixel g_k incrementally (no divisions)
-  long long f_p = p_begin + g_k, f_n;
-  int f_ox, f_oy;
+  // fetches run over consecutive K-blocks: walk (n, oy, ox) of pixel g_k incrementally (no divisions).
+  // Everything is 32-bit (the launcher rejects more than 2^31 pixels) and the per-tap constants are hoisted:
+  // the gather is the instruction-issue bound of this kernel.
+  int f_p = (int)p_begin + g_k, f_n, f_ox, f_oy;
   {
-    f_ox = (int)(f_p % a.OW);
-    const long long q = f_p / a.OW;
-    f_oy = (int)(q % a.OH);
+    f_ox = f_p % a.OW;
+    const int q = f_p / a.OW;
+    f_oy = q % a.OH;
     f_n = q / a.OH;
   }
+  const int pe = (int)p_end;
+  struct TapC { const float* src; int sH, sW, ss, dy, dx; };
+  auto tapc = [&](const Tap& tp) {
+    TapC c;
+    c.src = (tp.src ? a.src2 : a.src) + g_c * 4;
+    c.sH = tp.src ? a.src2H : a.srcH; c.sW = tp.src ? a.src2W : a.srcW; c.ss = tp.src ? a.in_s2 : a.in_s;
+    c.dy = tp.dy; c.dx = tp.dx;
+    return c;
+  };
+  const TapC ta = tapc(tpa), tb = tapc(tpb);
+  const float* const dyp = a.dy + g_c * 4;
   float4 av0[4], bv0[2], av1[4], bv1[2];
   const bool want_db = a.part_db != nullptr && pair == 0;   // one CTA per chunk sums dy for the bias gradient
   float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto gather = [&](const Tap& tp, bool tap_ok, bool pix_ok, int oy, int ox, long long n) -> float4 {
-    // source of the tap (the fused skip projection reads a second tensor at its own stride)
-    const float* src = tp.src ? a.src2 : a.src;
-    const int sH = tp.src ? a.src2H : a.srcH, sW = tp.src ? a.src2W : a.srcW, ss = tp.src ? a.in_s2 : a.in_s;
-    const int iy = oy * ss + tp.dy, ix = ox * ss + tp.dx;
-    if (tap_ok && pix_ok && iy >= 0 && iy < sH && ix >= 0 && ix < sW)
-      return ldg4(src + ((n * sH + iy) * sW + ix) * 64 + g_c * 4);
+  auto gather = [&](const TapC& t, bool ok, int oy, int ox, int n) -> float4 {
+    const int iy = oy * t.ss + t.dy, ix = ox * t.ss + t.dx;
+    if (ok && (unsigned)iy < (unsigned)t.sH && (unsigned)ix < (unsigned)t.sW)
+      return ldg4(t.src + (long long)((n * t.sH + iy) * t.sW + ix) * 64);
     return make_float4(0.f, 0.f, 0.f, 0.f);
   };
   auto fetch = [&](long long, float4 (&av)[4], float4 (&bv)[2]) {
-    int ox = f_ox, oy = f_oy;
-    long long n = f_n;
+    int ox = f_ox, oy = f_oy, n = f_n;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const long long p = f_p + 16 * i;
-      const bool pix_ok = p < p_end;
-      av[i] = gather(tpa, true, pix_ok, oy, ox, n);
-      av[2 + i] = gather(tpb, t1_ok, pix_ok, oy, ox, n);
-      bv[i] = pix_ok ? ldg4(a.dy + p * 64 + g_c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int p = f_p + 16 * i;
+      const bool pix_ok = p < pe;
+      av[i] = gather(ta, pix_ok, oy, ox, n);
+      av[2 + i] = gather(tb, pix_ok && t1_ok, oy, ox, n);
+      bv[i] = pix_ok ? ldg4(dyp + (long long)p * 64) : make_float4(0.f, 0.f, 0.f, 0.f);
       ox += 16;
       while (ox >= a.OW) {
         ox -= a.OW;
@@ -504,6 +512,9 @@ int launch_tapconv_umma(const TapConvArgs& a, int precision, cudaStream_t st) {
 int launch_tapwgrad_umma(const TapWgradArgs& a, int precision, cudaStream_t st) {
   if (a.Cin != 64 || a.Cout != 64 || a.ntaps > kMaxTaps || a.ntaps < 1 || a.pix_per_chunk % kWgK != 0)
     return B200NP_E_UNSUPPORTED;
+  if ((long long)a.N * a.OH * a.OW >= (1LL << 31) - 64 || (long long)a.N * a.srcH * a.srcW >= (1LL << 31) ||
+      (long long)a.N * a.src2H * a.src2W >= (1LL << 31))
+    return B200NP_E_UNSUPPORTED;  // the kernel indexes pixels with 32-bit integers
   return precision == B200NP_PREC_TF32 ? launch_wgrad<false>(a, st) : launch_wgrad<true>(a, st);
 }
 
