@@ -213,7 +213,9 @@ def run_b200_arm(args, rank, world, local_rank):
     # end to end: pinned host inputs -> device every step, loss read back every step
     def e2e_step(i):
         if args.graph:
-            return float(gstep(host[i % nbatch]))        # H2D straight into the graph's static input buffers
+            # this step's inputs were put on the wire (pinned host -> device, copy stream) while the previous step
+            # computed; this call starts the copy of the next step's inputs and reads this step's loss back
+            return float(gstep(host[i % nbatch], next_batch=host[(i + 1) % nbatch]))
         b = [t.to(dev, non_blocking=True) for t in host[i % nbatch]]
         return float(step(b).detach())
     e2e_steps = max(3, min(args.steps, 10))

@@ -214,8 +214,10 @@ def test_cuda_graph_step_equals_eager():
             # capture + warm-up advanced the weights: rewind parameters and optimizer state
             model.load_state_dict(init)
             opt.m.zero_(), opt.v.zero_(), opt.t_dev.zero_()
-            for b in batches:
-                losses.append(float(g(b)))
+            # inputs come from pinned host memory through the prefetching pipeline (copy of batch i+1 overlaps step i)
+            hb = [[t.cpu().pin_memory() for t in b] for b in batches]
+            for i, b in enumerate(hb):
+                losses.append(float(g(b, next_batch=hb[i + 1] if i + 1 < len(hb) else None)))
         else:
             for cx, cy, tx, ty in batches:
                 opt.zero_grad()
