@@ -58,9 +58,12 @@ long long b200np_launch_count(void);
 /* precision (B200NP_PREC_*): the 1-channel 5x5 stem runs on tcgen05 in the TF32 modes (im2col tile built
  * in shared memory, K = 25 padded to one 32-wide K-block); every other variant and fp32 mode run on
  * CUDA cores in exact fp32. */
+/* relu_bits (nullable, tcgen05 stem only): the ReLU gates of y as 1 bit per element, [pixel][Cout/32] words,
+ * bit j of word h = channel 32 h + j -- what b200np_conv_dgrad takes as `mask_bits` (8 B per pixel instead of
+ * re-reading the 256 B activation). */
 int b200np_conv_small_fwd(const float* x, const float* w, const float* bias, float* y, int N,
                           int Cin, int H, int W, int Cout, int R, int stride, int pad, int relu,
-                          int precision, void* stream);
+                          int precision, uint32_t* relu_bits, void* stream);
 size_t b200np_conv_small_wgrad_workspace(int N, int Cin, int H, int W, int Cout, int R, int stride,
                                          int pad, int precision);
 /* dy NHWC is the gradient w.r.t. the pre-activation output; writes dw [Cout,Cin,R,R], db [Cout] */
@@ -95,10 +98,12 @@ int b200np_conv_fwd(const float* x, const float* wf, const float* bias, float* y
 /* dx = relu_mask(act_saved) * ( dgrad_RxR(dy; wd, stride) [+ dgrad_1x1(dys; wsd, stride_s)] )
  * dy [N,H/stride,W/stride,Cout] -> dx [N,H,W,Cin]; `mask_src` (same shape as dx, may be NULL) is
  * the saved post-ReLU activation whose positivity gates the gradient; optional second gradient
- * source dys [N,H/stride_s,W/stride_s,Cs] through a 1x1 stride_s conv (the skip projection). */
-int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, const float* mask_src, int N, int H,
-                      int W, int Cin, int Cout, int R, int stride, const float* dys, const float* wsd,
-                      int Cs, int stride_s, int precision, void* stream);
+ * source dys [N,H/stride_s,W/stride_s,Cs] through a 1x1 stride_s conv (the skip projection).
+ * `mask_bits` (nullable, 64-channel dx only) is the same gate packed 1 bit per element (see
+ * b200np_conv_small_fwd) and takes precedence over mask_src. */
+int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, const float* mask_src,
+                      const uint32_t* mask_bits, int N, int H, int W, int Cin, int Cout, int R, int stride,
+                      const float* dys, const float* wsd, int Cs, int stride_s, int precision, void* stream);
 
 size_t b200np_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int stride);
 /* dw [Cout,Cin,R,R] (torch layout) = sum over pixels of dy (x) im2col(x);  db [Cout] = sum dy

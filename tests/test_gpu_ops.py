@@ -331,3 +331,43 @@ def test_gemm_sum_groups(prec, rows, H, d, K):
     ops.gemm([dyc.data_ptr() + 4 * h * d for h in range(H)], [w.data_ptr() for w in wc], [dx.data_ptr()] * H,
              rows, K, d, H * d, 1, K, 1, K, prec=P, sum_groups=True)
     assert rel(dx, ref) < (2e-3 if prec == "tf32" else 3e-6)
+
+
+def _pack_bits(act_nhwc):
+    """[N,H,W,64] -> int32 [N,H,W,2]: bit j of word h = (act[..., 32h + j] > 0) (include/b200np.h)."""
+    g = (act_nhwc > 0).to(torch.int64).reshape(*act_nhwc.shape[:-1], 2, 32)
+    w = (g << torch.arange(32, device=g.device, dtype=torch.int64)).sum(-1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32"])
+def test_stem_relu_bits(prec):
+    """The tcgen05 stem writes the ReLU gates of its output as 1 bit per element."""
+    ops = _ops()
+    from b200np import lib
+    P = {"tf32x3": lib.PREC_TF32X3, "tf32": lib.PREC_TF32}[prec]
+    x, w, b = rnd(5, 1, 64, 64, seed=1).float().cuda(), rnd(64, 1, 5, 5, seed=2, scale=0.2).float().cuda(), rnd(64, seed=3).float().cuda()
+    bits = torch.full((5, 32, 32, 2), 0x5a5a5a5a, device="cuda", dtype=torch.int32)
+    y = ops.conv_small_fwd(x, w, b, prec=P, relu_bits=bits)
+    assert torch.equal(bits, _pack_bits(y))
+    assert 0.2 < float((y > 0).float().mean()) < 0.8
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("hw,n,stride", [(64, 2, 2), (32, 3, 1), (8, 4, 2), (8, 4, 1)])
+def test_conv_dgrad_mask_bits_equals_float_mask(prec, hw, n, stride):
+    """The packed gates give bit-identical data gradients to the float activation mask on every kernel path
+    (halo incl. the fused stride-2 classes, gather, CUDA cores)."""
+    ops = _ops()
+    from b200np import lib
+    P = {"fp32": lib.PREC_FP32_SIMT, "tf32x3": lib.PREC_TF32X3}[prec]
+    w = rnd(64, 64, 3, 3, seed=5, scale=0.05).float().cuda()
+    ws = rnd(64, 64, 1, 1, seed=6, scale=0.1).float().cuda()
+    pw, pws = ops.pack_conv_weight(w), ops.pack_conv_weight(ws)
+    act = rnd(n, hw, hw, 64, seed=7).float().cuda()                       # NHWC activation whose sign gates dx
+    dy = rnd(n, hw // stride, hw // stride, 64, seed=8).float().cuda()
+    skip = (rnd(n, hw // stride, hw // stride, 64, seed=9).float().cuda(), pws, 2) if stride == 2 else None
+    a = ops.conv_dgrad(dy, pw, act.shape, stride, P, mask_src=act, skip=skip)
+    b = ops.conv_dgrad(dy, pw, act.shape, stride, P, mask_src=None, skip=skip, mask_bits=_pack_bits(act))
+    assert torch.equal(a, b)
+    assert float((a == 0).float().mean()) > 0.3

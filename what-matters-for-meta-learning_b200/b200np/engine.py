@@ -50,10 +50,17 @@ class TrunkFn(Function):
         N = sum(Ns)
         _, H, W = imgs[0].shape[1:]
         x0 = ops.empty((N, H // 2, W // 2, 64), imgs[0])
+        # 1-bit ReLU gates of the stem output: the stride-2 data gradient of layer1 ends in this tensor and would
+        # otherwise re-read all of it (1 MB per image) just for the sign
+        bits0 = None
+        if ops.relu_bits_supported(imgs[0].shape[1], c1w.shape[2], c1w.shape[0], prec):
+            bits0 = torch.empty((N, H // 2, W // 2, 2), device=x0.device, dtype=torch.int32)
         off = 0
         for im, n in zip(imgs, Ns):
-            ops.conv_small_fwd(im, c1w, c1b, out=x0[off:off + n], relu=True, prec=prec)
+            ops.conv_small_fwd(im, c1w, c1b, out=x0[off:off + n], relu=True, prec=prec,
+                               relu_bits=None if bits0 is None else bits0[off:off + n])
             off += n
+        ctx.bits0 = bits0
         x, acts, packs = x0, [], []
         for l in range(4):
             w1, b1, w2, b2, wsk, bsk = params[2 + 6 * l: 8 + 6 * l]
@@ -104,7 +111,8 @@ class TrunkFn(Function):
                 dw2, db2, dws = ops.conv_wgrad(h, dy, 3, 1, prec, skip=(x, 2))
             dh = ops.conv_dgrad(dy, p2, h.shape, 1, prec, mask_src=h)
             dw1, db1, _ = ops.conv_wgrad(x, dh, 3, 2, prec)
-            dx = ops.conv_dgrad(dh, p1, x.shape, 2, prec, mask_src=x, skip=(dy, ps, 2))
+            dx = ops.conv_dgrad(dh, p1, x.shape, 2, prec, mask_src=x, skip=(dy, ps, 2),
+                                mask_bits=ctx.bits0 if l == 0 else None)
             grads[2 + 6 * l: 8 + 6 * l] = [dw1, db1, dw2, db2, dws, db2.clone()]
             dy = dx
         off, dw_acc, db_acc = 0, None, None

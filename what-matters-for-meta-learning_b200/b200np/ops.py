@@ -36,8 +36,14 @@ def empty(shape, like, dtype=F32):
 # ----------------------------------------------------------------------------------------------
 # convolutions
 # ----------------------------------------------------------------------------------------------
-def conv_small_fwd(x, w, b, out=None, relu=True, prec=lib.PREC_FP32_SIMT):
-    """x NCHW [N,Cin,H,W] -> NHWC [N,H/2,W/2,Cout] (stride 2, pad R//2)."""
+def relu_bits_supported(Cin, R, Cout, prec):
+    """The tcgen05 stem kernel can emit the packed ReLU gates (include/b200np.h)."""
+    return prec != lib.PREC_FP32_SIMT and (Cin, R, Cout) == (1, 5, 64)
+
+
+def conv_small_fwd(x, w, b, out=None, relu=True, prec=lib.PREC_FP32_SIMT, relu_bits=None):
+    """x NCHW [N,Cin,H,W] -> NHWC [N,H/2,W/2,Cout] (stride 2, pad R//2).  relu_bits: optional int32 tensor
+    [N,H/2,W/2,2] receiving the ReLU gates, 1 bit per element."""
     for t, n in ((x, "x"), (w, "w"), (b, "b"), (out, "out")):
         _chk(t, n)
     N, Cin, H, W = x.shape
@@ -45,7 +51,7 @@ def conv_small_fwd(x, w, b, out=None, relu=True, prec=lib.PREC_FP32_SIMT):
     if out is None:
         out = empty((N, H // 2, W // 2, Cout), x)
     check(LIB.b200np_conv_small_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(out), N, Cin, H, W, Cout, R, 2, R // 2,
-                                    int(relu), prec, _stream()), "conv_small_fwd")
+                                    int(relu), prec, _ptr(relu_bits), _stream()), "conv_small_fwd")
     return out
 
 
@@ -99,7 +105,7 @@ def conv_fwd(x, pw, bias, stride, act, prec, skip=None):
     return y
 
 
-def conv_dgrad(dy, pw, x_shape, stride, prec, mask_src=None, skip=None):
+def conv_dgrad(dy, pw, x_shape, stride, prec, mask_src=None, skip=None, mask_bits=None):
     """dy NHWC [N,H/stride,W/stride,Cout] -> dx [N,H,W,Cin], gated by mask_src > 0;
     skip = (dys, pws, stride_s) adds the gradient through a 1x1 stride_s projection."""
     _chk(dy, "dy"), _chk(pw.d, "wd"), _chk(mask_src, "mask")
@@ -113,7 +119,7 @@ def conv_dgrad(dy, pw, x_shape, stride, prec, mask_src=None, skip=None):
         dys, pws, ss = skip
         _chk(dys, "dys"), _chk(pws.d, "wsd")
         wsd, Cs = pws.d, dys.shape[3]
-    check(LIB.b200np_conv_dgrad(_ptr(dy), _ptr(pw.d), _ptr(dx), _ptr(mask_src), N, H, W, Cin, Cout, pw.R, stride,
+    check(LIB.b200np_conv_dgrad(_ptr(dy), _ptr(pw.d), _ptr(dx), _ptr(mask_src), _ptr(mask_bits), N, H, W, Cin, Cout, pw.R, stride,
                                 _ptr(dys), _ptr(wsd), Cs, ss, prec, _stream()), "conv_dgrad")
     return dx
 

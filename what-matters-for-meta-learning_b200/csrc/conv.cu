@@ -116,9 +116,10 @@ extern "C" int b200np_conv_fwd(const float* x, const float* wf, const float* bia
                      (img && xs) ? wsf + 4096 : nullptr, 1);
 }
 
-extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, const float* mask_src, int N, int H,
-                                 int W, int Cin, int Cout, int R, int stride, const float* dys, const float* wsd,
-                                 int Cs, int stride_s, int precision, void* stream) {
+extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, const float* mask_src,
+                                 const uint32_t* mask_bits, int N, int H, int W, int Cin, int Cout, int R, int stride,
+                                 const float* dys, const float* wsd, int Cs, int stride_s, int precision,
+                                 void* stream) {
   if (!dy || !wd || !dx || N <= 0 || H <= 0 || W <= 0) return B200NP_E_BADARG;
   if ((R != 1 && R != 3) || (stride != 1 && stride != 2) || H % stride || W % stride) return B200NP_E_UNSUPPORTED;
   if (dys && (!wsd || Cs != Cout || stride_s != stride || stride != 2)) return B200NP_E_UNSUPPORTED;
@@ -133,7 +134,8 @@ extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, co
   a.Cin = Cout;  // reduction runs over the conv's output channels
   a.Cout = Cin;  // and produces the conv's input channels
   a.bias = a.bias2 = nullptr;
-  a.dst = dx; a.mask = mask_src;
+  if (mask_bits && Cin != 64) return B200NP_E_UNSUPPORTED;  // the packed gates are defined for 64-channel tensors
+  a.dst = dx; a.mask = mask_src; a.mask_bits = mask_bits;
   a.N = N; a.dstH = H; a.dstW = W;
   a.act = B200NP_ACT_NONE;
   cudaStream_t st = as_stream(stream);

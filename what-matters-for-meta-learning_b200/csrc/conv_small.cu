@@ -12,8 +12,8 @@ using namespace b200np;
 
 namespace b200np {  // conv_stem_umma.cu
 bool stem_umma_supported(int Cin, int R, int Cout, int precision);
-int launch_stem_fwd_umma(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int relu,
-                         int precision, cudaStream_t st);
+int launch_stem_fwd_umma(const float* x, const float* w, const float* bias, float* y, uint32_t* relu_bits, int N, int H,
+                         int W, int relu, int precision, cudaStream_t st);
 size_t stem_wgrad_umma_workspace(int N, int H, int W);
 int launch_stem_wgrad_umma(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int precision,
                            void* ws, size_t ws_bytes, cudaStream_t st);
@@ -273,13 +273,15 @@ bool supported(int Cin, int R, int Cout, int stride, int pad, int H, int W) {
 
 extern "C" int b200np_conv_small_fwd(const float* x, const float* w, const float* bias, float* y, int N, int Cin,
                                      int H, int W, int Cout, int R, int stride, int pad, int relu, int precision,
-                                     void* stream) {
+                                     uint32_t* relu_bits, void* stream) {
   if (!x || !w || !bias || !y || N <= 0) return B200NP_E_BADARG;
   if (!supported(Cin, R, Cout, stride, pad, H, W)) return B200NP_E_UNSUPPORTED;
   if (!aligned16(y) || !aligned16(bias)) return B200NP_E_BADARG;
   const int OH = H / 2, OW = W / 2;
   cudaStream_t st = as_stream(stream);
-  if (stem_umma_supported(Cin, R, Cout, precision)) return launch_stem_fwd_umma(x, w, bias, y, N, H, W, relu, precision, st);
+  if (stem_umma_supported(Cin, R, Cout, precision))
+    return launch_stem_fwd_umma(x, w, bias, y, relu_bits, N, H, W, relu, precision, st);
+  if (relu_bits) return B200NP_E_UNSUPPORTED;  // only the tcgen05 stem writes the 1-bit gates
   const long long tiles = (long long)N * ((OH + kFwdTH - 1) / kFwdTH) * ((OW + kTW - 1) / kTW);
   const long long cap = 8LL * kNumSMs;
   const int grid = (int)(tiles < cap ? tiles : cap);

@@ -56,7 +56,8 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 template <bool X3>
 __global__ void __launch_bounds__(128, 4)
     stem_fwd_umma_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                         float* __restrict__ y, int N, int H, int W, int relu, long long tiles) {
+                         float* __restrict__ y, uint32_t* __restrict__ relu_bits, int N, int H, int W, int relu,
+                         long long tiles) {
   constexpr uint32_t kA = 128 * 32 * 4, kB = 64 * 32 * 4;
   constexpr uint32_t kCols = X3 ? 128 : 64;
   extern __shared__ uint8_t smem_raw[];
@@ -201,6 +202,13 @@ __global__ void __launch_bounds__(128, 4)
         const int rr = it * 2 + (lane >> 4);
         const float4 o = *reinterpret_cast<const float4*>(piece + rr * 128 + ((j ^ (rr & 7)) << 4));
         if (p_base + rr < M) *reinterpret_cast<float4*>(y + (p_base + rr) * 64 + c * 4) = o;
+        if (relu_bits) {  // 1-bit ReLU gates for the data gradient that ends in this tensor: [pixel][2] words
+          uint32_t wbits = ((o.x > 0.f) | ((o.y > 0.f) << 1) | ((o.z > 0.f) << 2) | ((o.w > 0.f) << 3)) << (4 * j);
+          wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+          wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+          wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);   // the 8 lanes of one 32-channel half
+          if (j == 0 && p_base + rr < M) relu_bits[(p_base + rr) * 2 + h] = wbits;
+        }
       }
     }
     __syncwarp();
@@ -392,8 +400,8 @@ bool stem_umma_supported(int Cin, int R, int Cout, int precision) {
   return precision != B200NP_PREC_FP32_SIMT && Cin == 1 && R == 5 && Cout == 64;
 }
 
-int launch_stem_fwd_umma(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int relu,
-                         int precision, cudaStream_t st) {
+int launch_stem_fwd_umma(const float* x, const float* w, const float* bias, float* y, uint32_t* relu_bits, int N, int H,
+                         int W, int relu, int precision, cudaStream_t st) {
   const bool x3 = precision != B200NP_PREC_TF32;
   const long long M = (long long)N * (H / 2) * (W / 2);
   const long long tiles = ceil_div(M, 128);
@@ -406,8 +414,8 @@ int launch_stem_fwd_umma(const float* x, const float* w, const float* bias, floa
   }
   const long long cap = 4LL * kNumSMs;
   const int grid = (int)(tiles < cap ? tiles : cap);
-  if (x3) stem_fwd_umma_kernel<true><<<grid, 128, smem, st>>>(x, w, bias, y, N, H, W, relu, tiles);
-  else stem_fwd_umma_kernel<false><<<grid, 128, smem, st>>>(x, w, bias, y, N, H, W, relu, tiles);
+  if (x3) stem_fwd_umma_kernel<true><<<grid, 128, smem, st>>>(x, w, bias, y, relu_bits, N, H, W, relu, tiles);
+  else stem_fwd_umma_kernel<false><<<grid, 128, smem, st>>>(x, w, bias, y, relu_bits, N, H, W, relu, tiles);
   return launch_status();
 }
 

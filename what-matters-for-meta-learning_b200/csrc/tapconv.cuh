@@ -36,6 +36,9 @@ struct TapConvArgs {
   const float* bias2;  // nullable
   float* dst;
   const float* mask;   // nullable; same geometry as dst: result *= (mask > 0)
+  const uint32_t* mask_bits;  // nullable, takes precedence over `mask`: the same gate as 1 bit per element,
+                              // [dst pixel][Cout / 32] words, bit j of word h = channel 32 h + j (8 B instead of
+                              // 256 B read per pixel); written by the forward kernels' ReLU epilogues
   int N, OH, OW;       // pixel grid of this launch
   int dstH, dstW, dst_s, dst_oy, dst_ox;  // dst pixel = (oy*dst_s + dst_oy, ox*dst_s + dst_ox)
   int ntaps;

@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           tc_fence_before();
           mbar_arrive(acc_empty + set);
         }
+        const uint32_t mword = a.mask_bits ? __ldg(a.mask_bits + (off >> 6) * 2 + hf) : 0u;   // 32 ReLU gates
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq) {
           const int c = hf * 32 + 4 * qq;
@@ -455,7 +456,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             const float4 b = ldg4(a.bias2 + c);
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
-          if (a.mask && !(dflags & 4)) {
+          if (a.mask_bits) {
+            const uint32_t nb4 = mword >> (4 * qq);
+            o.x = (nb4 & 1u) ? o.x : 0.f; o.y = (nb4 & 2u) ? o.y : 0.f;
+            o.z = (nb4 & 4u) ? o.z : 0.f; o.w = (nb4 & 8u) ? o.w : 0.f;
+          } else if (a.mask && !(dflags & 4)) {
             const float4 mk = ldg4(a.mask + off + c);
             o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
             o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;

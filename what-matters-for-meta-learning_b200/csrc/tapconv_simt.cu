@@ -122,7 +122,11 @@ __global__ void __launch_bounds__(128) tapconv_simt_kernel(const TapConvArgs a) 
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = acc[i][j] + bsum[j];
-    if (a.mask) {
+    if (a.mask_bits) {  // Cout == 64 (checked by the caller): two 32-bit words per pixel
+      const uint32_t byte = __ldg(a.mask_bits + (off >> 6) * 2 + (co0 >> 5)) >> (co0 & 31);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = ((byte >> j) & 1u) ? o[j] : 0.f;
+    } else if (a.mask) {
       const float4 m0v = ldg4(a.mask + off), m1v = ldg4(a.mask + off + 4);
       const float mk[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
 #pragma unroll

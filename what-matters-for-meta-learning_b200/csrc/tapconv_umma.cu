@@ -210,7 +210,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) tapconv_umma_kernel(const Tap
       float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4));
       if (off < 0) continue;
       o.x += bsum.x; o.y += bsum.y; o.z += bsum.z; o.w += bsum.w;
-      if (a.mask) {
+      if (a.mask_bits) {
+        const uint32_t nb4 = __ldg(a.mask_bits + (off >> 6) * 2 + half) >> (4 * cj);
+        o.x = (nb4 & 1u) ? o.x : 0.f; o.y = (nb4 & 2u) ? o.y : 0.f;
+        o.z = (nb4 & 4u) ? o.z : 0.f; o.w = (nb4 & 8u) ? o.w : 0.f;
+      } else if (a.mask) {
         const float4 mk = ldg4(a.mask + off + c);
         o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
         o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
