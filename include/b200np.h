@@ -209,6 +209,12 @@ int b200np_ctx_aggregate_fwd(const float* feats, float* out, int32_t* idx, int T
                              int mode, void* stream);
 int b200np_ctx_aggregate_bwd(const float* dout, const int32_t* idx, float* dfeats, int T, int nc, int D,
                              int mode, void* stream);
+/* Bayesian context aggregation "baco" (networks/CNPDistractor.py:60-75,104-110): mu, s [T,nc,D] (s = the
+ * pre-softplus output of latent_var) -> r [T,D];  var = 1e-5 + softplus(s), prior N(0,1).  The backward
+ * recomputes the sums from mu, s and r. */
+int b200np_baco_fwd(const float* mu, const float* s, float* r, int T, int nc, int D, void* stream);
+int b200np_baco_bwd(const float* dr, const float* mu, const float* s, const float* r, float* dmu, float* ds,
+                    int T, int nc, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * FAVOR+ (Performer) attention exactly as networks/fast_attention.py:74-99,151-156 computes it

@@ -371,3 +371,24 @@ def test_conv_dgrad_mask_bits_equals_float_mask(prec, hw, n, stride):
     b = ops.conv_dgrad(dy, pw, act.shape, stride, P, mask_src=None, skip=skip, mask_bits=_pack_bits(act))
     assert torch.equal(a, b)
     assert float((a == 0).float().mean()) > 0.3
+
+
+def test_baco_aggregation():
+    """Bayesian context aggregation forward/backward against torch fp64 autograd (CNPDistractor.py:60-75)."""
+    ops = _ops()
+    T, nc, D = 3, 7, 256
+    mu = rnd(T, nc, D, seed=1).requires_grad_(True)
+    s = (rnd(T, nc, D, seed=2) * 3).requires_grad_(True)      # covers softplus' linear branch (> 20 is rare: add one)
+    with torch.no_grad():
+        s[0, 0, 0] = 25.0
+    var = 1e-5 + F.softplus(s)
+    sig_inv = 1.0 / var
+    sz = 1.0 / (1.0 + sig_inv.sum(1))
+    ref = sz * (sig_inv * mu).sum(1)
+    dr = rnd(T, D, seed=3)
+    ref.backward(dr)
+    r = ops.baco_fwd(mu.detach().float().cuda(), s.detach().float().cuda())
+    assert rel(r, ref) < 2e-6
+    dmu, ds = ops.baco_bwd(dr.float().cuda(), mu.detach().float().cuda(), s.detach().float().cuda(), r)
+    assert rel(dmu, mu.grad) < 5e-6
+    assert rel(ds, s.grad) < 5e-6

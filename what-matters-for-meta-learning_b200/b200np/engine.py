@@ -287,6 +287,22 @@ class AggregateFn(Function):
         return None, ops.ctx_aggregate_bwd(dout.contiguous(), ctx.idx, T, nc, D, ctx.mode)
 
 
+class BacoFn(Function):
+    """Bayesian context aggregation (networks/CNPDistractor.py:60-75,104-110): mu, s [T,nc,D] -> r [T,D]."""
+
+    @staticmethod
+    def forward(ctx, mu, s):
+        mu, s = mu.contiguous(), s.contiguous()
+        r = ops.baco_fwd(mu, s)
+        ctx.save_for_backward(mu, s, r)
+        return r
+
+    @staticmethod
+    def backward(ctx, dr):
+        mu, s, r = ctx.saved_tensors
+        return ops.baco_bwd(dr.contiguous(), mu, s, r)
+
+
 class RepeatFn(Function):
     """x[:, None, :].repeat(1, rep, 1) (networks/CNPDistractor.py:99)."""
 
@@ -428,9 +444,12 @@ def _forward_resnet_family(m, ctx_x, ctx_y, tgt_x):
             rep = _attention(m, T, nt, nc, x_ctx, cf, x_tgt)
             sample = _lin(ACT_NONE, rep, None, m.mu)
         else:
-            if m.agg_mode == "baco":
-                raise NotImplementedError("agg_mode='baco' is not on the CUDA path yet (SURVEY.md 8a/a8)")
-            r = AggregateFn.apply(0 if m.agg_mode == "mean" else 1, cf.view(T, nc, -1))
+            if m.agg_mode == "baco":   # CNPDistractor.py:104-110
+                lm = _lin(ACT_NONE, cf, None, m.latent_mu)
+                ls = _lin(ACT_NONE, cf, None, m.latent_var)
+                r = BacoFn.apply(lm.view(T, nc, -1), ls.view(T, nc, -1))
+            else:
+                r = AggregateFn.apply(0 if m.agg_mode == "mean" else 1, cf.view(T, nc, -1))
             sample = RepeatFn.apply(nt, _lin(ACT_NONE, r, None, m.mu))
     else:
         sample = ops.zeros((T * nt, 256), tgt_imgs)
@@ -465,7 +484,10 @@ def _forward_shapenet1d_family(m, ctx_x, ctx_y, tgt_x):
             z = _lin(ACT_NONE, r, None, m.r_to_z)
         else:
             if m.agg_mode == "baco":
-                raise NotImplementedError("agg_mode='baco' is not on the CUDA path yet (SURVEY.md 8a/a8)")
+                # CNPShapeNet1D.py:74-76 builds rs_to_mu / rs_to_var as Linear(256, 256) but feeds them dim_r-wide
+                # features (100 in every shipped config): the reference itself fails on this path
+                raise NotImplementedError("agg_mode='baco' is shape-inconsistent in the reference's ShapeNet1D CNP "
+                                          "(SURVEY.md 8a/a8)")
             if m.agg_mode not in ("mean", "max"):
                 raise TypeError("agg_mode is not applicable for CNP, choose from ['mean', 'max', 'baco']")
             r = AggregateFn.apply(0 if m.agg_mode == "mean" else 1, rs.view(T, nc, -1))

@@ -58,6 +58,8 @@ SIGNATURES = {
     "b200np_scale_by_device_scalar": (_i, [_p, _p, _p, _ll, _p]),
     "b200np_ctx_aggregate_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "b200np_ctx_aggregate_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "b200np_baco_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "b200np_baco_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "b200np_favor_rowstats": (_i, [_p, _p, _p, _p, _p, _ll, _i, _i, _ll, _p]),
     "b200np_reduce": (_i, [_p, _ll, _p, _i, _p]),
     "b200np_favor_attn_fwd": (_i, [_p] * 11 + [_i] * 6 + [_ll, _p]),

@@ -319,6 +319,22 @@ def ctx_aggregate_bwd(dout, idx, T, nc, D, mode):
     return df
 
 
+def baco_fwd(mu, s):
+    _chk(mu, "mu"), _chk(s, "s")
+    T, nc, D = mu.shape
+    r = empty((T, D), mu)
+    check(LIB.b200np_baco_fwd(_ptr(mu), _ptr(s), _ptr(r), T, nc, D, _stream()), "baco_fwd")
+    return r
+
+
+def baco_bwd(dr, mu, s, r):
+    _chk(dr, "dr")
+    T, nc, D = mu.shape
+    dmu, ds = torch.empty_like(mu), torch.empty_like(s)
+    check(LIB.b200np_baco_bwd(_ptr(dr), _ptr(mu), _ptr(s), _ptr(r), _ptr(dmu), _ptr(ds), T, nc, D, _stream()), "baco_bwd")
+    return dmu, ds
+
+
 def loss_fwd_bwd(mu, y, kind, want_grad=True):
     _chk(mu, "mu"), _chk(y, "y")
     R = mu.numel() // mu.shape[-1]

@@ -319,6 +319,58 @@ extern "C" int b200np_ctx_aggregate_bwd(const float* dout, const int32_t* idx, f
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bayesian context aggregation (networks/CNPDistractor.py:60-75,104-110): per task and feature, with
+//   var_i = 1e-5 + softplus(s_i),  a_i = 1 / var_i,  sigma_z = 1 / (1 + sum_i a_i),  r = sigma_z * sum_i a_i mu_i
+// (prior mean 0, variance 1).  softplus follows torch (threshold 20).  One thread per (task, feature).
+// Backward:  d mu_i = dr * sigma_z * a_i,   d s_i = -dr * sigma_z * (mu_i - r) * a_i^2 * sigmoid(s_i).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__global__ void baco_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ s, float* __restrict__ r,
+                                int T, int nc, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * D) return;
+  const int t = (int)(i / D), dd = (int)(i - (long long)t * D);
+  float A = 0.f, B = 0.f;
+  for (int j = 0; j < nc; ++j) {
+    const long long o = ((long long)t * nc + j) * D + dd;
+    const float a = 1.f / (1e-5f + softplus_t(s[o]));
+    A += a;
+    B = fmaf(a, mu[o], B);
+  }
+  r[i] = B / (1.f + A);
+}
+__global__ void baco_bwd_kernel(const float* __restrict__ dr, const float* __restrict__ mu, const float* __restrict__ s,
+                                const float* __restrict__ r, float* __restrict__ dmu, float* __restrict__ ds, int T,
+                                int nc, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * D) return;
+  const int t = (int)(i / D), dd = (int)(i - (long long)t * D);
+  float A = 0.f;
+  for (int j = 0; j < nc; ++j) A += 1.f / (1e-5f + softplus_t(s[((long long)t * nc + j) * D + dd]));
+  const float sz = 1.f / (1.f + A), g = dr[i] * sz, ri = r[i];
+  for (int j = 0; j < nc; ++j) {
+    const long long o = ((long long)t * nc + j) * D + dd;
+    const float x = s[o], a = 1.f / (1e-5f + softplus_t(x));
+    const float sig = x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
+    dmu[o] = g * a;
+    ds[o] = -g * (mu[o] - ri) * a * a * sig;
+  }
+}
+extern "C" int b200np_baco_fwd(const float* mu, const float* s, float* r, int T, int nc, int D, void* stream) {
+  if (!mu || !s || !r || T <= 0 || nc <= 0 || D <= 0) return B200NP_E_BADARG;
+  const long long n = (long long)T * D;
+  baco_fwd_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(mu, s, r, T, nc, D);
+  return launch_status();
+}
+extern "C" int b200np_baco_bwd(const float* dr, const float* mu, const float* s, const float* r, float* dmu, float* ds,
+                               int T, int nc, int D, void* stream) {
+  if (!dr || !mu || !s || !r || !dmu || !ds || T <= 0 || nc <= 0 || D <= 0) return B200NP_E_BADARG;
+  const long long n = (long long)T * D;
+  baco_bwd_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(dr, mu, s, r, dmu, ds, T, nc, D);
+  return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Losses: one block; rows are tiny ([T*nt, 2|4]).  Writes the mean loss and d loss / d mu.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
