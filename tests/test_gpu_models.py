@@ -255,3 +255,14 @@ def test_evaluation_shapes_and_degree_loss():
             loss_o = np_oracle.calc_loss(task, mu_o, torch.from_numpy(batch[3]), test=True)
         assert rel_l2(mu.cpu().numpy(), mu_o.numpy()) < 1e-3, case
         assert abs(float(loss) - float(loss_o)) < 1e-3 * abs(float(loss_o)), (case, float(loss), float(loss_o))
+        # the same forward as a per-shape CUDA graph (b200np.optim.GraphedEval), twice: capture, then replay
+        from b200np.optim import GraphedEval
+        ge = GraphedEval(model, LossFunc("mse", task))
+        for _ in range(2):
+            mu_g, loss_g = ge(cx, cy, tx, ty)
+            assert torch.equal(mu_g, mu) and float(loss_g) == float(loss)
+        batch2 = synth.task_batch(task, T, nc, nt, seed=4)
+        mu_g2, _ = ge(*(torch.from_numpy(a).cuda() for a in batch2))
+        with torch.no_grad():
+            mu2, _, _ = model(*(torch.from_numpy(a).cuda() for a in batch2[:3]), test=True)
+        assert torch.equal(mu_g2, mu2) and len(ge.cache) == 1

@@ -160,3 +160,47 @@ class GraphedStep:
         if next_batch is not None:
             self.prefetch(next_batch)
         return self.loss
+
+
+class GraphedEval:
+    """The validation / evaluation forward (evaluator/model_evaluator.py:144-179: no-grad `model(ctx_x, ctx_y,
+    tgt_x, test=True)` + `calc_loss(test=True)`) as CUDA graphs, one per (context, target) shape -- the evaluator
+    sweeps nc = 1..25 with all views as targets, so a handful of shapes repeat for thousands of tasks.
+    Returns `(mu, loss)`; both live in static buffers that the next call with the same shape overwrites."""
+
+    def __init__(self, model, lossf=None, warmup=1):
+        self.model, self.lossf, self.warmup = model, lossf, warmup
+        self.cache = {}
+
+    def _forward(self, cx, cy, tx, ty):
+        mu, _, _ = self.model(cx, cy, tx, test=True)
+        loss = self.lossf.calc_loss(mu, None, ty, test=True) if (self.lossf is not None and ty is not None) else None
+        return mu, loss
+
+    def __call__(self, ctx_x, ctx_y, tgt_x, tgt_y=None):
+        batch = [ctx_x, ctx_y, tgt_x] + ([tgt_y] if tgt_y is not None else [])
+        key = tuple(tuple(t.shape) for t in batch)
+        ent = self.cache.get(key)
+        if ent is None:
+            static = [torch.empty(t.shape, device=tgt_x.device if tgt_x.is_cuda else "cuda", dtype=t.dtype) for t in batch]
+            for s_, t in zip(static, batch):
+                s_.copy_(t)
+            args = static + [None] * (4 - len(static))
+            with torch.no_grad():
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(self.warmup):
+                        self._forward(*args)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self._forward(*args)
+            ent = self.cache[key] = (graph, static, out)
+        graph, static, out = ent
+        for s_, t in zip(static, batch):
+            if s_.data_ptr() != t.data_ptr():
+                s_.copy_(t, non_blocking=True)
+        graph.replay()
+        return out
