@@ -190,6 +190,13 @@ int b200np_axpy(float* y, const float* x, long long n, float a, void* stream); /
  * (replaces autograd's per-parameter accumulate kernels).  src / dst_off / numel are HOST arrays. */
 int b200np_multi_copy(const float* const* src, const long long* dst_off, const long long* numel, int nseg,
                       float* dst, void* stream);
+
+/* Device-side task assembly: out [M,C,H,W] fp32 = (255 - bank[rows[m]]) / 255 from a uint8 channel-last image bank
+ * [n,H,W,C] resident in HBM (dataset/shapenet_distractor.py:233-234,256-259 + utils/utils.py:26-30: `255 - x`,
+ * `astype(float32) / 255.0`, channel-last -> NCHW).  With the bank on the device a training step uploads the few KB
+ * of row indices and labels instead of 47 MB of images.  H*W must be a multiple of 4. */
+int b200np_gather_images_u8(const uint8_t* bank, const int32_t* rows, float* out, long long M, int H, int W,
+                            int C, void* stream);
 /* y[r, :] = x[r / rep, :] (rep consecutive copies of each row; the reference's .repeat) */
 int b200np_repeat_rows(const float* x, float* y, long long rows_in, int rep, int cols, void* stream);
 /* x[r,:] = sum over the rep copies of dy (backward of repeat_rows) */

@@ -255,6 +255,20 @@ def zeros(shape, like):
     return fill(empty(shape, like), 0.0)
 
 
+def gather_images_u8(bank, rows, out=None):
+    """bank uint8 [n,H,W,C] (CUDA), rows int32 [...] (CUDA) -> fp32 [..., C, H, W] = (255 - bank[rows]) / 255."""
+    if not (bank.is_cuda and rows.is_cuda and bank.dtype == torch.uint8 and rows.dtype == torch.int32):
+        raise lib.B200NPError("gather_images_u8: needs a CUDA uint8 bank and CUDA int32 row indices")
+    if not (bank.is_contiguous() and rows.is_contiguous()):
+        raise lib.B200NPError("gather_images_u8: tensors must be contiguous")
+    _, H, W, Cc = bank.shape
+    if out is None:
+        out = torch.empty(tuple(rows.shape) + (Cc, H, W), device=bank.device, dtype=F32)
+    check(LIB.b200np_gather_images_u8(_ptr(bank), _ptr(rows), _ptr(out), rows.numel(), H, W, Cc, _stream()),
+          "gather_images_u8")
+    return out
+
+
 def multi_copy(dst, segments):
     """dst[off:off+n] = src (zeros for src None) for every (src, off, n) in segments -- one launch per 64."""
     k = len(segments)

@@ -87,6 +87,46 @@ extern "C" int b200np_multi_copy(const float* const* src, const long long* dst_o
   return B200NP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Device-side task assembly (dataset/shapenet_distractor.py:233-234,256-259; utils/utils.py:26-30):
+// out[m, c, y, x] = float(255 - bank[rows[m], y, x, c]) / 255   -- uint8 image bank resident in HBM, channel-last,
+// gathered by row index into the fp32 NCHW batch the model consumes.  HBM-bound byte work: 1 B read, 4 B written
+// per element; a thread converts 4 consecutive pixels of one channel plane (uchar4 -> float4 when C == 1).
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_images_u8_kernel(const uint8_t* __restrict__ bank, const int32_t* __restrict__ rows,
+                                        float* __restrict__ out, long long M, int H, int W, int C) {
+  const long long plane = (long long)H * W, per = plane * C;
+  const long long quads = M * per / 4;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (; q < quads; q += st) {
+    const long long e = q * 4;                       // first output element of this quad
+    const long long m = e / per, r = e - m * per;
+    const int c = (int)(r / plane);
+    const long long pix = r - (long long)c * plane;  // plane % 4 == 0: the quad stays inside one channel plane
+    const uint8_t* src = bank + (long long)__ldg(rows + m) * per + pix * C + c;
+    float4 v;
+    if (C == 1) {
+      const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(src));
+      v = make_float4((float)(255 - u.x) / 255.0f, (float)(255 - u.y) / 255.0f, (float)(255 - u.z) / 255.0f,
+                      (float)(255 - u.w) / 255.0f);
+    } else {
+      v = make_float4((float)(255 - __ldg(src)) / 255.0f, (float)(255 - __ldg(src + C)) / 255.0f,
+                      (float)(255 - __ldg(src + 2 * C)) / 255.0f, (float)(255 - __ldg(src + 3 * C)) / 255.0f);
+    }
+    *reinterpret_cast<float4*>(out + e) = v;
+  }
+}
+extern "C" int b200np_gather_images_u8(const uint8_t* bank, const int32_t* rows, float* out, long long M, int H, int W,
+                                       int C, void* stream) {
+  if (M <= 0) return B200NP_OK;
+  if (!bank || !rows || !out || H <= 0 || W <= 0 || C <= 0) return B200NP_E_BADARG;
+  if (((long long)H * W) % 4 != 0 || !aligned16(out) || (reinterpret_cast<uintptr_t>(bank) & 3u)) return B200NP_E_UNSUPPORTED;
+  const long long quads = M * H * W * C / 4;
+  gather_images_u8_kernel<<<ew_grid(quads, 256), 256, 0, as_stream(stream)>>>(bank, rows, out, M, H, W, C);
+  return launch_status();
+}
+
 __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                float* __restrict__ dz, long long n, int act) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, st = (long long)gridDim.x * blockDim.x;
