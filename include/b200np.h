@@ -91,9 +91,11 @@ int b200np_pack_conv_weight(const float* w, float* wf, float* wd, int Cout, int 
  * x  [N,H,W,Cin], y [N,H/stride,W/stride,Cout]; optional skip source xs [N,OH*stride_s,OW*stride_s,Cs]
  * (pass xs = NULL to disable).  This one call is conv1 (+ReLU) or conv2 + downsample + add + ReLU
  * of a BasicBlock. */
+/* relu_bits (nullable; 64-channel tensor-core modes only): the gates (y > 0) of the output as 1 bit per element in
+ * the format b200np_conv_dgrad takes as `mask_bits`. */
 int b200np_conv_fwd(const float* x, const float* wf, const float* bias, float* y, int N, int H, int W,
                     int Cin, int Cout, int R, int stride, const float* xs, const float* wsf,
-                    const float* bias_s, int Cs, int stride_s, int act, int precision, void* stream);
+                    const float* bias_s, int Cs, int stride_s, int act, int precision, uint32_t* relu_bits, void* stream);
 
 /* dx = relu_mask(act_saved) * ( dgrad_RxR(dy; wd, stride) [+ dgrad_1x1(dys; wsd, stride_s)] )
  * dy [N,H/stride,W/stride,Cout] -> dx [N,H,W,Cin]; `mask_src` (same shape as dx, may be NULL) is

@@ -392,3 +392,19 @@ def test_baco_aggregation():
     dmu, ds = ops.baco_bwd(dr.float().cuda(), mu.detach().float().cuda(), s.detach().float().cuda(), r)
     assert rel(dmu, mu.grad) < 5e-6
     assert rel(ds, s.grad) < 5e-6
+
+
+@pytest.mark.parametrize("hw,n,stride,skip", [(64, 2, 1, True), (64, 2, 2, False), (8, 5, 1, True), (8, 5, 2, False)])
+def test_conv_fwd_relu_bits(hw, n, stride, skip):
+    """The tensor-core forward kernels (halo and gather paths) emit the gates of their ReLU output as packed bits."""
+    ops = _ops()
+    from b200np import lib
+    w = rnd(64, 64, 3, 3, seed=5, scale=0.05).float().cuda()
+    ws = rnd(64, 64, 1, 1, seed=6, scale=0.1).float().cuda()
+    b = rnd(64, seed=7, scale=0.1).float().cuda()
+    x = rnd(n, hw, hw, 64, seed=8).float().cuda()
+    xs = rnd(n, 2 * hw // stride, 2 * hw // stride, 64, seed=9).float().cuda()
+    sk = (xs, ops.pack_conv_weight(ws), b, 2) if skip else None
+    y, bits = ops.conv_fwd(x, ops.pack_conv_weight(w), b, stride, lib.ACT_RELU, lib.PREC_TF32X3, skip=sk, want_bits=True)
+    assert bits is not None and torch.equal(bits, _pack_bits(y))
+    assert 0.2 < float((y > 0).float().mean()) < 0.8

@@ -26,7 +26,8 @@ def report(name, fl):
 
 for name, fn in (("fwd conv1 s2", lambda: ops.conv_fwd(x, w2, b, 2, 1, prec)),
                  ("fwd conv2+skip", lambda: ops.conv_fwd(h, w2, b, 1, 1, prec, skip=(x, ws, b, 2))),
-                 ("dgrad s1", lambda: ops.conv_dgrad(h, w2, h.shape, 1, prec, mask_src=h))):
+                 ("dgrad s1", lambda: ops.conv_dgrad(h, w2, h.shape, 1, prec, mask_src=h)),
+                 ("dgrad s2 + skip (4 classes fused)", lambda: ops.conv_dgrad(h, w2, x.shape, 2, prec, mask_src=x, skip=(h, ws, 2)))):
     for fl in flag_list:  # diagnostic flags, see tapconv_halo.cu (1 weights, 2 planes, 4 epilogue, 8 cross MMAs, 16 MMAs)
         LIB.b200np_debug_set_halo_flags(fl)
         fn(); torch.cuda.synchronize()

@@ -60,16 +60,18 @@ class TrunkFn(Function):
             ops.conv_small_fwd(im, c1w, c1b, out=x0[off:off + n], relu=True, prec=prec,
                                relu_bits=None if bits0 is None else bits0[off:off + n])
             off += n
-        ctx.bits0 = bits0
-        x, acts, packs = x0, [], []
+        x, acts, packs, bits, bits_x = x0, [], [], [], bits0
         for l in range(4):
             w1, b1, w2, b2, wsk, bsk = params[2 + 6 * l: 8 + 6 * l]
             p1, p2, ps = ops.pack_conv_weight(w1), ops.pack_conv_weight(w2), ops.pack_conv_weight(wsk)
-            h = ops.conv_fwd(x, p1, b1, 2, ACT_RELU, prec)
-            y = ops.conv_fwd(h, p2, b2, 1, ACT_RELU, prec, skip=(x, ps, bsk, 2))
+            # the forward epilogues also emit the ReLU gates as 1 bit per element (None in fp32 mode): the data
+            # gradients read those instead of the activations
+            h, bits_h = ops.conv_fwd(x, p1, b1, 2, ACT_RELU, prec, want_bits=True)
+            y, bits_y = ops.conv_fwd(h, p2, b2, 1, ACT_RELU, prec, skip=(x, ps, bsk, 2), want_bits=True)
             acts.append((x, h, y))
+            bits.append((bits_x, bits_h))
             packs.append((p1, p2, ps))
-            x = y
+            x, bits_x = y, bits_y
         outs, idxs, off = [], [], 0
         for n in Ns:
             xs = x[off:off + n]
@@ -82,7 +84,7 @@ class TrunkFn(Function):
                 idxs.append(i)
             off += n
         ctx.img_agg, ctx.prec, ctx.Ns = img_agg, prec, Ns
-        ctx.imgs, ctx.acts, ctx.packs, ctx.idxs = imgs, acts, packs, idxs
+        ctx.imgs, ctx.acts, ctx.packs, ctx.idxs, ctx.bits = imgs, acts, packs, idxs, bits
         ctx.c1w_shape = tuple(c1w.shape)
         ctx.pool_idx = idxs  # exposed for parity tests (bit-exact argmax)
         return tuple(outs)
@@ -109,10 +111,10 @@ class TrunkFn(Function):
                 dws, _, _ = ops.conv_wgrad(x, dy, 1, 2, prec, want_db=False)
             else:  # the skip projection's weight gradient rides along as a 10th tap of conv2's
                 dw2, db2, dws = ops.conv_wgrad(h, dy, 3, 1, prec, skip=(x, 2))
-            dh = ops.conv_dgrad(dy, p2, h.shape, 1, prec, mask_src=h)
+            bits_x, bits_h = ctx.bits[l]
+            dh = ops.conv_dgrad(dy, p2, h.shape, 1, prec, mask_src=h, mask_bits=bits_h)
             dw1, db1, _ = ops.conv_wgrad(x, dh, 3, 2, prec)
-            dx = ops.conv_dgrad(dh, p1, x.shape, 2, prec, mask_src=x, skip=(dy, ps, 2),
-                                mask_bits=ctx.bits0 if l == 0 else None)
+            dx = ops.conv_dgrad(dh, p1, x.shape, 2, prec, mask_src=x, skip=(dy, ps, 2), mask_bits=bits_x)
             grads[2 + 6 * l: 8 + 6 * l] = [dw1, db1, dw2, db2, dws, db2.clone()]
             dy = dx
         off, dw_acc, db_acc = 0, None, None

@@ -35,7 +35,7 @@ SIGNATURES = {
     "b200np_conv_small_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "b200np_packed_weight_floats": (_sz, [_i, _i, _i]),
     "b200np_pack_conv_weight": (_i, [_p, _p, _p, _i, _i, _i, _p]),
-    "b200np_conv_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "b200np_conv_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "b200np_conv_dgrad": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
     "b200np_conv_wgrad_workspace": (_sz, [_i] * 7),
     "b200np_conv_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _sz, _p]),

@@ -88,8 +88,9 @@ def pack_conv_weight(w, want_fwd=True, want_dgrad=True):
     return PackedConvWeight(wf, wd, Cout, Cin, R)
 
 
-def conv_fwd(x, pw, bias, stride, act, prec, skip=None):
-    """x NHWC, pw PackedConvWeight; skip = (xs, pws, bias_s, stride_s) fuses a 1x1 projection of xs."""
+def conv_fwd(x, pw, bias, stride, act, prec, skip=None, want_bits=False):
+    """x NHWC, pw PackedConvWeight; skip = (xs, pws, bias_s, stride_s) fuses a 1x1 projection of xs.
+    want_bits: also return the packed gates (y > 0) [N,OH,OW,2] int32 (tensor-core modes, 64 channels) -> (y, bits)."""
     _chk(x, "x"), _chk(pw.f, "wf"), _chk(bias, "bias")
     N, H, W, Cin = x.shape
     assert Cin == pw.Cin
@@ -100,9 +101,12 @@ def conv_fwd(x, pw, bias, stride, act, prec, skip=None):
         xs, pws, bs, ss = skip
         _chk(xs, "xs"), _chk(pws.f, "wsf"), _chk(bs, "bias_s")
         wsf, Cs = pws.f, xs.shape[3]
+    bits = None
+    if want_bits and prec != lib.PREC_FP32_SIMT and Cin == 64 and pw.Cout == 64:
+        bits = torch.empty((N, H // stride, W // stride, 2), device=x.device, dtype=torch.int32)
     check(LIB.b200np_conv_fwd(_ptr(x), _ptr(pw.f), _ptr(bias), _ptr(y), N, H, W, Cin, pw.Cout, pw.R, stride,
-                              _ptr(xs), _ptr(wsf), _ptr(bs), Cs, ss, act, prec, _stream()), "conv_fwd")
-    return y
+                              _ptr(xs), _ptr(wsf), _ptr(bs), Cs, ss, act, prec, _ptr(bits), _stream()), "conv_fwd")
+    return (y, bits) if want_bits else y
 
 
 def conv_dgrad(dy, pw, x_shape, stride, prec, mask_src=None, skip=None, mask_bits=None):

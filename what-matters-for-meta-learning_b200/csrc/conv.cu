@@ -89,8 +89,10 @@ extern "C" size_t b200np_packed_weight_floats(int Cout, int Cin, int R) {
 
 extern "C" int b200np_conv_fwd(const float* x, const float* wf, const float* bias, float* y, int N, int H, int W,
                                int Cin, int Cout, int R, int stride, const float* xs, const float* wsf,
-                               const float* bias_s, int Cs, int stride_s, int act, int precision, void* stream) {
+                               const float* bias_s, int Cs, int stride_s, int act, int precision, uint32_t* relu_bits,
+                               void* stream) {
   if (!x || !wf || !y || N <= 0 || H <= 0 || W <= 0) return B200NP_E_BADARG;
+  if (relu_bits && !(use_umma(precision, Cin, Cout))) return B200NP_E_UNSUPPORTED;  // written by the tcgen05 epilogues only
   if ((R != 1 && R != 3) || (stride != 1 && stride != 2) || H % stride || W % stride) return B200NP_E_UNSUPPORTED;
   if (xs && (!wsf || Cs != Cin || stride_s < 1)) return B200NP_E_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(wf) || !aligned16(y) || (xs && (!aligned16(xs) || !aligned16(wsf))))
@@ -98,7 +100,7 @@ extern "C" int b200np_conv_fwd(const float* x, const float* wf, const float* bia
   TapConvArgs a{};
   a.src[0] = x; a.srcH[0] = H; a.srcW[0] = W; a.in_s[0] = stride; a.w[0] = wf;
   a.Cin = Cin; a.Cout = Cout; a.bias = bias; a.bias2 = xs ? bias_s : nullptr;
-  a.dst = y; a.mask = nullptr;
+  a.dst = y; a.mask = nullptr; a.mask_bits = nullptr; a.relu_bits = relu_bits;
   a.N = N; a.OH = H / stride; a.OW = W / stride;
   a.dstH = a.OH; a.dstW = a.OW; a.dst_s = 1; a.dst_oy = 0; a.dst_ox = 0;
   a.act = act;

@@ -39,6 +39,7 @@ struct TapConvArgs {
   const uint32_t* mask_bits;  // nullable, takes precedence over `mask`: the same gate as 1 bit per element,
                               // [dst pixel][Cout / 32] words, bit j of word h = channel 32 h + j (8 B instead of
                               // 256 B read per pixel); written by the forward kernels' ReLU epilogues
+  uint32_t* relu_bits; // nullable output (tcgen05 kernels, Cout == 64): the gates (dst > 0) in the mask_bits format
   int N, OH, OW;       // pixel grid of this launch
   int dstH, dstW, dst_s, dst_oy, dst_ox;  // dst pixel = (oy*dst_s + dst_oy, ox*dst_s + dst_ox)
   int ntaps;

@@ -407,7 +407,23 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
       const int r0 = rb * kTileRows;
       const int n = r0 / a.OH, oy = r0 - n * a.OH + (m >> 3), ox = xt * kTileCols + (m & 7);
-     for (int cls = 0; cls < ncls; ++cls) {              // class mode: the tile's outputs, one accumulator set each
+      // The packed ReLU gates of this thread's pixels (all classes) are fetched BEFORE the accumulators are waited
+      // for: with one epilogue warp per scheduler a load issued after the wait is pure exposed latency, and that
+      // latency (8 dependent mask loads per tile) was what paced the fused stride-2 data gradient.
+      uint32_t mw[4][2] = {};
+      if (a.mask_bits) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          if (cc < ncls) {
+            const int d_oy = ncls > 1 ? h.cls_oy[cc] : a.dst_oy, d_ox = ncls > 1 ? h.cls_ox[cc] : a.dst_ox;
+            const long long px = ((long long)n * a.dstH + (long long)oy * a.dst_s + d_oy) * a.dstW + (long long)ox * a.dst_s + d_ox;
+            const uint2 w2 = __ldg(reinterpret_cast<const uint2*>(a.mask_bits + px * 2));
+            mw[cc][0] = w2.x; mw[cc][1] = w2.y;
+          }
+      }
+#pragma unroll
+     for (int cls = 0; cls < 4; ++cls) {                  // class mode: the tile's outputs, one accumulator set each
+      if (cls >= ncls) break;
       const int set = ncls > 1 ? cls : acc_set;
       const int d_oy = ncls > 1 ? h.cls_oy[cls] : a.dst_oy, d_ox = ncls > 1 ? h.cls_ox[cls] : a.dst_ox;
       const long long off =
@@ -443,7 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           tc_fence_before();
           mbar_arrive(acc_empty + set);
         }
-        const uint32_t mword = a.mask_bits ? __ldg(a.mask_bits + (off >> 6) * 2 + hf) : 0u;   // 32 ReLU gates
+        const uint32_t mword = mw[cls][hf];                // 32 ReLU gates
+        uint32_t gates = 0u;                               // (output > 0) of this thread's 32 channels
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq) {
           const int c = hf * 32 + 4 * qq;
@@ -469,7 +486,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
           }
           if (!(dflags & 4) || o.x == 12345.678f) *reinterpret_cast<float4*>(a.dst + off + c) = o;
+          gates |= (uint32_t)((o.x > 0.f) | ((o.y > 0.f) << 1) | ((o.z > 0.f) << 2) | ((o.w > 0.f) << 3)) << (4 * qq);
         }
+        if (a.relu_bits) a.relu_bits[(off >> 6) * 2 + hf] = gates;
       }
      }
       if (ncls > 1) acc_phase ^= 1;                      // every class set is used once per tile

@@ -224,6 +224,19 @@ __global__ void __launch_bounds__(kConvThreads, 2) tapconv_umma_kernel(const Tap
       }
       *reinterpret_cast<float4*>(a.dst + off + c) = o;
     }
+    if (a.relu_bits) {  // gates of the outputs just written: the 8 lanes of a pixel's 32-channel half OR their nibbles
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        const long long off = off_s[q4 * 32 + rr];
+        const float4 o = off >= 0 ? *reinterpret_cast<const float4*>(a.dst + off + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t wb = (uint32_t)((o.x > 0.f) | ((o.y > 0.f) << 1) | ((o.z > 0.f) << 2) | ((o.w > 0.f) << 3)) << (4 * cj);
+        wb |= __shfl_xor_sync(0xffffffffu, wb, 1);
+        wb |= __shfl_xor_sync(0xffffffffu, wb, 2);
+        wb |= __shfl_xor_sync(0xffffffffu, wb, 4);
+        if (cj == 0 && off >= 0) a.relu_bits[(off >> 6) * 2 + half] = wb;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
