@@ -184,13 +184,17 @@ __global__ void __launch_bounds__(128, 4)
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
       }
       uint8_t* piece = (half ? a_lo : a_hi) + warp * 4096 + lane * 128;
+      uint32_t gates = 0u;   // (y > 0) of this thread's pixel, channels 32 half .. 32 half + 31
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias_s + half * 32 + 4 * j);
         float4 o = make_float4(acc[4 * j] + b4.x, acc[4 * j + 1] + b4.y, acc[4 * j + 2] + b4.z, acc[4 * j + 3] + b4.w);
         if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
         *reinterpret_cast<float4*>(piece + ((j ^ (lane & 7)) << 4)) = o;
+        gates |= (uint32_t)((o.x > 0.f) | ((o.y > 0.f) << 1) | ((o.z > 0.f) << 2) | ((o.w > 0.f) << 3)) << (4 * j);
       }
+      // 1-bit ReLU gates for the data gradient that ends in this tensor: [pixel][2] words (thread = pixel here)
+      if (relu_bits && tile * 128 + tid < M) relu_bits[(tile * 128 + tid) * 2 + half] = gates;
     }
     __syncwarp();
     {
@@ -202,13 +206,6 @@ __global__ void __launch_bounds__(128, 4)
         const int rr = it * 2 + (lane >> 4);
         const float4 o = *reinterpret_cast<const float4*>(piece + rr * 128 + ((j ^ (rr & 7)) << 4));
         if (p_base + rr < M) *reinterpret_cast<float4*>(y + (p_base + rr) * 64 + c * 4) = o;
-        if (relu_bits) {  // 1-bit ReLU gates for the data gradient that ends in this tensor: [pixel][2] words
-          uint32_t wbits = ((o.x > 0.f) | ((o.y > 0.f) << 1) | ((o.z > 0.f) << 2) | ((o.w > 0.f) << 3)) << (4 * j);
-          wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
-          wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
-          wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);   // the 8 lanes of one 32-channel half
-          if (j == 0 && p_base + rr < M) relu_bits[(p_base + rr) * 2 + h] = wbits;
-        }
       }
     }
     __syncwarp();
