@@ -48,6 +48,14 @@ if what in ("all", "fwd"):
 if what in ("all", "dgrad"):
     timed("dgrad 3x3 s1 (mask)", lambda: ops.conv_dgrad(dz, wd2, h.shape, 1, prec, mask_src=h), 2.0 * M1 * 64 * 576)
     timed("dgrad 3x3 s2 + skip (mask)", lambda: ops.conv_dgrad(dz, wd1, x.shape, 2, prec, mask_src=x, skip=(dz, wds, 2)), 2.0 * M1 * 64 * 640)
+if what in ("all", "dgrad") and prec != 0:
+    def pack_bits(act):
+        g_ = (act > 0).to(torch.int64).reshape(*act.shape[:-1], 2, 32)
+        w_ = (g_ << torch.arange(32, device=act.device, dtype=torch.int64)).sum(-1)
+        return torch.where(w_ >= 2 ** 31, w_ - 2 ** 32, w_).to(torch.int32).contiguous()
+    bh, bx = pack_bits(h), pack_bits(x)
+    timed("dgrad 3x3 s1 (packed gates)", lambda: ops.conv_dgrad(dz, wd2, h.shape, 1, prec, mask_bits=bh), 2.0 * M1 * 64 * 576)
+    timed("dgrad 3x3 s2 + skip (gates)", lambda: ops.conv_dgrad(dz, wd1, x.shape, 2, prec, mask_bits=bx, skip=(dz, wds, 2)), 2.0 * M1 * 64 * 640)
 if what in ("all", "wgrad"):
     timed("wgrad 3x3 s1", lambda: ops.conv_wgrad(h, dz, 3, 1, prec), 2.0 * M1 * 64 * 576)
     timed("wgrad 3x3 s2", lambda: ops.conv_wgrad(x, dz, 3, 2, prec), 2.0 * M1 * 64 * 576)

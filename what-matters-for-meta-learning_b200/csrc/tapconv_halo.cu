@@ -421,9 +421,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             mw[cc][0] = w2.x; mw[cc][1] = w2.y;
           }
       }
-#pragma unroll
-     for (int cls = 0; cls < 4; ++cls) {                  // class mode: the tile's outputs, one accumulator set each
-      if (cls >= ncls) break;
+     for (int cls = 0; cls < ncls; ++cls) {               // class mode: the tile's outputs, one accumulator set each
+      // (not unrolled: four copies of the epilogue body thrash the instruction cache; the prefetched gate words
+      // are picked with selects instead of register indexing)
+      const uint32_t mw0 = cls == 0 ? mw[0][0] : cls == 1 ? mw[1][0] : cls == 2 ? mw[2][0] : mw[3][0];
+      const uint32_t mw1 = cls == 0 ? mw[0][1] : cls == 1 ? mw[1][1] : cls == 2 ? mw[2][1] : mw[3][1];
       const int set = ncls > 1 ? cls : acc_set;
       const int d_oy = ncls > 1 ? h.cls_oy[cls] : a.dst_oy, d_ox = ncls > 1 ? h.cls_ox[cls] : a.dst_ox;
       const long long off =
@@ -459,8 +461,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
           tc_fence_before();
           mbar_arrive(acc_empty + set);
         }
-        const uint32_t mword = mw[cls][hf];                // 32 ReLU gates
+        const uint32_t mword = hf ? mw1 : mw0;             // 32 ReLU gates
         uint32_t gates = 0u;                               // (output > 0) of this thread's 32 channels
+        // float-mask variant: all eight loads are issued before the first use (one exposed latency, not eight)
+        const bool fmask = !a.mask_bits && a.mask && !(dflags & 4);
+        float4 mk8[8];
+        if (fmask) {
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) mk8[qq] = ldg4(a.mask + off + hf * 32 + 4 * qq);
+        }
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq) {
           const int c = hf * 32 + 4 * qq;
@@ -477,8 +486,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
             const uint32_t nb4 = mword >> (4 * qq);
             o.x = (nb4 & 1u) ? o.x : 0.f; o.y = (nb4 & 2u) ? o.y : 0.f;
             o.z = (nb4 & 4u) ? o.z : 0.f; o.w = (nb4 & 8u) ? o.w : 0.f;
-          } else if (a.mask && !(dflags & 4)) {
-            const float4 mk = ldg4(a.mask + off + c);
+          } else if (fmask) {
+            const float4 mk = mk8[qq];
             o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
             o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
           }
