@@ -95,24 +95,37 @@ __global__ void __launch_bounds__(256) favor_attn_fwd_kernel(
   __syncthreads();
   for (int f0 = 0; f0 < M; f0 += FC) {
     const int fc = M - f0 < FC ? M - f0 : FC;
-    for (int idx = tid; idx < (nt + nc) * FC; idx += 256) {
-      const int row = idx / FC, f = idx - row * FC;
-      float val = 0.f;
-      if (f < fc) {
-        if (row < nt) {
-          const long long r = ((long long)t * nt + row) * H + h;
-          const float u = U[r * ldu + f0 + f];
-          val = rho * (expf(u - s1[row] - s2[row]) + kEps);
-        } else {
-          const int j = row - nt;
-          const long long r = ((long long)t * nc + j) * H + h;
-          const float w = W[r * ldu + f0 + f];
-          val = rho * (expf(w - s3[j] - gmax) + kEps);
-          tie_local += (w == gmax);
+    // the chunk's U / W values are fetched eight at a time before the exponentials: one exposed load latency per
+    // batch instead of one per element (this loop was the kernel's critical path)
+    for (int base = tid; base < (nt + nc) * FC; base += 256 * 8) {
+      float raw[8];
+#pragma unroll
+      for (int u8 = 0; u8 < 8; ++u8) {
+        const int idx = base + u8 * 256;
+        const int row = idx / FC, f = idx - row * FC;
+        raw[u8] = 0.f;
+        if (idx < (nt + nc) * FC && f < fc) {
+          const long long r = row < nt ? ((long long)t * nt + row) * H + h : ((long long)t * nc + (row - nt)) * H + h;
+          raw[u8] = (row < nt ? U : W)[r * ldu + f0 + f];
         }
       }
-      if (row < nt) Qs[row * PITCH + f] = val;
-      else Ks[(row - nt) * PITCH + f] = val;
+#pragma unroll
+      for (int u8 = 0; u8 < 8; ++u8) {
+        const int idx = base + u8 * 256;
+        if (idx >= (nt + nc) * FC) break;
+        const int row = idx / FC, f = idx - row * FC;
+        float val = 0.f;
+        if (f < fc) {
+          if (row < nt) {
+            val = rho * (expf(raw[u8] - s1[row] - s2[row]) + kEps);
+          } else {
+            val = rho * (expf(raw[u8] - s3[row - nt] - gmax) + kEps);
+            tie_local += (raw[u8] == gmax);
+          }
+        }
+        if (row < nt) Qs[row * PITCH + f] = val;
+        else Ks[(row - nt) * PITCH + f] = val;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -236,21 +249,28 @@ __global__ void __launch_bounds__(256) favor_attn_bwd_kernel(
   for (int f0 = 0; f0 < M; f0 += FC) {
     const int fc = M - f0 < FC ? M - f0 : FC;
     __syncthreads();
-    for (int idx = tid; idx < (nt + nc) * FC; idx += 256) {
-      const int row = idx / FC, ff = idx - row * FC;
-      float val = 0.f;
-      if (ff < fc) {
-        if (row < nt) {
-          const long long r = ((long long)t * nt + row) * H + h;
-          val = rho * expf(U[r * ldu + f0 + ff] - s1[row] - s2[row]);
-        } else {
-          const int j = row - nt;
-          const long long r = ((long long)t * nc + j) * H + h;
-          val = rho * expf(W[r * ldu + f0 + ff] - s3[j] - gmax);
+    for (int base = tid; base < (nt + nc) * FC; base += 256 * 8) {   // loads batched as in the forward kernel
+      float raw[8];
+#pragma unroll
+      for (int u8 = 0; u8 < 8; ++u8) {
+        const int idx = base + u8 * 256;
+        const int row = idx / FC, ff = idx - row * FC;
+        raw[u8] = 0.f;
+        if (idx < (nt + nc) * FC && ff < fc) {
+          const long long r = row < nt ? ((long long)t * nt + row) * H + h : ((long long)t * nc + (row - nt)) * H + h;
+          raw[u8] = (row < nt ? U : W)[r * ldu + f0 + ff];
         }
       }
-      if (row < nt) Eq[row * PITCH + ff] = val;
-      else Ek[(row - nt) * PITCH + ff] = val;
+#pragma unroll
+      for (int u8 = 0; u8 < 8; ++u8) {
+        const int idx = base + u8 * 256;
+        if (idx >= (nt + nc) * FC) break;
+        const int row = idx / FC, ff = idx - row * FC;
+        float val = 0.f;
+        if (ff < fc) val = row < nt ? rho * expf(raw[u8] - s1[row] - s2[row]) : rho * expf(raw[u8] - s3[row - nt] - gmax);
+        if (row < nt) Eq[row * PITCH + ff] = val;
+        else Ek[(row - nt) * PITCH + ff] = val;
+      }
     }
     __syncthreads();
     for (int i = half; i < nt; i += 2) {
