@@ -125,7 +125,8 @@ def test_integer_results_bit_exact(case, golden):
 
     def spy_pool(x, out=None, idx=None):
         o, i = orig_pool(x, out, idx)
-        captured.setdefault("pool_idx", i)
+        if x.shape[0] == T * nc:        # the context encoder's pooling (the decoder CNN pools the T*nt target images)
+            captured.setdefault("pool_idx", i)
         return o, i
     ops.amp2_flatten_fwd = spy_pool
     try:

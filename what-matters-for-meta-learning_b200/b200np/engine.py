@@ -34,6 +34,23 @@ def _p(t, off=0):
     return t.data_ptr() + 4 * off
 
 
+# The decoder's CNN (networks/models.py:160-180) depends on the target images only, so it runs on a second stream
+# beside the encoder CNN / attention / MLP chain of the main stream and joins where `fc_mu` consumes it.  Autograd runs
+# each backward node on its forward stream, so the two trunks' backward passes overlap the same way; inside a captured
+# step the fork/join becomes two branches of the CUDA graph.  The big persistent conv kernels still take turns on the
+# SMs -- what overlaps are the latency-bound kernels of one branch (small maps, partial reductions, dense layers,
+# FAVOR+) with the other branch, and every kernel's tail.  B200NP_OVERLAP=0 keeps everything on one stream.
+OVERLAP = os.environ.get("B200NP_OVERLAP", "1") != "0"
+_SIDE = {}
+
+
+def _side_stream(device):
+    s = _SIDE.get(device)
+    if s is None:
+        s = _SIDE[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 # ================================================================================================
 # CNN trunk: stem 5x5 s2 + 4 residual stages + pooling, several image sources in one pass
 # ================================================================================================
@@ -427,6 +444,14 @@ def _forward_resnet_family(m, ctx_x, ctx_y, tgt_x):
     T, nc, nt = m.task_num, ctx_x.shape[1], tgt_x.shape[1]
     C, H, W = m.img_channels, m.img_size[0], m.img_size[1]
     tgt_imgs = tgt_x.reshape(T * nt, C, H, W).contiguous()
+    dec_params = _trunk_params(m.decoder)
+    side = None
+    if OVERLAP and nc:
+        main = torch.cuda.current_stream()
+        side = _side_stream(tgt_imgs.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            (x_dec,) = TrunkFn.apply(m.img_agg, PRECISION, 1, tgt_imgs, *dec_params)
     if nc:
         ctx_imgs = ctx_x.reshape(T * nc, C, H, W).contiguous()
         lab = ctx_y.reshape(T * nc, -1).contiguous()
@@ -455,7 +480,10 @@ def _forward_resnet_family(m, ctx_x, ctx_y, tgt_x):
             sample = RepeatFn.apply(nt, _lin(ACT_NONE, r, None, m.mu))
     else:
         sample = ops.zeros((T * nt, 256), tgt_imgs)
-    (x_dec,) = TrunkFn.apply(m.img_agg, PRECISION, 1, tgt_imgs, *_trunk_params(m.decoder))
+    if side is not None:
+        main.wait_stream(side)
+    else:
+        (x_dec,) = TrunkFn.apply(m.img_agg, PRECISION, 1, tgt_imgs, *dec_params)
     fc = m.decoder.fc_mu
     h = _lin(ACT_RELU, x_dec, sample, fc[0])
     h = _lin(ACT_RELU, h, None, fc[2])
