@@ -40,14 +40,19 @@ def _p(t, off=0):
 # step the fork/join becomes two branches of the CUDA graph.  The big persistent conv kernels still take turns on the
 # SMs -- what overlaps are the latency-bound kernels of one branch (small maps, partial reductions, dense layers,
 # FAVOR+) with the other branch, and every kernel's tail.  B200NP_OVERLAP=0 keeps everything on one stream.
-OVERLAP = os.environ.get("B200NP_OVERLAP", "1") != "0"
+#
+# Level 2 (default): inside a trunk's backward pass the weight gradients are off the critical path (only the
+# data-gradient chain feeds the next layer), so they are issued on a companion stream of the stream the backward node
+# runs on and join before the node returns.
+OVERLAP = int(os.environ.get("B200NP_OVERLAP", "2"))
 _SIDE = {}
 
 
-def _side_stream(device):
-    s = _SIDE.get(device)
+def _side_stream(key):
+    """One lazily created companion stream per key (a device, or the handle of the stream it accompanies)."""
+    s = _SIDE.get(key)
     if s is None:
-        s = _SIDE[device] = torch.cuda.Stream(device=device)
+        s = _SIDE[key] = torch.cuda.Stream()
     return s
 
 
@@ -120,29 +125,47 @@ class TrunkFn(Function):
                 ops.amp2_flatten_bwd(do, idx, y_last[off:off + n], dy[off:off + n])
             off += n
         grads = [None] * 26
+        cur = torch.cuda.current_stream()
+        wst = _side_stream(("wgrad", cur.cuda_stream)) if OVERLAP >= 2 else None
+        if wst is None:
+            wst = cur
+            fork = join = lambda: None
+        else:
+            fork, join = (lambda: wst.wait_stream(cur)), (lambda: cur.wait_stream(wst))
+        keep = []   # tensors the companion stream reads stay referenced until it has joined (allocator reuse is per stream)
         for l in (3, 2, 1, 0):
             x, h, _ = ctx.acts[l]
             p1, p2, ps = ctx.packs[l]
-            if prec == PREC_FP32_SIMT:
-                dw2, db2, _ = ops.conv_wgrad(h, dy, 3, 1, prec)
-                dws, _, _ = ops.conv_wgrad(x, dy, 1, 2, prec, want_db=False)
-            else:  # the skip projection's weight gradient rides along as a 10th tap of conv2's
-                dw2, db2, dws = ops.conv_wgrad(h, dy, 3, 1, prec, skip=(x, 2))
             bits_x, bits_h = ctx.bits[l]
+            fork()
+            with torch.cuda.stream(wst):
+                if prec == PREC_FP32_SIMT:
+                    dw2, db2, _ = ops.conv_wgrad(h, dy, 3, 1, prec)
+                    dws, _, _ = ops.conv_wgrad(x, dy, 1, 2, prec, want_db=False)
+                else:  # the skip projection's weight gradient rides along as a 10th tap of conv2's
+                    dw2, db2, dws = ops.conv_wgrad(h, dy, 3, 1, prec, skip=(x, 2))
+                dbs = db2.clone()
             dh = ops.conv_dgrad(dy, p2, h.shape, 1, prec, mask_src=h, mask_bits=bits_h)
-            dw1, db1, _ = ops.conv_wgrad(x, dh, 3, 2, prec)
+            fork()
+            with torch.cuda.stream(wst):
+                dw1, db1, _ = ops.conv_wgrad(x, dh, 3, 2, prec)
             dx = ops.conv_dgrad(dh, p1, x.shape, 2, prec, mask_src=x, skip=(dy, ps, 2), mask_bits=bits_x)
-            grads[2 + 6 * l: 8 + 6 * l] = [dw1, db1, dw2, db2, dws, db2.clone()]
+            grads[2 + 6 * l: 8 + 6 * l] = [dw1, db1, dw2, db2, dws, dbs]
+            keep += [dy, dh]
             dy = dx
+        fork()
         off, dw_acc, db_acc = 0, None, None
-        for im, n in zip(ctx.imgs, Ns):
-            dw, db = ops.conv_small_wgrad(im, dy[off:off + n], ctx.c1w_shape, prec)
-            if dw_acc is None:
-                dw_acc, db_acc = dw, db
-            else:
-                ops.axpy(dw_acc, dw)
-                ops.axpy(db_acc, db)
-            off += n
+        with torch.cuda.stream(wst):
+            for im, n in zip(ctx.imgs, Ns):
+                dw, db = ops.conv_small_wgrad(im, dy[off:off + n], ctx.c1w_shape, prec)
+                if dw_acc is None:
+                    dw_acc, db_acc = dw, db
+                else:
+                    ops.axpy(dw_acc, dw)
+                    ops.axpy(db_acc, db)
+                off += n
+        join()
+        del keep
         grads[0], grads[1] = dw_acc, db_acc
         return (None, None, None) + (None,) * len(Ns) + tuple(grads)
 
@@ -446,9 +469,9 @@ def _forward_resnet_family(m, ctx_x, ctx_y, tgt_x):
     tgt_imgs = tgt_x.reshape(T * nt, C, H, W).contiguous()
     dec_params = _trunk_params(m.decoder)
     side = None
-    if OVERLAP and nc:
+    if OVERLAP >= 1 and nc:
         main = torch.cuda.current_stream()
-        side = _side_stream(tgt_imgs.device)
+        side = _side_stream(("decoder", main.cuda_stream))
         side.wait_stream(main)
         with torch.cuda.stream(side):
             (x_dec,) = TrunkFn.apply(m.img_agg, PRECISION, 1, tgt_imgs, *dec_params)
