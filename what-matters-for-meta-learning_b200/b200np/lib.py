@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libb200np.so")
+LIB_PATH = os.environ.get("B200NP_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libb200np.so")
 
 PREC_FP32_SIMT, PREC_TF32X3, PREC_TF32 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2

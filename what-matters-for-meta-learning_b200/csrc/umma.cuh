@@ -100,7 +100,14 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
 __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
-// X3: hi = rn_tf32(x), lo = rn_tf32(x - hi) (x - hi is exact in fp32); single pass: rn_tf32(x).
+// X3: hi = rn_tf32(x), lo = x - hi (exact in fp32; the tensor core truncates it to tf32); single pass: rn_tf32(x).
+// Rounding lo as well (B200NP_LO_RN=1) halves the residual of the split -- 2^-23 |x| instead of 2^-22 |x| on average,
+// random in sign either way because sign(lo) is -- at 2 more integer instructions per element in loops that are
+// instruction-issue bound; both are below the fp32 rounding of the products' sum.
+#ifndef B200NP_LO_RN
+#define B200NP_LO_RN 0
+#endif
+__device__ __forceinline__ float lo_part(float x, float hi) { return B200NP_LO_RN ? to_tf32(x - hi) : x - hi; }
 // The stores are explicit st.shared with 32-bit addresses: through the 1024-byte alignment arithmetic on the
 // dynamic shared-memory base the compiler loses the address space and emits generic 64-bit ST.E (and splits some
 // of them into scalar stores).
@@ -113,7 +120,7 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
   sts128(smem_u32(hi_base) + off, h);
   if (x3) {
     float4 l;
-    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+    l.x = lo_part(v.x, h.x); l.y = lo_part(v.y, h.y); l.z = lo_part(v.z, h.z); l.w = lo_part(v.w, h.w);
     sts128(smem_u32(lo_base) + off, l);
   }
 }
