@@ -193,6 +193,40 @@ def test_fused_adam_training_steps_match_oracle():
     assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
 
 
+@pytest.mark.parametrize("case", ["anp_distractor", "cnp_distractor_max"])
+def test_stream_overlap_is_bit_identical(case):
+    """Running the decoder CNN and the weight gradients on companion streams (engine.OVERLAP) reorders nothing inside
+    a kernel: mu, loss and every gradient are bit-identical to the single-stream schedule."""
+    from b200np import engine
+    from trainer.losses import LossFunc
+    engine.set_precision("tf32x3")
+    method, task, agg, img_agg, extra, T, nc, nt = CASES[case]
+    cx, cy, tx, ty = (torch.from_numpy(a).cuda() for a in synth.task_batch(task, T, nc, nt, seed=23))
+    results = []
+    saved = engine.OVERLAP
+    try:
+        for level in (0, 1, 2):
+            engine.OVERLAP = level
+            model, cfg = build_product_model(case, device="cuda")
+            model = model.to("cuda")
+            for rep in range(2):   # second pass: the caching allocator now re-uses blocks across the streams
+                model.zero_grad(set_to_none=True)
+                mu, _, _ = model(cx, cy, tx)
+                loss = LossFunc("mse", task).calc_loss(mu, None, ty)
+                loss.backward()
+            torch.cuda.synchronize()
+            results.append((mu.detach().clone(), loss.detach().clone(),
+                            {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    finally:
+        engine.OVERLAP = saved
+    mu0, loss0, g0 = results[0]
+    for mu, loss, g in results[1:]:
+        assert torch.equal(mu, mu0) and torch.equal(loss, loss0)
+        assert g.keys() == g0.keys()
+        for k in g0:
+            assert torch.equal(g[k], g0[k]), k
+
+
 def test_cuda_graph_step_equals_eager():
     """The captured-graph step replays exactly the eager step (same kernels, same order)."""
     from b200np import engine

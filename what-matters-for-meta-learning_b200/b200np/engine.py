@@ -48,11 +48,19 @@ OVERLAP = int(os.environ.get("B200NP_OVERLAP", "2"))
 _SIDE = {}
 
 
-def _side_stream(key):
-    """One lazily created companion stream per key (a device, or the handle of the stream it accompanies)."""
+# Stream priorities (CUDA clamps them to the device's range; captured kernel nodes inherit them): the stream that
+# carries the encoder CNN -> attention -> loss chain should win SMs over the decoder branch, and a trunk's data-gradient
+# chain over its weight gradients, so the companions only fill what the critical chain leaves idle.  The caller's own
+# stream has the default (lowest) priority in eager mode; `optim.GraphedStep` captures on a stream of MAIN_PRIORITY.
+MAIN_PRIORITY, DECODER_PRIORITY, WGRAD_PRIORITY = -2, -1, 0
+USE_PRIORITIES = os.environ.get("B200NP_PRIO", "1") != "0"
+
+
+def _side_stream(key, priority=0):
+    """One lazily created companion stream per key (the role and the handle of the stream it accompanies)."""
     s = _SIDE.get(key)
     if s is None:
-        s = _SIDE[key] = torch.cuda.Stream()
+        s = _SIDE[key] = torch.cuda.Stream(priority=priority if USE_PRIORITIES else 0)
     return s
 
 
@@ -126,7 +134,7 @@ class TrunkFn(Function):
             off += n
         grads = [None] * 26
         cur = torch.cuda.current_stream()
-        wst = _side_stream(("wgrad", cur.cuda_stream)) if OVERLAP >= 2 else None
+        wst = _side_stream(("wgrad", cur.cuda_stream), WGRAD_PRIORITY) if OVERLAP >= 2 else None
         if wst is None:
             wst = cur
             fork = join = lambda: None
@@ -471,7 +479,7 @@ def _forward_resnet_family(m, ctx_x, ctx_y, tgt_x):
     side = None
     if OVERLAP >= 1 and nc:
         main = torch.cuda.current_stream()
-        side = _side_stream(("decoder", main.cuda_stream))
+        side = _side_stream(("decoder", main.cuda_stream), DECODER_PRIORITY)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             (x_dec,) = TrunkFn.apply(m.img_agg, PRECISION, 1, tgt_imgs, *dec_params)

@@ -114,7 +114,10 @@ class GraphedStep:
         self._staged = None
         for s, t in zip(self.static, example_batch):
             s.copy_(t)
-        side = torch.cuda.Stream()
+        from . import engine
+        # warm-up and capture run on one high-priority stream: the engine's companion streams (decoder CNN, weight
+        # gradients) rank below it, and the captured kernel nodes keep those priorities
+        side = torch.cuda.Stream(priority=engine.MAIN_PRIORITY if engine.USE_PRIORITIES else 0)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -122,7 +125,7 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.loss = self._eager()
 
     def _eager(self):
