@@ -54,6 +54,7 @@ _SIDE = {}
 # stream has the default (lowest) priority in eager mode; `optim.GraphedStep` captures on a stream of MAIN_PRIORITY.
 MAIN_PRIORITY, DECODER_PRIORITY, WGRAD_PRIORITY = -2, -1, 0
 USE_PRIORITIES = os.environ.get("B200NP_PRIO", "1") != "0"
+FORK = os.environ.get("B200NP_FORK", "early")   # where the decoder branch forks: early | late (see the forward)
 
 
 def _side_stream(key, priority=0):
@@ -476,13 +477,23 @@ def _forward_resnet_family(m, ctx_x, ctx_y, tgt_x):
     C, H, W = m.img_channels, m.img_size[0], m.img_size[1]
     tgt_imgs = tgt_x.reshape(T * nt, C, H, W).contiguous()
     dec_params = _trunk_params(m.decoder)
-    side = None
-    if OVERLAP >= 1 and nc:
+    side = x_dec = None
+
+    def fork_decoder():
+        nonlocal side, x_dec, main
         main = torch.cuda.current_stream()
         side = _side_stream(("decoder", main.cuda_stream), DECODER_PRIORITY)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             (x_dec,) = TrunkFn.apply(m.img_agg, PRECISION, 1, tgt_imgs, *dec_params)
+    main = None
+    # Where the decoder branch forks: before the encoder CNN (default), or after it is enqueued ("late": the decoder
+    # CNN's big kernels then run beside the latency-bound dense / FAVOR+ chain instead of beside the encoder CNN).
+    # Measured on ANPDistractor: late 8.155 ms/step, early 8.12 -- the attention section runs alone less (FAVOR+ forward
+    # 0.12 -> 0.07 ms solo, tools/timeline_gaps.py) but the two CNNs' small-map layers lose their overlap.
+    late_fork = OVERLAP >= 1 and nc and FORK == "late"
+    if OVERLAP >= 1 and nc and not late_fork:
+        fork_decoder()
     if nc:
         ctx_imgs = ctx_x.reshape(T * nc, C, H, W).contiguous()
         lab = ctx_y.reshape(T * nc, -1).contiguous()
@@ -491,10 +502,14 @@ def _forward_resnet_family(m, ctx_x, ctx_y, tgt_x):
         enc = _trunk_params(m.img_encoder)
         if m.attention:
             x_ctx, x_tgt = TrunkFn.apply(m.img_agg, PRECISION, 2, ctx_imgs, tgt_imgs, *enc)
+            if late_fork:
+                fork_decoder()
         else:
             if m.agg_mode not in ("mean", "max", "baco"):
                 raise TypeError("agg_mode is not applicable for CNP, choose from ['mean', 'max', 'baco']")
             (x_ctx,) = TrunkFn.apply(m.img_agg, PRECISION, 1, ctx_imgs, *enc)
+            if late_fork:
+                fork_decoder()
         cf = _lin(ACT_RELU, x_ctx, lab, m.task_encoder[0])
         cf = _lin(ACT_RELU, cf, None, m.task_encoder[2])
         cf = _lin(ACT_RELU, cf, None, m.task_encoder[4])
