@@ -146,6 +146,8 @@ def run_b200_arm(args, rank, world, local_rank):
     from oracle import synth  # input generator only (integer hash); no oracle compute here
     from trainer.losses import LossFunc
 
+    if "B200NP_WGRAD_WAVES" in os.environ:   # diagnostic entry point: pixel chunks per weight-gradient launch
+        LIB.b200np_debug_set_wgrad_waves(int(os.environ["B200NP_WGRAD_WAVES"]))
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     if world > 1:

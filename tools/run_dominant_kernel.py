@@ -10,6 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "what-matters-for-meta-learning_b200")]
 from b200np import ops  # noqa: E402
 
+if "B200NP_WGRAD_WAVES" in os.environ:   # diagnostic entry point: pixel chunks per weight-gradient launch
+    ops.LIB.b200np_debug_set_wgrad_waves(int(os.environ["B200NP_WGRAD_WAVES"]))
+
 prec = {"fp32": 0, "tf32x3": 1, "tf32": 2}[sys.argv[1] if len(sys.argv) > 1 else "tf32x3"]
 what = sys.argv[2] if len(sys.argv) > 2 else "all"
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 1140

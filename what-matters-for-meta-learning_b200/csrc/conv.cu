@@ -39,12 +39,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
 }
 
 // Pixel chunks per weight gradient.  The tcgen05 kernel runs one CTA per (tap pair, chunk), two CTAs
-// per SM: size the grid to four full waves (a ragged last wave costs a whole wave; shorter chunks also
-// halve the number of truncating fp32 accumulations per TMEM block).  The CUDA-core kernel runs one CTA
-// per (tap, chunk).
+// per SM: size the grid to full waves (a ragged last wave costs a whole wave).  Fewer, longer chunks mean fewer
+// partial tiles to write and reduce but more truncating fp32 accumulations per TMEM block: measured on the layer1
+// weight gradient of a 20-task step (1.17 M pixels), rel-L2 against the CUDA-core fp32 kernel / step time:
+// 4 waves 5.5e-6 / 8.12 ms, 2 waves 1.1e-5 / 8.01 ms, 1 wave 2.3e-5 / 7.98 ms.  Two waves.  The CUDA-core kernel
+// runs one CTA per (tap, chunk).
+static int g_wgrad_waves = 2;   // full waves of (two CTAs per SM) per weight-gradient launch
 int wgrad_chunks(long long M, int ntaps) {
   const int pairs = (ntaps + 1) / 2;
-  long long want = (8LL * kNumSMs) / pairs;
+  long long want = (2LL * g_wgrad_waves * kNumSMs) / pairs;
   long long maxc = ceil_div(M, 64);
   if (want > maxc) want = maxc;
   return (int)(want < 1 ? 1 : want);
@@ -258,3 +261,6 @@ extern "C" int b200np_conv_wgrad(const float* x, const float* dy, float* dw, flo
   }
   return B200NP_OK;
 }
+
+// diagnostics (tools/run_dominant_kernel.py, bench.py): pixel chunks per weight-gradient launch, in full waves
+extern "C" void b200np_debug_set_wgrad_waves(int w) { g_wgrad_waves = w < 1 ? 1 : w; }
