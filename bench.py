@@ -277,7 +277,7 @@ def run_b200_arm(args, rank, world, local_rank):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at exactly the size
 # timed below, from `ncu --set full` of `bench.py --roofline-only` (profiles/ncu_tapwgrad_r1.txt,
 # profiles/ncu_tapconv_halo_r1.txt).
-NCU_TRAFFIC_BYTES = {"tapwgrad": 941.2e6, "tapconv_halo": 863.2e6}
+NCU_TRAFFIC_BYTES = {"tapwgrad": 921.6e6, "tapconv_halo": 862.4e6}
 
 
 def _time_kernel(run, reps=10):
