@@ -161,6 +161,36 @@ __global__ void __launch_bounds__(128) gemm_kernel(const GemmArgs g) {
   }
 }
 
+// Few outputs, long reduction (the 256 -> 2 output layer and its weight gradient, the label embedding's weight gradient):
+// the tiled kernel would run a handful of CTAs through K/16 dependent iterations (~20 us).  One warp per output element,
+// lanes stride over k, shuffle reduction; same epilogue.  Deterministic (fixed lane assignment and reduction tree).
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmArgs g) {
+  const b200np_gemm_desc& d = g.d;
+  const int grp = blockIdx.y;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (o >= d.M * d.N) return;
+  const int m = o / d.N, n = o - m * d.N;
+  const float* __restrict__ a = d.A[grp] + (long long)m * d.a_rs;
+  const float* __restrict__ b = d.B[grp] + (long long)n * d.b_cs;
+  float s0 = 0.f, s1 = 0.f;
+  int k = lane;
+  for (; k + 32 < d.K; k += 64) {
+    s0 = fmaf(__ldg(a + (long long)k * d.a_cs), __ldg(b + (long long)k * d.b_rs), s0);
+    s1 = fmaf(__ldg(a + (long long)(k + 32) * d.a_cs), __ldg(b + (long long)(k + 32) * d.b_rs), s1);
+  }
+  if (k < d.K) s0 = fmaf(__ldg(a + (long long)k * d.a_cs), __ldg(b + (long long)k * d.b_rs), s0);
+  const float acc = warp_sum(s0 + s1);
+  if (lane) return;
+  float v = d.alpha * acc;
+  if (d.bias[grp]) v += __ldg(d.bias[grp] + n);
+  float* cp = d.C[grp] + (long long)m * d.ldc + n;
+  if (d.beta != 0.f) v = fmaf(d.beta, *cp, v);
+  if (d.row_scale && grp == 0) v = fmaf(__ldg(d.row_scale + m), __ldg(d.addend + (long long)m * d.ld_add + n), v);
+  if (d.act == B200NP_ACT_RELU) v = fmaxf(v, 0.f);
+  else if (d.act == B200NP_ACT_TANH) v = tanhf(v);
+  *cp = v;
+}
+
 }  // namespace
 
 extern "C" size_t b200np_gemm_workspace(const b200np_gemm_desc* dp) {
@@ -212,6 +242,10 @@ extern "C" int b200np_gemm(const b200np_gemm_desc* dp, void* stream) {
       if (rc != B200NP_OK) return rc;
     }
     return B200NP_OK;
+  }
+  if ((long long)d.M * d.N <= 4096 && d.K >= 64) {
+    gemm_skinny_kernel<<<dim3((unsigned)((d.M * d.N + 7) / 8), d.groups), 256, 0, as_stream(stream)>>>(g);
+    return launch_status();
   }
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.groups);
   gemm_kernel<<<grid, 128, 0, as_stream(stream)>>>(g);
