@@ -125,6 +125,19 @@ def test_conv_block_ops(prec, cin, cout, hw, n):
         assert rel(from_nhwc(dx), x.grad) < tol
 
 
+def test_wgrad_halo_formulation_opt_in():
+    """The halo formulation of the 3x3 stride-1 (+ skip) weight gradient (csrc/tapwgrad_halo.cu) is selected per process
+    by B200NP_WGRAD_HALO=1: run the conv-block parity cases whose maps it covers (32x32 and 16x16) in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, B200NP_WGRAD_HALO="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k",
+                        "conv_block and (64-64-64-2 or 64-64-32-3) and not fp32"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "4 passed" in r.stdout, r.stdout[-500:]
+
+
 def test_pools_and_flatten():
     ops = _ops()
     x = rnd(5, 64, 4, 4, seed=1)

@@ -1,8 +1,14 @@
 // C ABI of the channel-dense NHWC convolutions: builds tap tables (tapconv.cuh) for forward,
 // data-gradient and weight-gradient and dispatches to the tcgen05 kernels (64-channel layers) or
 // the CUDA-core kernels (fp32 validation mode; 32/48-channel layers of encoder_w0).
+#include <cstdlib>
+
 #include "tapconv.cuh"
 #include "umma.cuh"
+
+#ifndef WGRAD_HALO_DEFAULT
+#define WGRAD_HALO_DEFAULT false
+#endif
 
 using namespace b200np;
 
@@ -203,11 +209,22 @@ extern "C" int b200np_conv_dgrad(const float* dy, const float* wd, float* dx, co
   return B200NP_OK;
 }
 
+// The halo formulation of the 3x3 stride-1 weight gradient (tapwgrad_halo.cu).  B200NP_WGRAD_HALO=0 keeps the gather kernel.
+static bool wgrad_halo_enabled() {
+  static const bool on = [] { const char* e = getenv("B200NP_WGRAD_HALO"); return e ? e[0] != '0' : WGRAD_HALO_DEFAULT; }();
+  return on;
+}
+static int halo_chunks_for(int N, int OH, int OW, int Cin, int Cout, int R, int stride) {
+  return (wgrad_halo_enabled() && Cin == 64 && Cout == 64 && R == 3 && stride == 1) ? tapwgrad_halo_chunks(N, OH, OW) : 0;
+}
+
 extern "C" size_t b200np_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int stride) {
   if (N <= 0 || stride <= 0) return 0;
   long long M = (long long)N * (H / stride) * (W / stride);
   int nt = R * R + 1;  // room for a fused skip-projection tap
   int chunks = wgrad_chunks(M, nt);
+  const int hc = halo_chunks_for(N, H / stride, W / stride, Cin, Cout, R, stride);
+  if (hc > chunks) chunks = hc;
   size_t part = (size_t)chunks * nt * Cout * Cin * sizeof(float);
   size_t dbw = b200np_colsum_workspace(M, Cout), dbp = (size_t)chunks * Cout * sizeof(float);
   return part + (dbw > dbp ? dbw : dbp);
@@ -239,12 +256,22 @@ extern "C" int b200np_conv_wgrad(const float* x, const float* dy, float* dw, flo
   a.pix_per_chunk = wgrad_pix_per_chunk(M, a.chunks);
   a.part = (float*)ws;
   const int per = nt * Cout * Cin;
-  const size_t part_bytes = (size_t)a.chunks * per * sizeof(float);
+  size_t part_bytes = (size_t)a.chunks * per * sizeof(float);
   int rc = B200NP_E_UNSUPPORTED;
   bool db_fused = false;
   if (use_umma(precision, Cin, Cout)) {
-    a.part_db = db ? (float*)((char*)ws + part_bytes) : nullptr;   // bias gradient from the dy tiles the kernel stages
-    rc = launch_tapwgrad_umma(a, precision, st);
+    const int hc = halo_chunks_for(N, a.OH, a.OW, Cin, Cout, R, stride);
+    if (hc > 0) {   // tile-staged taps (tapwgrad_halo.cu); sets a.chunks = hc
+      const size_t pb = (size_t)hc * per * sizeof(float);
+      a.part_db = db ? (float*)((char*)ws + pb) : nullptr;
+      rc = launch_tapwgrad_halo(a, precision, st);
+      if (rc == B200NP_OK) part_bytes = pb;
+      else if (rc == B200NP_E_UNSUPPORTED) a.chunks = wgrad_chunks(M, nt);
+    }
+    if (rc == B200NP_E_UNSUPPORTED) {
+      a.part_db = db ? (float*)((char*)ws + part_bytes) : nullptr;   // bias gradient from the dy tiles the kernel stages
+      rc = launch_tapwgrad_umma(a, precision, st);
+    }
     db_fused = rc == B200NP_OK && db;
   }
   if (rc == B200NP_E_UNSUPPORTED) {

@@ -68,6 +68,10 @@ int launch_tapwgrad_simt(const TapWgradArgs& a, cudaStream_t st);
 // tcgen05 path (tapconv_umma.cu); returns B200NP_E_UNSUPPORTED when the shape does not fit
 int launch_tapconv_umma(const TapConvArgs& a, int precision, cudaStream_t st);
 int launch_tapwgrad_umma(const TapWgradArgs& a, int precision, cudaStream_t st);
+// halo formulation of the 3x3 stride-1 (+ skip) weight gradient (tapwgrad_halo.cu): chunk count for the workspace
+// (0: shape does not fit) and the launch, which sets a.chunks
+int tapwgrad_halo_chunks(int N, int OH, int OW);
+int launch_tapwgrad_halo(TapWgradArgs& a, int precision, cudaStream_t st);
 // Several outputs from one staged input ("classes"): tap t accumulates into output class tap_cls[t] (taps sorted
 // by class), class c is written at dst pixel (oy*dst_s + oy_c, ox*dst_s + ox_c).  The four input-parity classes
 // of a stride-2 data gradient read the same dY halo, so one launch stages it once for all four.
