@@ -1,10 +1,12 @@
-// Hardware probe: cycles per tcgen05.mma.kind::tf32 (M=128, K=8) as a function of N and of the A operand's
+// Hardware probe: cycles per tcgen05.mma.kind::tf32 (M=128 or 64, K=8) as a function of N and of the A operand's
 // row-group stride (SBO), both operands in shared memory.  One CTA, one issuing thread, back-to-back MMAs.
+// (M = 64 added at the end of round 1, not yet run: is a single-tap MMA cheaper than the unused half of a tap pair in
+// csrc/tapwgrad_halo.cu role 1?)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(128) rate_kernel(long long* out, int N, int sbo_rows, int iters, int ncta_dummy) {
+__global__ void __launch_bounds__(128) rate_kernel(long long* out, int N, int sbo_rows, int iters, int M) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bar = (uint64_t*)(smem + 120 * 1024);
@@ -19,7 +21,7 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out, int N, int sb
   if (tid == 0) {
     uint32_t a16 = (smem_u32(smem) & 0x3FFFF) >> 4, b16 = (smem_u32(smem + 64 * 1024) & 0x3FFFF) >> 4;
     uint32_t a_hi = ((uint32_t)(sbo_rows * 128) >> 4) | (1u << 14) | (2u << 29), b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128 >> 4) << 24);
+    uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -44,11 +46,12 @@ int main() {
   size_t smem = 122 * 1024 + 1024;
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int iters = 2000;
-  for (int ncta : {1, 148}) for (int N : {64, 128, 256}) for (int sbo : {8, 10}) {
-    rate_kernel<<<ncta, 128, smem>>>(d, N, sbo, iters, 0);
+  for (int M : {128, 64}) for (int ncta : {1, 148}) for (int N : {64, 128, 256}) for (int sbo : {8, 10}) {
+    if (M == 64 && sbo != 8) continue;
+    rate_kernel<<<ncta, 128, smem>>>(d, N, sbo, iters, M);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    printf("ctas=%3d N=%3d sbo_rows=%2d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (%s)\n", ncta, N, sbo, (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), cudaGetErrorString(e));
+    printf("M=%3d ctas=%3d N=%3d sbo_rows=%2d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (%s)\n", ncta, N, sbo, (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), cudaGetErrorString(e));
   }
   return 0;
 }
