@@ -51,7 +51,7 @@ int main() {
     rate_kernel<<<ncta, 128, smem>>>(d, N, sbo, iters, M);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    printf("M=%3d ctas=%3d N=%3d sbo_rows=%2d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (%s)\n", ncta, N, sbo, (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), cudaGetErrorString(e));
+    printf("M=%3d ctas=%3d N=%3d sbo_rows=%2d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (%s)\n", M, ncta, N, sbo, (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), cudaGetErrorString(e));
   }
   return 0;
 }
