@@ -133,7 +133,8 @@ def test_wgrad_halo_formulation_opt_in():
     import sys
     env = dict(os.environ, B200NP_WGRAD_HALO="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k",
-                        "conv_block and (64-64-64-2 or 64-64-32-3) and not fp32"], env=env, capture_output=True, text=True)
+                        "conv_block and (64-64-64-2 or 64-64-32-3) and not fp32"], env=env, capture_output=True, text=True,
+                       timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "4 passed" in r.stdout, r.stdout[-500:]
 
