@@ -9,8 +9,14 @@ and 21 target images of 128x128x1 per task (weak scaling: per-GPU work is fixed)
 
 Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` times the same
 step through the public API with pinned HOST inputs copied in and the loss read back every step.
-`--impl reference` times the CPU restatement of the reference (oracle/np_oracle.py, kind "port":
-the Python reference itself cannot travel to the GPU box) on a bounded sample of the same workload.
+`--impl reference` times the reference's own modules (networks.ANPDistractor + trainer.losses.LossFunc +
+torch.optim.Adam, unmodified, from the byte-identical copy oracle/_ref that oracle/make_ref.py materialises;
+kind "reference") on the box's host cores, on the FULL 20-task step; without that copy it falls back to the CPU
+restatement (oracle/np_oracle.py, kind "port") on a 2-task sample.  `--impl reference-gpu` (internal; run as a
+subprocess by the B200 arm) times the same reference modules on the B200 through cuDNN / cuBLAS -- the on-box bar.
+
+Other workloads (BASELINE.json configs 2, 4, 5): --model CNPShapeNet1D|ANP|CNPDistractor|ANPShapeNet1D|CondNeuralProcess,
+--nc N (nt follows the dataset's split), --scaling strong --tasks G (global meta-batch G split over the ranks).
 """
 import argparse
 import json
@@ -33,11 +39,48 @@ import torch  # noqa: E402
 TASKS_PER_GPU, NC, NT = 20, 15, 21
 METRIC, UNIT = "ANPDistractor meta-train tasks/sec", "tasks/s"
 
+# model: (task, agg_mode, img_agg, extra config, default tasks/GPU, views per task)   -- cfg/train/*.yaml
+MODELS = {
+    "ANPDistractor": ("distractor", "attention", "max", dict(dim_w=16), 20, 36),
+    "CNPDistractor": ("distractor", "max", "max", dict(dim_w=16), 20, 36),
+    "ANP": ("shapenet_3d", "attention", "reshape", dict(), 20, 30),
+    "CondNeuralProcess": ("shapenet_3d", "max", "reshape", dict(), 20, 30),
+    "CNPShapeNet1D": ("shapenet_1d", "mean", "", dict(dim_w=64, dim_r=100, dim_z=64, n_hidden_units_r=[100, 100]), 10, 30),
+    "ANPShapeNet1D": ("shapenet_1d", "attention", "", dict(dim_w=64, dim_r=64, dim_z=64, n_hidden_units_r=[100, 100]), 10, 30),
+}
+IMG = {"distractor": ([128, 128, 1], 2, 2), "shapenet_1d": ([128, 128, 1], 3, 2), "shapenet_3d": ([64, 64, 4], 4, 4)}
 
-def make_cfg(T, device):
-    return types.SimpleNamespace(device=device, img_size=[128, 128, 1], task="distractor", tasks_per_batch=T,
-                                 input_dim=2, output_dim=2, agg_mode="attention", img_agg="max", dim_w=16,
-                                 seed=2578)
+
+def make_cfg(T, device, model="ANPDistractor"):
+    """Namespace with the attributes configs/config.py:33-104 would set from cfg/train/<model>.yaml."""
+    task, agg, img_agg, extra, _, _ = MODELS[model]
+    img_size, input_dim, output_dim = IMG[task]
+    base = dict(method=model, device=device, img_size=img_size, task=task, tasks_per_batch=T, input_dim=input_dim,
+                output_dim=output_dim, agg_mode=agg, img_agg=img_agg, dim_w=None, dim_r=None, dim_z=None,
+                n_hidden_units_r=None, temperature=0.07, seed=2578, loss_type="mse", beta=0, contrastive=False,
+                max_ctx_num=15)
+    base.update(extra)
+    return types.SimpleNamespace(**base)
+
+
+def workload(args):
+    """(model, task, tasks per rank, nc, nt) of this invocation."""
+    task, _, _, _, t_default, views = MODELS[args.model]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "strong":
+        if args.tasks % world:
+            raise SystemExit(f"--tasks {args.tasks} is not divisible by {world} ranks")
+        T = args.tasks // world
+    else:
+        T = args.tasks or t_default
+    nc = args.nc if args.nc is not None else 15
+    if args.nt is not None:
+        nt = args.nt
+    elif args.model == "ANPDistractor" or task == "distractor":
+        nt = views - nc            # train split of the 36 views (shapenet_distractor.py:287-294)
+    else:
+        nt = 15
+    return args.model, task, T, nc, nt
 
 
 def peaks():
@@ -50,8 +93,43 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port)
+# reference arms: the reference's own modules (oracle/_ref) on the host cores / on the GPU; oracle port fallback
 # --------------------------------------------------------------------------------------------
+REF_COPY = os.path.join(ROOT, "oracle", "_ref")
+
+
+def have_reference_copy():
+    return os.path.isfile(os.path.join(REF_COPY, "networks", "ANPDistractor.py"))
+
+
+def _reference_stepper(model_name, T, nc, nt, device):
+    """zero_grad -> forward -> loss -> backward -> Adam with the UNMODIFIED reference classes
+    (train.py:41-56,92; trainer/model_trainer.py:59-93), inputs resident on `device`."""
+    os.environ["B200NP_REFERENCE_ROOT"] = REF_COPY      # never /root/reference at run time: it is not on the GPU box
+    while PKG in sys.path:                              # none of the B200 package on this arm's import path
+        sys.path.remove(PKG)
+    for k in [k for k in sys.modules if k.split(".")[0] in ("networks", "trainer", "b200np")]:
+        del sys.modules[k]
+    from oracle import ref_shims, synth
+    cfg = make_cfg(T, device, model_name)
+    model = ref_shims.reference_class(model_name)(cfg).to(device)
+    lossf = ref_shims.reference_lossfunc()(cfg.loss_type, cfg.task)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    batch = [torch.from_numpy(a).to(device) for a in synth.task_batch(cfg.task, T, nc, nt, seed=1)]
+    model.train()
+
+    def step():
+        cx, cy, tx, ty = batch
+        opt.zero_grad()
+        mu, var, kl = model(cx, cy, tx)
+        loss = lossf.calc_loss(mu, var, ty)
+        loss += kl * cfg.beta
+        loss.backward()
+        opt.step()
+        return loss
+    return step
+
+
 def cpu_port_step_time(sample_tasks, steps, warmup):
     from oracle import np_oracle, synth
     from networks.ANPDistractor import ANPDistractor
@@ -71,25 +149,101 @@ def cpu_port_step_time(sample_tasks, steps, warmup):
 
 
 def run_reference_arm(args, rank):
+    """CPU arm.  With oracle/_ref: the reference's own modules on the full per-GPU step (same config as the B200 arm).
+    Otherwise the oracle port on a 2-task sample."""
     if rank != 0:
         return
-    sample = 2
-    times = cpu_port_step_time(sample, args.steps, args.warmup)
+    model_name, task, T, nc, nt = workload(args)
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    if have_reference_copy():
+        kind, sample = "reference", T
+        step = _reference_stepper(model_name, T, nc, nt, "cpu")
+        for _ in range(args.warmup):
+            step()
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            float(step().detach())
+            times.append(time.perf_counter() - t0)
+        what = (f"the reference's own {model_name} + LossFunc + torch.optim.Adam (oracle/_ref, unmodified), "
+                f"full step of {T} tasks (nc={nc}, nt={nt}) per timed step")
+    else:
+        if model_name != "ANPDistractor":
+            raise SystemExit("the oracle-port fallback of the reference arm only covers ANPDistractor")
+        kind, sample = "port", 2
+        times = cpu_port_step_time(sample, args.steps, args.warmup)
+        what = f"{sample} tasks/step (nc={nc}, nt={nt}), full fwd+loss+bwd+Adam, oracle/np_oracle.py"
     total = sum(times)
     value = sample * len(times) / total
-    cores = torch.get_num_threads()
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(model_name), "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ANPDistractor meta-train step, nc={NC} nt={NT} 128x128x1, {TASKS_PER_GPU} tasks/GPU",
-                   "note": "CPU arm: each step is a bounded sample of the workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} tasks/step (nc={NC}, nt={NT}), full fwd+loss+bwd+Adam, oracle/np_oracle.py"},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1, extra={"note": "CPU arm: host cores only; one rank's share of the step"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": what},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu_arm(args):
+    """On-box bar: the reference's own modules on the B200 through cuDNN / cuBLAS / ATen, once with
+    PyTorch's defaults (cuDNN convolutions may use TF32, matmuls stay fp32) and once with TF32 disallowed."""
+    if not have_reference_copy():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref not materialised"}))
+        return
+    model_name, task, T, nc, nt = workload(args)
+    out = {"impl": "reference-gpu", "model": model_name, "tasks": T, "nc": nc, "nt": nt}
+    for label, tf32 in (("cudnn_tf32_default", True), ("fp32", False)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        step = _reference_stepper(model_name, T, nc, nt, "cuda:0")
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[label] = {"ms_per_step": ms, "tasks_per_s": T / ms * 1e3}
+        del step
+        torch.cuda.empty_cache()
+    out["peak_mem_GB"] = torch.cuda.max_memory_allocated() / 1e9
+    print(json.dumps(out), flush=True)
+
+
+def _sub_json(argv, timeout):
+    """Run `python bench.py <argv>` in a fresh process (the reference's `networks` package and the drop-in one cannot
+    share an interpreter) and return its last JSON line, or a dict with the failure."""
+    try:
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, capture_output=True, text=True,
+                           timeout=timeout, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": (r.stderr or "no output").strip().splitlines()[-1][:200]}
+    except Exception as e:   # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
+
+
+def metric_name(model_name):
+    return f"{model_name} meta-train tasks/sec"
+
+
+def workload_config(args, world, extra=None):
+    model_name, task, T, nc, nt = workload(args)
+    img = "64x64x3" if task == "shapenet_3d" else "128x128x1"
+    cfg = {"workload": f"{model_name} meta-train step (fwd+loss+bwd+allreduce+Adam), {T} tasks/GPU, nc={nc} nt={nt}, "
+                       f"{img} images, global tasks={T * world}",
+           "model_class": model_name, "tasks_per_gpu": T, "global_tasks": T * world, "nc": nc, "nt": nt}
+    if extra:
+        cfg.update(extra)
+    return cfg
 
 
 # --------------------------------------------------------------------------------------------
@@ -138,11 +292,12 @@ class ClockSampler:
 # B200 arm
 # --------------------------------------------------------------------------------------------
 def run_b200_arm(args, rank, world, local_rank):
+    import importlib
+
     import torch.distributed as td
-    from b200np import engine, ops
+    from b200np import engine
     from b200np.lib import LIB
     from b200np.optim import FlatParams, FusedAdam, GraphedStep
-    from networks.ANPDistractor import ANPDistractor
     from oracle import synth  # input generator only (integer hash); no oracle compute here
     from trainer.losses import LossFunc
 
@@ -153,16 +308,17 @@ def run_b200_arm(args, rank, world, local_rank):
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
     engine.set_precision(args.precision)
-    T = TASKS_PER_GPU
-    model = ANPDistractor(make_cfg(T, str(dev))).to(dev)
+    model_name, task, T, nc, nt = workload(args)
+    cls = getattr(importlib.import_module(f"networks.{model_name}"), model_name)
+    model = cls(make_cfg(T, str(dev), model_name)).to(dev)
     flat = FlatParams(model)
     opt = FusedAdam(flat, lr=1e-4)
-    lossf = LossFunc("mse", "distractor")
+    lossf = LossFunc("mse", task)
 
-    # 4 distinct resident batches per rank (189 MB of inputs > 126 MB L2; a step also streams ~2 GB of
+    # 4 distinct resident batches per rank (ANPDistractor: 189 MB of inputs > 126 MB L2; a step also streams ~2 GB of
     # activations, far beyond L2), rotated between iterations
     nbatch = 4
-    host = [[torch.from_numpy(a).pin_memory() for a in synth.task_batch("distractor", T, NC, NT, seed=100 * rank + i)]
+    host = [[torch.from_numpy(a).pin_memory() for a in synth.task_batch(task, T, nc, nt, seed=100 * rank + i)]
             for i in range(nbatch)]
     resident = [[t.to(dev) for t in b] for b in host]
 
@@ -245,33 +401,172 @@ def run_b200_arm(args, rank, world, local_rank):
     if rank != 0:
         finish()
         return
-    roof = dominant_kernel_roofline(args, dev) if not args.profile else None
-    cpu = None
+    extras = {}
+    if world == 1 and not args.profile and not args.no_dropin:
+        extras["e2e_dropin"] = dropin_loop(args, dev, model_name, task, T, nc, nt)
+    is_headline = model_name == "ANPDistractor" and (nc, nt) == (NC, NT)
+    roof = dominant_kernel_roofline(args, dev) if (not args.profile and is_headline) else None
+    if roof is not None:
+        extras["tf32_cublas_peak"] = measured_tf32_peak(dev)
+        extras["hbm_kernels"] = hbm_bound_kernels(dev, T, nc, nt, flat.n_live)
+    cpu = gpu_ref = None
     if world == 1 and not args.no_cpu_baseline and not args.profile:
-        sample = 2
-        times = cpu_port_step_time(sample, 3, 1)
-        cpu = {"value": sample * len(times) / sum(times), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"3 steps of {sample} tasks (nc={NC}, nt={NT}), fwd+loss+bwd+Adam, oracle/np_oracle.py"}
+        # free this process's GPU memory first: the on-box bar below runs the reference on the same GPU
+        fwd = ["--model", model_name, "--nc", str(nc), "--nt", str(nt), "--tasks", str(T)]
+        sub = _sub_json(["--impl", "reference", "--steps", "3", "--warmup", "1"] + fwd, timeout=600)
+        cpu = sub.get("cpu_baseline") or {"unavailable": sub.get("unavailable", "no cpu_baseline in the sub-run")}
+        if "value" in cpu:
+            cpu["sample"] = "3 timed steps after 1 warm-up; " + cpu["sample"]
+        gpu_ref = _sub_json(["--impl", "reference-gpu", "--steps", "5", "--warmup", "3"] + fwd, timeout=600)
     tasks = T * world
     line = {
-        "metric": METRIC, "value": tasks * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+        "metric": metric_name(model_name), "value": tasks * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": args.scaling, "vs_baseline": None,
         "dtype": {"tf32x3": "f32 (3xTF32 split on tcgen05, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": f"ANPDistractor meta-train step (fwd+loss+bwd+allreduce+Adam), {T} tasks/GPU, "
-                               f"nc={NC} nt={NT}, 128x128x1 images, global tasks={tasks}",
-                   "precision": args.precision, "cuda_graph": bool(args.graph),
-                   "l2": "inputs rotate over 4 resident batches (189 MB > 126 MB L2); ~2 GB of activations streamed per step"},
+        "config": workload_config(args, world, extra={
+            "precision": args.precision, "cuda_graph": bool(args.graph),
+            "l2": "inputs rotate over 4 resident batches (ANPDistractor: 189 MB > 126 MB L2); ~2 GB of activations "
+                  "streamed per step"}),
         "e2e": {"value": tasks * e2e_steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "gpu_reference": gpu_ref,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
     finish()
+
+
+def dropin_loop(args, dev, model_name, task, T, nc, nt):
+    """The reference trainer's own loop (trainer/model_trainer.py:59-93) on the drop-in modules: zero_grad ->
+    .to(device) of a pinned host batch -> model -> calc_loss -> `losses += kl * beta` -> backward ->
+    torch.optim.Adam.step -> losses.item(), forward / backward replayed as per-shape CUDA graphs behind the nn.Module
+    contract (b200np/graphed.py).  Two numbers: the bench's fixed (nc, nt), and `shot ~ U{1..15}` redrawn per step
+    like dataset/shapenet_distractor.py:197 (nt = views - nc, so the work per step varies)."""
+    import importlib
+    import random
+
+    from oracle import synth
+    from trainer.losses import LossFunc
+    cls = getattr(importlib.import_module(f"networks.{model_name}"), model_name)
+    cfg = make_cfg(T, str(dev), model_name)
+    model = cls(cfg).to(dev)
+    model.enable_cuda_graphs(True)
+    lossf = LossFunc("mse", task)
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-4)
+    views = nc + nt
+    out = {}
+    for label, shots in (("fixed_shot", [nc]), ("shot_uniform_1_15", list(range(1, 16)))):
+        if label != "fixed_shot" and views - 15 < 1:
+            continue
+        pool = {k: [torch.from_numpy(a).pin_memory() for a in synth.task_batch(task, T, k, views - k, seed=7 + k)]
+                for k in shots}
+        rng = random.Random(0)
+
+        def one():
+            k = shots[rng.randrange(len(shots))]
+            model.train()
+            optimizer.zero_grad()
+            ctx_x, ctx_y, qry_x, qry_y = (t.to(dev) for t in pool[k])
+            pr_mu, pr_var, kl = model(ctx_x, ctx_y, qry_x)
+            losses = lossf.calc_loss(pr_mu, pr_var, qry_y)
+            losses += kl * cfg.beta
+            losses.backward()
+            optimizer.step()
+            return losses.item()
+        for k in shots:          # build every shape's graphs outside the timed region
+            rng_state = rng.getstate()
+            shots_saved, shots[:] = list(shots), [k]
+            one()
+            shots[:] = shots_saved
+            rng.setstate(rng_state)
+        n = max(5, min(args.steps, 20))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            one()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[label] = {"value": T * n / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / n, "steps": n}
+    out["h2d_bytes_per_step"] = sum(t.numel() * 4 for t in next(iter(pool.values())))
+    out["d2h_bytes_per_step"] = 4
+    out["what"] = ("reference-style training loop (model_trainer.py:59-93) with torch.optim.Adam on the drop-in modules, "
+                   "pinned host batch -> .to(device) and loss.item() every step, wall clock")
+    del model, optimizer
+    torch.cuda.empty_cache()
+    return out
+
+
+def measured_tf32_peak(dev):
+    """cuBLAS TF32 GEMM 8192^3 (torch.matmul with allow_tf32), best of 10 -- measured the way MEASURED_PEAKS.json
+    measures bf16 (BASELINE.md section 3 asks for the TF32 figure); context for the roofline's bf16/2 denominator."""
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(3):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return {"tflops": 2.0 * n ** 3 / (best * 1e-3) / 1e12, "how": "torch.matmul fp32 8192^3 with allow_tf32, best of 10"}
+
+
+def hbm_bound_kernels(dev, T, nc, nt, n_params):
+    """Achieved HBM GB/s of the HBM-bound class (north_star: aggregation, pooling, loss, Adam), each timed alone on
+    buffers larger than L2 where the op's own size allows (Adam; the others are KB-sized at this workload and are
+    reported at a 64x scaled batch so that the number is a bandwidth, not a launch latency)."""
+    from b200np import ops
+    pk = peaks()
+    out = {}
+
+    def entry(sec, nbytes, what):
+        return {"GBps": nbytes / sec / 1e9, "frac_of_hbm_peak": nbytes / sec / 1e9 / pk["hbm"], "bytes": nbytes,
+                "us": sec * 1e6, "what": what}
+    # Adam over 64 M parameters (16 B read + 12 B written each; the model's own 3.2 M-parameter launch is 90 MB)
+    n = 64 * 1024 * 1024
+    p, g, m, v = (torch.randn(n, device=dev) * 0.01 for _ in range(4))
+    v.abs_()
+    t_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+    sec = _time_kernel(lambda: ops.adam_step_dev(p, g, m, v, n, 1e-4, 0.9, 0.999, 1e-8, 0.0, t_dev))
+    out["adam"] = entry(sec, 28 * n, "fused Adam, 64 Mi parameters")
+    pm, gm, mm, vm = (t[:n_params] for t in (p, g, m, v))
+    sec = _time_kernel(lambda: ops.adam_step_dev(pm, gm, mm, vm, n_params, 1e-4, 0.9, 0.999, 1e-8, 0.0, t_dev))
+    out["adam_model_size"] = entry(sec, 28 * n_params, f"fused Adam at the model's size ({n_params} parameters, L2-resident)")
+    del p, g, m, v
+    # context max-aggregation over nc: reads T*nc*256 floats, writes T*256 values + indices
+    Tb = T * 2048
+    feats = torch.randn(Tb, nc, 256, device=dev)
+    sec = _time_kernel(lambda: ops.ctx_aggregate_fwd(feats, 1))
+    out["ctx_aggregate_max"] = entry(sec, feats.numel() * 4 + Tb * 256 * 8, f"max over nc={nc}, {Tb} tasks x 256 features")
+    del feats
+    # adaptive max-pool 2x2 + flatten of the trunk's last map [N,4,4,64] -> [N,256] (+ argmax)
+    Nb = T * (nc + nt) * 512
+    x = torch.randn(Nb, 4, 4, 64, device=dev)
+    sec = _time_kernel(lambda: ops.amp2_flatten_fwd(x))
+    out["adaptive_maxpool_flatten"] = entry(sec, x.numel() * 4 + Nb * 256 * 8, f"{Nb} maps of 4x4x64")
+    del x
+    # loss forward + backward (distractor): reads mu and y, writes d mu
+    R = T * nt * 65536
+    mu = torch.randn(R, 2, device=dev)
+    y = torch.randn(R, 2, device=dev)
+    sec = _time_kernel(lambda: ops.loss_fwd_bwd(mu, y, 0))
+    out["loss_fwd_bwd"] = entry(sec, R * 2 * 4 * 3, f"distractor loss, {R} rows")
+    return out
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at exactly the size
@@ -348,10 +643,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--precision", default=os.environ.get("B200NP_PRECISION", "tf32x3"),
                     choices=["tf32x3", "tf32", "fp32"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="ANPDistractor", choices=sorted(MODELS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --tasks (default: the YAML's tasks_per_batch) per GPU; strong: --tasks is the GLOBAL "
+                         "meta-batch, split over the ranks")
+    ap.add_argument("--tasks", type=int, default=0)
+    ap.add_argument("--nc", type=int, default=None, help="context images per task (default 15)")
+    ap.add_argument("--nt", type=int, default=None, help="target images per task (default: the dataset's train split)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and on-GPU reference legs")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the reference-style training-loop leg (e2e_dropin)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel from Python each step instead of replaying the captured CUDA graph")
     ap.add_argument("--roofline-only", action="store_true",
@@ -359,11 +662,16 @@ def main():
     ap.add_argument("--profile", action="store_true",
                     help="only the resident-input timed loop (for ncu launch lists); skips e2e / roofline / CPU legs")
     args = ap.parse_args()
+    if args.scaling == "strong" and not args.tasks:
+        ap.error("--scaling strong needs --tasks (the global meta-batch)")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.impl == "reference-gpu":
+        run_reference_gpu_arm(args)
         return
     if args.roofline_only:
         print(json.dumps(dominant_kernel_roofline(args, torch.device("cuda:0"))))

@@ -285,6 +285,29 @@ int b200np_adam_step_dev(float* p, const float* g, float* m, float* v, long long
                          float beta2, float eps, float weight_decay, int* step_dev, float grad_scale,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics (tools/ only; never called on the product path).  They switch global state of the
+ * library and are NOT thread-safe.
+ *   b200np_debug_set_wgrad_waves   pixel chunks per weight-gradient launch = waves * resident CTAs
+ *   b200np_debug_set_halo_flags    work-elimination bit mask for tools/halo_stalls.py (results become garbage)
+ *   b200np_debug_set_halo_min_taps route tap convolutions with fewer taps to the gather kernel
+ *   b200np_debug_set_halo_timing   device buffer [grid][8] of per-role stall-cycle counters (NULL = off)
+ * ------------------------------------------------------------------------------------------ */
+void b200np_debug_set_wgrad_waves(int waves);
+void b200np_debug_set_halo_flags(int flags);
+void b200np_debug_set_halo_min_taps(int ntaps);
+void b200np_debug_set_halo_timing(long long* buf);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU.  SURVEY.md 8b sketched `b200np_comm_{init,allreduce_sum,allreduce_max,destroy}` wrappers over
+ * NCCL.  They are deliberately NOT part of this ABI: the host side is Python/PyTorch (north_star), which already
+ * owns the NCCL communicator (`torch.distributed`, backend "nccl", one process per GPU); the three exchanges of
+ * the path -- the SUM all-reduce of the flat gradient and the FAVOR+ key-stabiliser MAX / its gradient SUM -- are
+ * issued on that communicator from b200np/dist.py on the same stream as the kernels and are captured into the
+ * step's CUDA graph with them.  A second communicator inside this library would duplicate NCCL's bootstrap for
+ * no data-path benefit.
+ * ------------------------------------------------------------------------------------------ */
+
 #ifdef __cplusplus
 }
 #endif

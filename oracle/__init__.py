@@ -17,6 +17,10 @@ Contents
                 does not exist on the GPU box, so nothing run there touches ``ref_shims``.
 
 Parity status: **pinned** -- ``np_oracle`` is checked against the live reference modules
-(tests/test_oracle_vs_reference.py, runs only where /root/reference exists) and against the
-committed golden vectors produced by the live reference (tests/test_oracle_golden.py).
+through the committed golden vectors that ``tests/golden/make_golden.py`` (2-task cases) and
+``tests/golden/make_golden_full.py`` (BASELINE.json's full sizes) produced by running the unmodified
+reference: ``tests/test_oracle_golden.py`` and ``tests/test_parity_at_size.py``.
+``make_ref``    copies the unmodified reference into the git-ignored ``oracle/_ref/`` so that it travels
+                to the GPU box: CPU / on-GPU reference arms of ``bench.py`` and the unmodified
+                ``ModelTrainer`` that ``tests/test_dropin.py`` drives on the drop-in modules.
 """

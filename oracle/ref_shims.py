@@ -10,7 +10,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("B200NP_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the byte-identical copy that
+    ``oracle/make_ref.py`` materialised into ``oracle/_ref/`` (git-ignored, shipped with the snapshot)."""
+    env = os.environ.get("B200NP_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/networks"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def reference_available():
@@ -34,7 +48,10 @@ def install():
         mods = _stub("torchmeta.modules", MetaModule=_Meta, MetaSequential=nn.Sequential,
                      MetaConv2d=nn.Conv2d, MetaBatchNorm2d=nn.BatchNorm2d, MetaLinear=nn.Linear)
         _stub("torchmeta", modules=mods)
-        _stub("torchmeta.utils", gradient_based=types.ModuleType("gradient_based"))
+        def _unavailable(*a, **k):
+            raise NotImplementedError("torchmeta is not installed in this image (MAML paths are outside the hot path)")
+        gb = _stub("torchmeta.utils.gradient_based", gradient_update_parameters=_unavailable)
+        _stub("torchmeta.utils", gradient_based=gb, gradient_update_parameters=_unavailable)
     if "pytorch_metric_learning" not in sys.modules:
         losses = _stub("pytorch_metric_learning.losses", NTXentLoss=object)
         _stub("pytorch_metric_learning", losses=losses)

@@ -69,6 +69,10 @@ SIGNATURES = {
     "b200np_loss_fwd_bwd": (_i, [_p, _p, _p, _p, _ll, _i, _i, _i, _p]),
     "b200np_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
     "b200np_adam_step_dev": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _f, _p]),
+    "b200np_debug_set_wgrad_waves": (None, [_i]),
+    "b200np_debug_set_halo_flags": (None, [_i]),
+    "b200np_debug_set_halo_min_taps": (None, [_i]),
+    "b200np_debug_set_halo_timing": (None, [_p]),
 }
 
 

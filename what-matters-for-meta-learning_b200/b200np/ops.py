@@ -356,7 +356,7 @@ def baco_bwd(dr, mu, s, r):
 def loss_fwd_bwd(mu, y, kind, want_grad=True):
     _chk(mu, "mu"), _chk(y, "y")
     R = mu.numel() // mu.shape[-1]
-    loss = empty((1,), mu)
+    loss = empty((), mu)   # 0-dim, owns its storage (LossFunc hands it out as the loss)
     dmu = torch.empty_like(mu) if want_grad else None
     check(LIB.b200np_loss_fwd_bwd(_ptr(mu), _ptr(y), _ptr(loss), _ptr(dmu), R, mu.shape[-1], y.shape[-1], kind,
                                   _stream()), "loss_fwd_bwd")

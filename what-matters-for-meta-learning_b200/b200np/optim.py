@@ -95,41 +95,79 @@ class GraphedStep:
     """One meta-train step (zero_grad, forward, loss, backward, all-reduce, Adam) captured in a CUDA graph.
 
     Every kernel of the path is launched on torch's current stream without host synchronisation or
-    allocation outside torch's caching allocator, so the whole step -- ~400 launches -- can be recorded once
-    per (nc, nt) shape and replayed with a single cudaGraphLaunch: no Python / ctypes / autograd time and no
-    launch gaps on the GPU.  Inputs are copied into static buffers before each replay.
+    allocation outside torch's caching allocator, so the whole step -- a few hundred launches -- can be recorded
+    once per (nc, nt) shape and replayed with a single cudaGraphLaunch: no Python / ctypes / autograd time and
+    no launch gaps on the GPU.  Inputs are copied into static buffers before each replay.
+
+    Shapes: the reference draws `shot ~ U{1..max_ctx_num}` per batch (dataset/shapenet_distractor.py:197), so the
+    context / target split changes from step to step.  Graphs are therefore kept in a cache keyed by the batch's
+    shapes (at most `max_ctx_num` entries) and built on first use; all of them share one memory pool, because they
+    never run concurrently.
+
+    Building a graph runs `warmup` real steps and the capture itself on the model; parameters, Adam moments and
+    the step counter are snapshotted before and restored afterwards, so constructing the object (or meeting a new
+    shape) does NOT advance training.
 
     Input pipeline: ``step(batch, next_batch=...)`` starts the host-to-device copy of the NEXT batch on a
     second stream into staging buffers while this step computes (the reference gets the same overlap from
     its pinned-memory DataLoader, trainer/model_trainer.py:59-67); the staged batch reaches the graph's
-    static inputs with a device-to-device copy (47 MB, ~20 us) at the start of its own step.
+    static inputs with a device-to-device copy (47 MB, ~20 us) at the start of its own step.  A batch handed to
+    ``prefetch`` must not be modified until the step that consumes it has been called: the staged copy is
+    matched to the step by object identity of its tensors.
     """
 
-    def __init__(self, model, lossf, opt, example_batch, warmup=3):
-        self.model, self.lossf, self.opt = model, lossf, opt
-        self.static = [torch.empty_like(t) for t in example_batch]
-        self.stage = [torch.empty_like(t) for t in example_batch]
+    def __init__(self, model, lossf, opt, example_batch=None, warmup=3):
+        self.model, self.lossf, self.opt, self.warmup = model, lossf, opt, warmup
         self.copy_stream = torch.cuda.Stream()
         self.ev_ready, self.ev_free = torch.cuda.Event(), torch.cuda.Event()
-        self._staged = None
-        for s, t in zip(self.static, example_batch):
-            s.copy_(t)
+        self._staged = None          # (graph entry, the prefetched batch's tensors)
+        self.cache = {}
+        self.pool = torch.cuda.graph_pool_handle()
         from . import engine
         # warm-up and capture run on one high-priority stream: the engine's companion streams (decoder CNN, weight
         # gradients) rank below it, and the captured kernel nodes keep those priorities
-        side = torch.cuda.Stream(priority=engine.MAIN_PRIORITY if engine.USE_PRIORITIES else 0)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._eager()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=side):
-            self.loss = self._eager()
+        self.side = torch.cuda.Stream(priority=engine.MAIN_PRIORITY if engine.USE_PRIORITIES else 0)
+        self.graph = self.loss = None
+        if example_batch is not None:
+            ent = self._entry(example_batch)
+            self.graph, self.loss = ent["graph"], ent["loss"]
 
-    def _eager(self):
-        cx, cy, tx, ty = self.static
+    @staticmethod
+    def _key(batch):
+        return tuple(tuple(t.shape) for t in batch)
+
+    def _entry(self, batch):
+        key = self._key(batch)
+        ent = self.cache.get(key)
+        if ent is not None:
+            return ent
+        dev = self.opt.flat.flat.device
+        ent = {"static": [torch.empty(t.shape, device=dev, dtype=t.dtype) for t in batch],
+               "stage": [torch.empty(t.shape, device=dev, dtype=t.dtype) for t in batch]}
+        for s, t in zip(ent["static"], batch):
+            s.copy_(t)
+        opt = self.opt
+        snap = (opt.flat.flat.clone(), opt.m.clone(), opt.v.clone(), opt.t_dev.clone(), opt.t)
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            for _ in range(self.warmup):
+                self._eager(ent["static"])
+        cur.wait_stream(self.side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=self.side, pool=self.pool):
+            loss = self._eager(ent["static"])
+        # neither the warm-up steps nor the capture may advance training
+        opt.flat.flat.copy_(snap[0]), opt.m.copy_(snap[1]), opt.v.copy_(snap[2]), opt.t_dev.copy_(snap[3])
+        opt.t = snap[4]
+        torch.cuda.synchronize()
+        ent["graph"], ent["loss"] = graph, loss
+        self.cache[key] = ent
+        return ent
+
+    def _eager(self, static):
+        cx, cy, tx, ty = static
         self.opt.zero_grad()
         mu, _, _ = self.model(cx, cy, tx)
         loss = self.lossf.calc_loss(mu, None, ty)
@@ -138,31 +176,37 @@ class GraphedStep:
         return loss.detach()
 
     def prefetch(self, batch):
-        """Start copying `batch` (pinned host or device tensors) into the staging buffers on the copy stream."""
+        """Start copying `batch` (pinned host or device tensors) into the staging buffers of its shape on the
+        copy stream."""
+        ent = self._entry(batch)
         cs = self.copy_stream
         cs.wait_event(self.ev_free)            # the previous occupant of the staging buffers has been consumed
         with torch.cuda.stream(cs):
-            for s, t in zip(self.stage, batch):
+            for s, t in zip(ent["stage"], batch):
                 s.copy_(t, non_blocking=True)
             self.ev_ready.record(cs)
-        self._staged = tuple(t.data_ptr() for t in batch)
+        self._staged = (ent, tuple(batch))     # holds the tensors: identity, not addresses, names the batch
 
     def __call__(self, batch, next_batch=None):
         cur = torch.cuda.current_stream()
-        if self._staged is not None and self._staged == tuple(t.data_ptr() for t in batch):
+        st = self._staged
+        if st is not None and len(st[1]) == len(batch) and all(a is b for a, b in zip(st[1], batch)):
+            ent = st[0]
             cur.wait_event(self.ev_ready)      # prefetched during the previous step
-            for s, t in zip(self.static, self.stage):
+            for s, t in zip(ent["static"], ent["stage"]):
                 s.copy_(t, non_blocking=True)
         else:
-            for s, t in zip(self.static, batch):
+            ent = self._entry(batch)
+            for s, t in zip(ent["static"], batch):
                 if s.data_ptr() != t.data_ptr():
                     s.copy_(t, non_blocking=True)
         self._staged = None
         self.ev_free.record(cur)
-        self.graph.replay()
+        ent["graph"].replay()
+        self.opt.t += 1
         if next_batch is not None:
             self.prefetch(next_batch)
-        return self.loss
+        return ent["loss"]
 
 
 class GraphedEval:

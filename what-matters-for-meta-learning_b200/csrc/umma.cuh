@@ -27,11 +27,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (sticky error the host sees) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (sticky error the host sees) instead of hanging the GPU.  The bound is WALL TIME
+// (20 s on %globaltimer, sampled every 64 K failed probes), not a spin count: under compute-sanitizer / ncu replay
+// or when a co-resident stream starves the CTA, a healthy wait can take millions of probes.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
+    if ((++spins & 0xffffu) == 0) {
+      uint64_t t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 20000000000ull) __trap();
+    }
   }
 }
 // One lane of a converged warp (the lowest active one).  The MMA-issuing code runs warp-uniformly and only

@@ -9,10 +9,12 @@
 Constructors create sub-modules in exactly the reference's order (the seeded RNG stream and the
 ``state_dict`` key order depend on it); ``forward`` hands the tensors to the CUDA engine.
 """
+import os
+
 import torch
 from torch import nn
 
-from networks.models import AttnLinear, EncoderFC, FastAttention, ImageEncoder, NPDecoder
+from networks._holders import AttnLinear, EncoderFC, FastAttention, ImageEncoder, NPDecoder
 
 N_HEADS = 8
 
@@ -43,11 +45,29 @@ class _NPBase(nn.Module):
         self.img_agg = config.img_agg
         self.y_dim = config.output_dim
 
+    def enable_cuda_graphs(self, on=True):
+        """Replay the forward (and, through autograd, the backward) as CUDA graphs cached per input shape
+        (b200np/graphed.py); the call contract is unchanged.  Also switched on by B200NP_GRAPHS=1."""
+        object.__setattr__(self, "_graphed", None)
+        object.__setattr__(self, "_use_graphs", bool(on))
+        return self
+
     def forward(self, batch_train_images, label_train, batch_test_images, test=False):
         """(ctx_x [T,nc,C,H,W], ctx_y [T,nc,L], tgt_x [T,nt,C,H,W]) -> (mu [T,nt,out], None, 0);
         same contract as networks/ANPDistractor.py:103-135."""
         from b200np import engine
-        mu = engine.forward(self, batch_train_images, label_train, batch_test_images)
+        use = getattr(self, "_use_graphs", None)
+        if use is None:
+            use = os.environ.get("B200NP_GRAPHS", "0") == "1"
+        if use and not torch.cuda.is_current_stream_capturing():
+            g = getattr(self, "_graphed", None)
+            if g is None:
+                from b200np.graphed import GraphedModel
+                g = GraphedModel(self)
+                object.__setattr__(self, "_graphed", g)   # not a sub-module / buffer: invisible to state_dict
+            mu = g(batch_train_images, label_train, batch_test_images)
+        else:
+            mu = engine.forward(self, batch_train_images, label_train, batch_test_images)
         return mu, None, 0
 
 

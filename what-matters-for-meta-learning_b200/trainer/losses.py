@@ -1,9 +1,14 @@
 """Drop-in ``LossFunc`` (trainer/losses.py:22-80 in the reference) on the CUDA loss kernel.
 
 Only ``loss_type == "mse"`` exists in the reference (losses.py:33); the four task losses it
-dispatches to are one fused forward+backward kernel here (b200np_loss_fwd_bwd).  The NT-Xent
-contrastive losses (losses.py:82-99) are third-party arithmetic outside the hot path.
+dispatches to are one fused forward+backward kernel here (b200np_loss_fwd_bwd).  When the reference
+checkout is on the path behind this package (``b200_run.py``), ``LossFunc`` subclasses the
+reference's own class, so everything outside the hot path (``pascal_1d``, the NT-Xent contrastive
+losses at losses.py:82-99) stays the reference's code.
 """
+import importlib.util
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -19,7 +24,9 @@ class _LossFn(Function):
         want = kind != 3
         loss, dmu = ops.loss_fwd_bwd(mu, y, kind, want_grad=want)
         ctx.dmu = dmu
-        return loss.view(())
+        # `loss` is a fresh 0-dim tensor, not a view: the reference trainer modifies the result in place
+        # (`losses += kl * beta`, trainer/model_trainer.py:80), which autograd forbids on a view made inside a Function
+        return loss
 
     @staticmethod
     def backward(ctx, g):
@@ -28,7 +35,27 @@ class _LossFn(Function):
         return None, ops.scale_by_device_scalar(ctx.dmu, g.contiguous().view(1)), None
 
 
-class LossFunc():
+def _reference_lossfunc():
+    """The reference's own LossFunc, if its trainer/losses.py sits behind this package on the path."""
+    import trainer
+    here = os.path.dirname(os.path.abspath(__file__))
+    for d in list(trainer.__path__):
+        cand = os.path.join(d, "losses.py")
+        if os.path.abspath(d) != here and os.path.isfile(cand):
+            try:
+                spec = importlib.util.spec_from_file_location("trainer._reference_losses", cand)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                return mod.LossFunc
+            except Exception:      # its third-party imports (pytorch_metric_learning) may be absent
+                return None
+    return None
+
+
+_Base = _reference_lossfunc() or object
+
+
+class LossFunc(_Base):
     def __init__(self, loss_type, task):
         """loss_type: only "mse" is implemented by the reference; task: distractor | shapenet_3d |
         shapenet_1d."""
@@ -44,6 +71,8 @@ class LossFunc():
             kind = 1
         elif self.task == "shapenet_1d":
             kind = 3 if test else 2
+        elif _Base is not object:
+            return super().calc_loss(pr_mu, pr_var, gt_y, test)   # e.g. pascal_1d: not on the hot path
         else:
             raise NotImplementedError(f"task {self.task!r} is outside the B200 hot path")
         if not (pr_mu.is_cuda and gt_y.is_cuda):
