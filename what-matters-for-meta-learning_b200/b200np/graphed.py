@@ -62,7 +62,9 @@ class GraphedModel:
             self._param_sig = sig
 
     def _build(self, key, inputs, train):
-        from . import engine
+        from torch.nn.utils.stateless import _reparametrize_module
+
+        from . import engine, ops
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
             self.side = torch.cuda.Stream(priority=engine.MAIN_PRIORITY if engine.USE_PRIORITIES else 0)
@@ -71,38 +73,59 @@ class GraphedModel:
         for s, t in zip(static, inputs):
             s.copy_(t)
         ent = {"static": static}
-        params = self._params()
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        params = [p for _, p in named]
+        # Warm-up and capture see the parameters through fresh leaf ALIASES (same storage): their gradient
+        # accumulators are created on the capturing streams and die with this build.  The model's own parameters may
+        # carry accumulators from an earlier iteration (kept alive by a retained loss tensor) that live on the
+        # caller's stream; autograd would then pull that stream into the capture and invalidate it.  It also leaves
+        # the caller's `.grad` fields alone.
+        alias = {n: p.detach().requires_grad_(True) for n, p in named}
+        leaves = [alias[n] for n, _ in named]
+
+        def fwd_bwd(dmu):
+            with _reparametrize_module(model, alias):
+                mu = engine.forward(model, *static)
+            if train:
+                mu.backward(dmu if dmu is not None else torch.ones_like(mu))
+            return mu
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)
-        with torch.cuda.stream(self.side):
+        with torch.cuda.stream(self.side), torch.set_grad_enabled(train):
             for _ in range(self.warmup):
-                with torch.set_grad_enabled(train):
-                    mu = engine.forward(model, *static)
-                    if train:
-                        torch.autograd.grad((mu,), params, (torch.ones_like(mu),), allow_unused=True)
+                fwd_bwd(None)
+                for a in leaves:
+                    a.grad = None
         cur.wait_stream(self.side)
         torch.cuda.synchronize()
         fwd = torch.cuda.CUDAGraph()
         with torch.set_grad_enabled(train):
             with torch.cuda.graph(fwd, stream=self.side, pool=self.pool):
-                mu = engine.forward(model, *static)
+                with _reparametrize_module(model, alias):
+                    mu = engine.forward(model, *static)
         ent["fwd"], ent["mu"] = fwd, mu
         if train:
-            dmu = torch.zeros_like(mu)
+            with torch.cuda.stream(self.side):
+                dmu = torch.zeros_like(mu)
+            torch.cuda.synchronize()
             bwd = torch.cuda.CUDAGraph()
             with torch.cuda.graph(bwd, stream=self.side, pool=self.pool):
-                grads = torch.autograd.grad((mu,), params, (dmu,), allow_unused=True)
+                # .backward(), not autograd.grad(inputs=...): the engine joins the streams of executed accumulator
+                # nodes (decoder CNN / weight-gradient companions) back into the caller's; captured inputs are not joined
+                mu.backward(dmu)
+                grads = [a.grad for a in leaves]
                 # one flat buffer (16-byte aligned segments), filled by a multi-copy launch per 64 tensors
                 pad = lambda k: (k + 3) // 4 * 4
-                total = sum(pad(p.numel()) for p, g in zip(params, grads) if g is not None)
+                total = sum(pad(g.numel()) for g in grads if g is not None)
                 gflat = torch.empty(max(total, 4), device=mu.device, dtype=torch.float32)
-                from . import ops
                 segs, views, off = [], [], 0
+                keep = []
                 for p, g in zip(params, grads):
                     if g is None:
                         views.append((0, 0, tuple(p.shape), False))
                         continue
                     g = g.contiguous()
+                    keep.append(g)
                     segs.append((g, off, g.numel()))
                     views.append((off, g.numel(), tuple(p.shape), True))
                     off += pad(g.numel())
@@ -111,7 +134,9 @@ class GraphedModel:
             # drop the captured autograd graph: its saved activations go back to the (graph-private) pool, where the
             # two graphs of this entry keep using them and later captures may share the addresses
             ent["mu"] = mu.detach()
-            del mu, grads
+            for a in leaves:
+                a.grad = None
+            del mu, grads, keep
         torch.cuda.synchronize()
         self.cache[key] = ent
         return ent

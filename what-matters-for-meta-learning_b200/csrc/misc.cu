@@ -328,6 +328,59 @@ __global__ void ctx_agg_fwd_kernel(const float* __restrict__ f, float* __restric
     if (idx) idx[i] = a;
   }
 }
+// D % 4 == 0, 16-byte aligned: thread = four consecutive features of one task; the context loop issues four
+// independent 16-byte loads per trip (a warp instruction covers 512 contiguous bytes), results leave as one float4 /
+// int4.  Same element order and comparison rule as the scalar kernel, so the results are bit-identical.
+__global__ void __launch_bounds__(128) ctx_agg_fwd_vec4_kernel(const float* __restrict__ f, float* __restrict__ out,
+                                                               int32_t* __restrict__ idx, int T, int nc, int D4,
+                                                               int mode) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * D4) return;
+  const int t = (int)(i / D4), c4 = (int)(i - (long long)t * D4);
+  const float4* p = reinterpret_cast<const float4*>(f) + (long long)t * nc * D4 + c4;
+  if (mode == 0) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; j + 4 <= nc; j += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (long long)(j + u) * D4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; j < nc; ++j) {
+      const float4 v = __ldg(p + (long long)j * D4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float inv = (float)nc;
+    reinterpret_cast<float4*>(out)[i] = make_float4(s.x / inv, s.y / inv, s.z / inv, s.w / inv);
+  } else {
+    float4 m = __ldg(p);
+    int4 a = make_int4(0, 0, 0, 0);
+    int j = 1;
+    for (; j + 4 <= nc; j += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (long long)(j + u) * D4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {   // strict '>' keeps the FIRST maximum (torch.max(dim) rule)
+        if (v[u].x > m.x) { m.x = v[u].x; a.x = j + u; }
+        if (v[u].y > m.y) { m.y = v[u].y; a.y = j + u; }
+        if (v[u].z > m.z) { m.z = v[u].z; a.z = j + u; }
+        if (v[u].w > m.w) { m.w = v[u].w; a.w = j + u; }
+      }
+    }
+    for (; j < nc; ++j) {
+      const float4 v = __ldg(p + (long long)j * D4);
+      if (v.x > m.x) { m.x = v.x; a.x = j; }
+      if (v.y > m.y) { m.y = v.y; a.y = j; }
+      if (v.z > m.z) { m.z = v.z; a.z = j; }
+      if (v.w > m.w) { m.w = v.w; a.w = j; }
+    }
+    reinterpret_cast<float4*>(out)[i] = m;
+    if (idx) reinterpret_cast<int4*>(idx)[i] = a;
+  }
+}
 __global__ void ctx_agg_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
                                    float* __restrict__ df, int T, int nc, int D, int mode) {
   long long n = (long long)T * nc * D;
@@ -346,6 +399,10 @@ extern "C" int b200np_ctx_aggregate_fwd(const float* feats, float* out, int32_t*
   if (!feats || !out || T <= 0 || nc <= 0 || D <= 0 || (mode != 0 && mode != 1)) return B200NP_E_BADARG;
   if (mode == 1 && !idx) return B200NP_E_BADARG;
   long long n = (long long)T * D;
+  if (D % 4 == 0 && aligned16(feats) && aligned16(out) && (!idx || aligned16(idx))) {
+    ctx_agg_fwd_vec4_kernel<<<(unsigned)ceil_div(n / 4, 128), 128, 0, as_stream(stream)>>>(feats, out, idx, T, nc, D / 4, mode);
+    return launch_status();
+  }
   ctx_agg_fwd_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(feats, out, idx, T, nc, D, mode);
   return launch_status();
 }
@@ -415,65 +472,95 @@ extern "C" int b200np_baco_bwd(const float* dr, const float* mu, const float* s,
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
 
+// One row of the loss: returns its term of the sum, writes d mu of the row (already divided by R).
+__device__ __forceinline__ float loss_row(const float* __restrict__ m, const float* __restrict__ t, float* __restrict__ d,
+                                          int L, int kind, float invR) {
+  if (kind == 0) {  // trainer/losses.py:35-36
+    const float2 mm = *reinterpret_cast<const float2*>(m);
+    float e0 = t[0] - mm.x, e1 = t[1] - mm.y;
+    float nrm = sqrtf(e0 * e0 + e1 * e1);
+    if (d) *reinterpret_cast<float2*>(d) = make_float2(-e0 / nrm * invR, -e1 / nrm * invR);
+    return nrm;
+  } else if (kind == 1) {  // trainer/losses.py:50-57
+    float q[4], g[4], nrm = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nrm += m[k] * m[k];
+    nrm = sqrtf(nrm);
+    float pos = 0.f, neg = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      q[k] = m[k] / nrm;
+      pos += fabsf(t[k] - q[k]);
+      neg += fabsf(-t[k] - q[k]);
+    }
+    if (d) {
+      float wp = pos < neg ? 1.f : (pos > neg ? 0.f : 0.5f);  // torch.minimum splits ties evenly
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g[k] = -(wp * sgn(t[k] - q[k]) + (1.f - wp) * sgn(-t[k] - q[k]));
+        dot += g[k] * q[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d[k] = (g[k] - q[k] * dot) / nrm * invR;
+    }
+    return fminf(pos, neg);
+  } else if (kind == 2) {  // trainer/losses.py:59-61
+    const float2 mm = *reinterpret_cast<const float2*>(m);
+    float e0 = t[0] - mm.x, e1 = t[1] - mm.y;
+    if (d) *reinterpret_cast<float2*>(d) = make_float2(-2.f * e0 * invR, -2.f * e1 * invR);
+    return e0 * e0 + e1 * e1;
+  }
+  // degree error, trainer/losses.py:63-76 (evaluation only)
+  const float r2d = 180.f / 3.14159265358979323846f;
+  float gt = t[L - 1] * r2d;
+  float a = acosf(m[0]);
+  if (m[1] < 0.f) a = -a + 2.f * 3.14159265358979323846f;
+  a *= r2d;
+  return fminf(fabsf(gt - a), fminf(fabsf(gt + 360.f - a), fabsf(gt - (a + 360.f))));
+}
+
+// The hot path's losses have a few hundred rows (T * nt): ONE block, one launch, deterministic block reduction.
 __global__ void loss_kernel(const float* __restrict__ mu, const float* __restrict__ y, float* __restrict__ loss,
                             float* __restrict__ dmu, long long R, int out, int L, int kind) {
   __shared__ float red[32];
   float acc = 0.f;
   const float invR = 1.f / (float)R;
-  for (long long r = threadIdx.x; r < R; r += blockDim.x) {
-    const float* m = mu + r * out;
-    const float* t = y + r * L;
-    if (kind == 0) {  // trainer/losses.py:35-36
-      float e0 = t[0] - m[0], e1 = t[1] - m[1];
-      float nrm = sqrtf(e0 * e0 + e1 * e1);
-      acc += nrm;
-      if (dmu) {
-        dmu[r * 2 + 0] = -e0 / nrm * invR;
-        dmu[r * 2 + 1] = -e1 / nrm * invR;
-      }
-    } else if (kind == 1) {  // trainer/losses.py:50-57
-      float q[4], g[4], nrm = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) nrm += m[k] * m[k];
-      nrm = sqrtf(nrm);
-      float pos = 0.f, neg = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        q[k] = m[k] / nrm;
-        pos += fabsf(t[k] - q[k]);
-        neg += fabsf(-t[k] - q[k]);
-      }
-      acc += fminf(pos, neg);
-      if (dmu) {
-        float wp = pos < neg ? 1.f : (pos > neg ? 0.f : 0.5f);  // torch.minimum splits ties evenly
-        float dot = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          g[k] = -(wp * sgn(t[k] - q[k]) + (1.f - wp) * sgn(-t[k] - q[k]));
-          dot += g[k] * q[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dmu[r * 4 + k] = (g[k] - q[k] * dot) / nrm * invR;
-      }
-    } else if (kind == 2) {  // trainer/losses.py:59-61
-      float e0 = t[0] - m[0], e1 = t[1] - m[1];
-      acc += e0 * e0 + e1 * e1;
-      if (dmu) {
-        dmu[r * 2 + 0] = -2.f * e0 * invR;
-        dmu[r * 2 + 1] = -2.f * e1 * invR;
-      }
-    } else {  // degree error, trainer/losses.py:63-76 (evaluation only)
-      const float r2d = 180.f / 3.14159265358979323846f;
-      float gt = t[L - 1] * r2d;
-      float a = acosf(m[0]);
-      if (m[1] < 0.f) a = -a + 2.f * 3.14159265358979323846f;
-      a *= r2d;
-      float e = fminf(fabsf(gt - a), fminf(fabsf(gt + 360.f - a), fabsf(gt - (a + 360.f))));
-      acc += e;
-    }
-  }
+  for (long long r = threadIdx.x; r < R; r += blockDim.x)
+    acc += loss_row(mu + r * out, y + r * L, dmu ? dmu + r * out : nullptr, L, kind, invR);
   float tot = block_sum(acc, red);
   if (threadIdx.x == 0) loss[0] = tot * invR;
+}
+// Large row counts (evaluation over whole datasets, the HBM-bandwidth measurement of bench.py): grid-stride over rows,
+// per-block partial sums, and the LAST block to finish (atomic ticket) adds the partials in block order -- one launch,
+// deterministic.  The partial buffer and the ticket are library globals: two such launches must not overlap (the
+// single-block kernel above, which the training step uses, has no shared state).
+constexpr int kLossBlocks = 4 * kNumSMs;
+__device__ float g_loss_part[kLossBlocks];
+__device__ unsigned int g_loss_ticket = 0;
+__global__ void __launch_bounds__(256) loss_multi_kernel(const float* __restrict__ mu, const float* __restrict__ y,
+                                                         float* __restrict__ loss, float* __restrict__ dmu, long long R,
+                                                         int out, int L, int kind) {
+  __shared__ float red[32];
+  __shared__ bool last;
+  float acc = 0.f;
+  const float invR = 1.f / (float)R;
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += st)
+    acc += loss_row(mu + r * out, y + r * L, dmu ? dmu + r * out : nullptr, L, kind, invR);
+  float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    g_loss_part[blockIdx.x] = tot;
+    __threadfence();
+    last = atomicAdd(&g_loss_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float s = 0.f;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(g_loss_part + b);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) { loss[0] = s * invR; g_loss_ticket = 0; }
 }
 extern "C" int b200np_loss_fwd_bwd(const float* mu, const float* y, float* loss, float* dmu, long long R,
                                    int out, int L, int kind, void* stream) {
@@ -483,6 +570,12 @@ extern "C" int b200np_loss_fwd_bwd(const float* mu, const float* y, float* loss,
   if (kind == 2 && (out != 2 || L < 2)) return B200NP_E_BADARG;
   if (kind == 3 && (out != 2 || L < 1 || dmu)) return B200NP_E_BADARG;
   if (kind < 0 || kind > 3) return B200NP_E_BADARG;
+  if (R > 16384) {
+    long long blocks = ceil_div(R, 256 * 4);
+    if (blocks > kLossBlocks) blocks = kLossBlocks;
+    loss_multi_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(mu, y, loss, dmu, R, out, L, kind);
+    return launch_status();
+  }
   loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(mu, y, loss, dmu, R, out, L, kind);
   return launch_status();
 }

@@ -123,6 +123,130 @@ struct Ring {
   }
 };
 
+// ===================== epilogue (shared by the register-staged and the TMA-fed kernel) =====================
+// warps kEpiWarp0 .. kEpiWarp0+3: TMEM -> registers -> bias / ReLU gates / activation -> NHWC global
+template <bool X3, bool DBG>
+__device__ __forceinline__ void halo_epilogue(const HaloArgs& h, uint64_t* acc_full, uint64_t* acc_empty,
+                                              uint32_t tmem_base, int warp, int lane, int dflags, long long* dbgp) {
+  const TapConvArgs& a = h.t;
+  constexpr uint32_t kAccCols = X3 ? 256u : 128u;
+  constexpr uint32_t kBlkCols = X3 ? 128u : 64u;
+  const int ncls = h.ncls, ntaps = a.ntaps;
+  const uint32_t set_stride = ncls > 1 ? kBlkCols : kAccCols;
+  // ===================== epilogue =====================
+  // (A shared-memory transposed store, which halved the stem kernel's time, was measured here and made this
+  // kernel slower -- 1.16 -> 2.3 ms for the fused stride-2 data gradient: with one epilogue warp per scheduler
+  // the extra STS/LDS/__syncwarp round trip is pure latency.  Direct 16-byte stores per pixel row are kept.)
+  const int q = warp & 3;                              // TMEM lane quarter this warp may access (warp id % 4)
+  const int m = q * 32 + lane;                         // accumulator row = output pixel of the tile
+  int acc_set = 0;
+  uint32_t acc_phase = 0;
+  long long w_e = 0;
+  const int kb_total = 2 * ntaps;
+  const int blocks_used = ncls > 1 ? 1 : (kb_total < kRot ? kb_total : kRot);
+  for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
+    const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
+    const int r0 = rb * kTileRows;
+    const int n = r0 / a.OH, oy = r0 - n * a.OH + (m >> 3), ox = xt * kTileCols + (m & 7);
+    // The packed ReLU gates of this thread's pixels (all classes) are fetched BEFORE the accumulators are waited
+    // for: with one epilogue warp per scheduler a load issued after the wait is pure exposed latency, and that
+    // latency (8 dependent mask loads per tile) was what paced the fused stride-2 data gradient.
+    uint32_t mw[4][2] = {};
+    if (a.mask_bits) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc)
+        if (cc < ncls) {
+          const int d_oy = ncls > 1 ? h.cls_oy[cc] : a.dst_oy, d_ox = ncls > 1 ? h.cls_ox[cc] : a.dst_ox;
+          const long long px = ((long long)n * a.dstH + (long long)oy * a.dst_s + d_oy) * a.dstW + (long long)ox * a.dst_s + d_ox;
+          const uint2 w2 = __ldg(reinterpret_cast<const uint2*>(a.mask_bits + px * 2));
+          mw[cc][0] = w2.x; mw[cc][1] = w2.y;
+        }
+    }
+   for (int cls = 0; cls < ncls; ++cls) {               // class mode: the tile's outputs, one accumulator set each
+    // (not unrolled: four copies of the epilogue body thrash the instruction cache; the prefetched gate words
+    // are picked with selects instead of register indexing)
+    const uint32_t mw0 = cls == 0 ? mw[0][0] : cls == 1 ? mw[1][0] : cls == 2 ? mw[2][0] : mw[3][0];
+    const uint32_t mw1 = cls == 0 ? mw[0][1] : cls == 1 ? mw[1][1] : cls == 2 ? mw[2][1] : mw[3][1];
+    const int set = ncls > 1 ? cls : acc_set;
+    const int d_oy = ncls > 1 ? h.cls_oy[cls] : a.dst_oy, d_ox = ncls > 1 ? h.cls_ox[cls] : a.dst_ox;
+    const long long off =
+        (((long long)n * a.dstH + (long long)oy * a.dst_s + d_oy) * a.dstW + (long long)ox * a.dst_s + d_ox) * 64;
+    mbar_wait_timed(acc_full + set, acc_phase, w_e, dbgp != nullptr);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + set * set_stride + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float acc[32];
+      {   // sum the rotating blocks (and, fp32-grade, their cross-term column group), smallest terms first
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        if (X3) {
+#pragma unroll
+          for (int b = 0; b < kRot; ++b)
+            if (b < blocks_used) {
+              tmem_ld32(taddr + b * 128 + 64 + hf * 32, r);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < kRot; ++b)
+          if (b < blocks_used) {
+            tmem_ld32(taddr + b * (X3 ? 128 : 64) + hf * 32, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+          }
+      }
+      if (hf == 1) {                                   // all TMEM reads of this set are done
+        tc_fence_before();
+        mbar_arrive(acc_empty + set);
+      }
+      const uint32_t mword = hf ? mw1 : mw0;             // 32 ReLU gates
+      uint32_t gates = 0u;                               // (output > 0) of this thread's 32 channels
+      // float-mask variant: all eight loads are issued before the first use (one exposed latency, not eight)
+      const bool fmask = !a.mask_bits && a.mask && !(dflags & 4);
+      float4 mk8[8];
+      if (fmask) {
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) mk8[qq] = ldg4(a.mask + off + hf * 32 + 4 * qq);
+      }
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq) {
+        const int c = hf * 32 + 4 * qq;
+        float4 o = make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
+        if (a.bias) {
+          const float4 b = ldg4(a.bias + c);
+          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        if (a.bias2) {
+          const float4 b = ldg4(a.bias2 + c);
+          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        if (a.mask_bits) {
+          const uint32_t nb4 = mword >> (4 * qq);
+          o.x = (nb4 & 1u) ? o.x : 0.f; o.y = (nb4 & 2u) ? o.y : 0.f;
+          o.z = (nb4 & 4u) ? o.z : 0.f; o.w = (nb4 & 8u) ? o.w : 0.f;
+        } else if (fmask) {
+          const float4 mk = mk8[qq];
+          o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
+          o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+        }
+        if (a.act == B200NP_ACT_RELU) {
+          o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        }
+        if (!(dflags & 4) || o.x == 12345.678f) *reinterpret_cast<float4*>(a.dst + off + c) = o;
+        gates |= (uint32_t)((o.x > 0.f) | ((o.y > 0.f) << 1) | ((o.z > 0.f) << 2) | ((o.w > 0.f) << 3)) << (4 * qq);
+      }
+      if (a.relu_bits) a.relu_bits[(off >> 6) * 2 + hf] = gates;
+    }
+   }
+    if (ncls > 1) acc_phase ^= 1;                      // every class set is used once per tile
+    else if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
+  }
+  if (dbgp && warp == kEpiWarp0 && lane == 0) dbgp[blockIdx.x * 8 + 7] = w_e;
+}
+
 // MAXT = 16-byte chunk tasks per producer thread and stage (ceil(total_slots / 32))
 // DBG: diagnostic build (stall counters, work-elimination flags); the production build compiles them out
 template <bool X3, int MAXT, bool DBG>
@@ -392,118 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
       }
     }
   } else {
-    // ===================== epilogue =====================
-    // (A shared-memory transposed store, which halved the stem kernel's time, was measured here and made this
-    // kernel slower -- 1.16 -> 2.3 ms for the fused stride-2 data gradient: with one epilogue warp per scheduler
-    // the extra STS/LDS/__syncwarp round trip is pure latency.  Direct 16-byte stores per pixel row are kept.)
-    const int q = warp & 3;                              // TMEM lane quarter this warp may access (warp id % 4)
-    const int m = q * 32 + lane;                         // accumulator row = output pixel of the tile
-    int acc_set = 0;
-    uint32_t acc_phase = 0;
-    long long w_e = 0;
-    const int kb_total = 2 * ntaps;
-    const int blocks_used = ncls > 1 ? 1 : (kb_total < kRot ? kb_total : kRot);
-    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
-      const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
-      const int r0 = rb * kTileRows;
-      const int n = r0 / a.OH, oy = r0 - n * a.OH + (m >> 3), ox = xt * kTileCols + (m & 7);
-      // The packed ReLU gates of this thread's pixels (all classes) are fetched BEFORE the accumulators are waited
-      // for: with one epilogue warp per scheduler a load issued after the wait is pure exposed latency, and that
-      // latency (8 dependent mask loads per tile) was what paced the fused stride-2 data gradient.
-      uint32_t mw[4][2] = {};
-      if (a.mask_bits) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          if (cc < ncls) {
-            const int d_oy = ncls > 1 ? h.cls_oy[cc] : a.dst_oy, d_ox = ncls > 1 ? h.cls_ox[cc] : a.dst_ox;
-            const long long px = ((long long)n * a.dstH + (long long)oy * a.dst_s + d_oy) * a.dstW + (long long)ox * a.dst_s + d_ox;
-            const uint2 w2 = __ldg(reinterpret_cast<const uint2*>(a.mask_bits + px * 2));
-            mw[cc][0] = w2.x; mw[cc][1] = w2.y;
-          }
-      }
-     for (int cls = 0; cls < ncls; ++cls) {               // class mode: the tile's outputs, one accumulator set each
-      // (not unrolled: four copies of the epilogue body thrash the instruction cache; the prefetched gate words
-      // are picked with selects instead of register indexing)
-      const uint32_t mw0 = cls == 0 ? mw[0][0] : cls == 1 ? mw[1][0] : cls == 2 ? mw[2][0] : mw[3][0];
-      const uint32_t mw1 = cls == 0 ? mw[0][1] : cls == 1 ? mw[1][1] : cls == 2 ? mw[2][1] : mw[3][1];
-      const int set = ncls > 1 ? cls : acc_set;
-      const int d_oy = ncls > 1 ? h.cls_oy[cls] : a.dst_oy, d_ox = ncls > 1 ? h.cls_ox[cls] : a.dst_ox;
-      const long long off =
-          (((long long)n * a.dstH + (long long)oy * a.dst_s + d_oy) * a.dstW + (long long)ox * a.dst_s + d_ox) * 64;
-      mbar_wait_timed(acc_full + set, acc_phase, w_e, dbgp != nullptr);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + set * set_stride + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        float acc[32];
-        {   // sum the rotating blocks (and, fp32-grade, their cross-term column group), smallest terms first
-          uint32_t r[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-          if (X3) {
-#pragma unroll
-            for (int b = 0; b < kRot; ++b)
-              if (b < blocks_used) {
-                tmem_ld32(taddr + b * 128 + 64 + hf * 32, r);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
-              }
-          }
-#pragma unroll
-          for (int b = 0; b < kRot; ++b)
-            if (b < blocks_used) {
-              tmem_ld32(taddr + b * (X3 ? 128 : 64) + hf * 32, r);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
-            }
-        }
-        if (hf == 1) {                                   // all TMEM reads of this set are done
-          tc_fence_before();
-          mbar_arrive(acc_empty + set);
-        }
-        const uint32_t mword = hf ? mw1 : mw0;             // 32 ReLU gates
-        uint32_t gates = 0u;                               // (output > 0) of this thread's 32 channels
-        // float-mask variant: all eight loads are issued before the first use (one exposed latency, not eight)
-        const bool fmask = !a.mask_bits && a.mask && !(dflags & 4);
-        float4 mk8[8];
-        if (fmask) {
-#pragma unroll
-          for (int qq = 0; qq < 8; ++qq) mk8[qq] = ldg4(a.mask + off + hf * 32 + 4 * qq);
-        }
-#pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {
-          const int c = hf * 32 + 4 * qq;
-          float4 o = make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
-          if (a.bias) {
-            const float4 b = ldg4(a.bias + c);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (a.bias2) {
-            const float4 b = ldg4(a.bias2 + c);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (a.mask_bits) {
-            const uint32_t nb4 = mword >> (4 * qq);
-            o.x = (nb4 & 1u) ? o.x : 0.f; o.y = (nb4 & 2u) ? o.y : 0.f;
-            o.z = (nb4 & 4u) ? o.z : 0.f; o.w = (nb4 & 8u) ? o.w : 0.f;
-          } else if (fmask) {
-            const float4 mk = mk8[qq];
-            o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
-            o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
-          }
-          if (a.act == B200NP_ACT_RELU) {
-            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-          }
-          if (!(dflags & 4) || o.x == 12345.678f) *reinterpret_cast<float4*>(a.dst + off + c) = o;
-          gates |= (uint32_t)((o.x > 0.f) | ((o.y > 0.f) << 1) | ((o.z > 0.f) << 2) | ((o.w > 0.f) << 3)) << (4 * qq);
-        }
-        if (a.relu_bits) a.relu_bits[(off >> 6) * 2 + hf] = gates;
-      }
-     }
-      if (ncls > 1) acc_phase ^= 1;                      // every class set is used once per tile
-      else if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
-    }
-    if (dbgp && warp == kEpiWarp0 && lane == 0) dbgp[blockIdx.x * 8 + 7] = w_e;
+    halo_epilogue<X3, DBG>(h, acc_full, acc_empty, tmem_base, warp, lane, dflags, dbgp);
   }
 
   tc_fence_before();
