@@ -7,7 +7,7 @@
 #include "umma.cuh"
 
 #ifndef WGRAD_HALO_DEFAULT
-#define WGRAD_HALO_DEFAULT false
+#define WGRAD_HALO_DEFAULT true
 #endif
 
 using namespace b200np;

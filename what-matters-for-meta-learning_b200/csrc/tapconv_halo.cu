@@ -33,7 +33,10 @@
 // A_hi x [B_hi;B_lo] (N = 128, 64 cycles) yields hi*hi (columns 0-63) and hi*lo (64-127), then A_lo x B_hi
 // (N = 64) adds the other cross term into columns 64-127.  Accumulator blocks of 128 columns rotate (kRot)
 // to bound the bias of the tensor core's truncating fp32 accumulation; the epilogue sums them.
+#include <cstdlib>
+
 #include "tapconv.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 
 namespace b200np {
@@ -91,6 +94,14 @@ struct HaloArgs {
   int nb;                  // weight ring depth
   int dbg_flags;
   long long* dbg;          // optional [gridDim.x][8] stall-cycle counters
+};
+
+// Tensor maps of the planes (TMA-fed kernel): one 4-D map per plane over its source tensor -- [channel][x][y][image],
+// for a stride-2 parity plane the view x[2j + px][2i + py] (base shifted, strides doubled) -- with a box of 32 channels
+// x HC x HR x 1 and SWIZZLE_128B, so that ONE bulk tensor copy lands a whole plane of a channel half in exactly the
+// slot layout the UMMA descriptors expect; out-of-bounds pixels arrive as zeros (= the convolution's padding).
+struct HaloTma {
+  tma::Map plane[kMaxPlanes];
 };
 
 template <bool X3>
@@ -526,6 +537,296 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// TMA-fed variant (default).  Same planes, taps, weight ring, accumulator sets and epilogue; what changes:
+//   warp  14    plane loader: per (tile, channel half) ONE cp.async.bulk.tensor per plane (HaloTma) lands the raw fp32
+//               pixels in the `hi` plane of the stage -- no global-load / address arithmetic in any thread, out-of-bounds
+//               pixels zero-filled by the copy engine;
+//   warps 0-7   split warps: shared memory -> shared memory.  They round the landed values to tf32 in place
+//               (hi = rn_tf32(x)) and, fp32-grade mode, write lo = x - hi to the `lo` plane: bit-identical operands to
+//               the register-staged kernel, at one LDS + one or two STS per 16 bytes instead of LDG + address decode +
+//               two STS (the L1 data pipe, which the tensor core's operand reads share, was 95 % busy);
+//   warp  9     MMA issuer with the tap loop unrolled (NT = 9 or 10 taps): every per-tap descriptor word is a
+//               loop-invariant uniform register, and the `weights landed` probe of tap t+1 is issued before the MMAs of
+//               tap t, so its ~90-cycle latency hides behind the issue of eight MMAs.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTmaWarp = kEpiWarp0 + 4;
+constexpr int kThreadsTma = kThreads + 32;
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+template <bool X3, int NT, int NB, bool DBG>
+__global__ void __launch_bounds__(kThreadsTma, 1) tapconv_halo_tma_kernel(const HaloArgs h, const __grid_constant__ HaloTma tm) {
+  constexpr uint32_t kBSlot = b_slot_bytes<X3>();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + h.bar_off);
+  uint64_t* a_full = bars;                  // [a_stages] split warps -> MMA          (count 256)
+  uint64_t* a_empty = bars + 2;             // [a_stages] MMA commit -> plane loader  (count 1)
+  uint64_t* acc_full = bars + 4;            // [4] MMA commit -> epilogue             (count 1)
+  uint64_t* acc_empty = bars + 8;           // [4] epilogue -> MMA                    (count 128)
+  uint64_t* b_full = bars + 12;             // [nb] bulk copy tx -> MMA               (count 1 + tx)
+  uint64_t* b_empty = b_full + kMaxBStages; // [nb] MMA commit -> weight warp         (count 1)
+  uint64_t* t_full = b_empty + kMaxBStages; // [a_stages] tensor copies tx -> split warps, MMA (count 1 + tx)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 2);
+  const int nb = h.nb, a_stages = h.a_stages;
+
+  const TapConvArgs& a = h.t;
+  const int dflags = DBG ? h.dbg_flags : 0;
+  long long* const dbgp = DBG ? h.dbg : nullptr;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t kAccCols = X3 ? 256u : 128u;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
+  constexpr uint32_t kBlkCols = X3 ? 128u : 64u;
+  const int ncls = h.ncls;
+
+  if (tid == 0) {
+    for (int s = 0; s < a_stages; ++s) {
+      mbar_init(a_full + s, kProducerThreads);
+      mbar_init(a_empty + s, 1);
+      mbar_init(t_full + s, 1);
+    }
+    for (int s = 0; s < nb; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWeightWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    for (int p = 0; p < h.nplanes; ++p) tma::prefetch_map(&tm.plane[p]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kProducerWarps) {
+    // ===================== split warps: smem -> smem =====================
+    Ring st;
+    const uint32_t units = (uint32_t)h.total_slots * 8u;      // 16-byte units of one plane copy
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x)
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(t_full + st.idx, st.phase);                  // the tensor copies of this stage have landed
+        const uint32_t hi = smem_u32(smem + st.idx * h.stage_bytes), lo = hi + h.plane_bytes;
+        for (uint32_t u0 = tid; u0 < units; u0 += 4 * kProducerThreads) {
+          float4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t u = u0 + j * kProducerThreads;
+            if (u < units) v[j] = lds128(hi + u * 16u);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t u = u0 + j * kProducerThreads;
+            if (u < units) {
+              float4 r;
+              r.x = to_tf32(v[j].x); r.y = to_tf32(v[j].y); r.z = to_tf32(v[j].z); r.w = to_tf32(v[j].w);
+              sts128(hi + u * 16u, r);
+              if (X3) {
+                float4 l;
+                l.x = lo_part(v[j].x, r.x); l.y = lo_part(v[j].y, r.y); l.z = lo_part(v[j].z, r.z); l.w = lo_part(v[j].w, r.w);
+                sts128(lo + u * 16u, l);
+              }
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(a_full + st.idx);
+        st.advance(a_stages);
+      }
+  } else if (warp == kTmaWarp) {
+    // ===================== plane loader (TMA) =====================
+    const uint32_t leader = elect_one_sync();
+    Ring st;
+    uint32_t stage_tx = 0;
+    for (int p = 0; p < h.nplanes; ++p) stage_tx += (uint32_t)(h.pl[p].HR * h.pl[p].HC) * 128u;
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
+      const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
+      const int r0 = rb * kTileRows;
+      const int n = r0 / a.OH, oy0 = r0 - n * a.OH, ox0 = xt * kTileCols;
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(a_empty + st.idx, st.phase ^ 1);             // the MMAs that read this stage have retired
+        if (leader) mbar_expect_tx(t_full + st.idx, stage_tx);
+        const uint32_t stage = smem_u32(smem + st.idx * h.stage_bytes);
+        for (int p = 0; p < h.nplanes; ++p)
+          tma::load_4d(stage + (uint32_t)h.pl[p].slot0 * 128u, &tm.plane[p], smem_u32(t_full + st.idx), half * 32,
+                       ox0 + h.pl[p].dx_min, oy0 + h.pl[p].dy_min, n, leader);
+        st.advance(a_stages);
+      }
+    }
+  } else if (warp == kWeightWarp) {
+    // ===================== weight producer =====================
+    const bool leader = elect_one_sync();
+    Ring bs;
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x)
+      for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const Tap tp = a.taps[t];
+          const float* src = h.bp[tp.src] + ((long long)half * h.nslabs[tp.src] + tp.slab) * (kBSlotBytes / 4);
+          mbar_wait(b_empty + bs.idx, bs.phase ^ 1);
+          if (leader) {
+            mbar_expect_tx(b_full + bs.idx, kBSlot);
+            bulk_g2s(smem + h.b_off + bs.idx * kBSlot, src, kBSlot, b_full + bs.idx);
+          }
+          bs.advance(nb);
+        }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer =====================
+    // Work elimination on the register-staged kernel (profiles/halo_stalls_r1.txt) showed MMAs + handshakes alone at
+    // 0.51 of 0.57 ms and the handshake skeleton WITHOUT any MMA at 8.4 K cycles per tile: the issuing lane's own
+    // ~100 instructions per K-block (constant-bank loads, R2UR moves, ring arithmetic, a 90-cycle barrier probe) do
+    // not overlap the 474 tensor cycles of the K-block, because the tensor queue is shallow.  So here everything that
+    // can be is a compile-time constant: taps and halves are unrolled, the weight ring depth NB divides the 2*NT
+    // K-blocks of a tile (slot index and phase parity of every K-block are literals), per-tap descriptor words are
+    // loop-invariant registers, the whole warp runs the loop uniformly and only tcgen05.mma / tcgen05.commit carry the
+    // elected-lane predicate (no divergent region, no R2UR), and the probe of the next weight slot is issued before
+    // the current tap's MMAs.
+    static_assert((2 * NT) % NB == 0, "ring depth must divide the K-blocks of a tile");
+    constexpr uint32_t kWraps = 2 * NT / NB;                 // ring passes per tile
+    const uint32_t leader = elect_one_sync();
+    int acc_set = 0;
+    uint32_t acc_phase = 0, cphase = 0;
+    const uint32_t plane16 = h.plane_bytes >> 4;
+    const uint32_t lbo_bits = 1u << 16;
+    const uint32_t b_hi_word = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t b_base16 = ((smem_u32(smem + h.b_off) & 0x3FFFFu) >> 4) | lbo_bits;
+    const uint32_t smem16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+    const uint32_t stage16_step = h.stage_bytes >> 4;
+    const uint32_t b_full_a = smem_u32(b_full), b_empty_a = smem_u32(b_empty);
+    constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t a_off16[NT], a_hiw[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      a_off16[t] = (uint32_t)h.tap_off[t] * 8u;
+      a_hiw[t] = (((uint32_t)h.tap_hc[t] * 128u) >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
+    }
+    auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t acc, uint32_t idesc) {
+      asm volatile(
+          "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+          "mov.b64 da, {%1, %2};\n\t"
+          "mov.b64 db, {%3, %4};\n\t"
+          "setp.ne.b32 p, %6, 0;\n\t"
+          "setp.ne.b32 q, %7, 0;\n\t"
+          "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+          ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi_word), "r"(idesc), "r"(acc), "r"(leader)
+          : "memory");
+    };
+    auto commit_a = [&](uint32_t bar_addr) {
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t"
+          "setp.ne.b32 q, %1, 0;\n\t"
+          "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+          ::"r"(bar_addr), "r"(leader)
+          : "memory");
+    };
+    auto probe = [&](uint32_t bar_addr, uint32_t parity) -> bool {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity)
+          : "memory");
+      return ok != 0;
+    };
+    bool b_ready = false;                                    // answer of the early probe of the next weight slot
+    uint32_t it = 0;                                         // tiles this CTA has processed
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x, ++it) {
+      if (ncls == 1) {
+        mbar_wait(acc_empty + acc_set, acc_phase ^ 1);       // the epilogue has drained this set
+        tc_fence_after();
+      }
+      const uint32_t d0 = tmem_base + acc_set * kAccCols;
+      const uint32_t ring_par0 = it * kWraps;                // ring passes completed before this tile
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t sidx = a_stages == 2 ? (uint32_t)half : 0u;
+        const uint32_t spar = a_stages == 2 ? (it & 1u) : ((2u * it + half) & 1u);
+        mbar_wait(t_full + sidx, spar);                      // hi plane landed (async proxy) ...
+        mbar_wait(a_full + sidx, spar);                      // ... and was rounded / split by the split warps
+        const uint32_t stage16 = (smem16 + sidx * stage16_step) | lbo_bits;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          constexpr int dummy = 0; (void)dummy;
+          const int kb = half * NT + t;                      // literal after unrolling
+          const uint32_t slot = (uint32_t)(kb % NB), pass = (uint32_t)(kb / NB);
+          const uint32_t kbn = (uint32_t)((kb + 1) % (2 * NT));
+          const uint32_t slot_n = kbn % NB, pass_n = kbn / NB + (kb + 1 == 2 * NT ? kWraps : 0u);
+          if (!b_ready) mbar_wait(b_full + slot, (ring_par0 + pass) & 1u);
+          b_ready = probe(b_full_a + slot_n * 8u, (ring_par0 + pass_n) & 1u);   // next slot: answer used after these MMAs
+          const uint32_t ah = stage16 + a_off16[t], al = ah + plane16;
+          const uint32_t bh = b_base16 + slot * (kBSlot >> 4);
+          uint32_t d_blk = d0 + (uint32_t)(kb % kRot) * kBlkCols;
+          uint32_t acc_first = kb >= kRot;
+          int cls = 0;
+          bool cls_last = false;
+          if (ncls > 1) {
+            cls = h.tap_cls[t];
+            const bool cls_first = t == 0 || h.tap_cls[t > 0 ? t - 1 : 0] != cls;
+            cls_last = t == NT - 1 || h.tap_cls[t < NT - 1 ? t + 1 : t] != cls;
+            if (half == 0 && cls_first) {                    // the epilogue has drained this class of the previous tile
+              mbar_wait(acc_empty + cls, cphase ^ 1);
+              tc_fence_after();
+            }
+            d_blk = tmem_base + cls * kBlkCols;
+            acc_first = !(half == 0 && cls_first);
+          }
+          if (X3) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hiw[t], bh + 2 * k, k == 0 ? acc_first : 1u, kIdescN128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma(d_blk + 64, al + 2 * k, a_hiw[t], bh + 2 * k, 1u, kIdescTf32_128x64);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hiw[t], bh + 2 * k, k == 0 ? acc_first : 1u, kIdescTf32_128x64);
+          }
+          commit_a(b_empty_a + slot * 8u);
+          if (ncls > 1 && half == 1 && cls_last) umma_commit(acc_full + cls, leader);   // class complete
+        }
+        umma_commit(a_empty + sidx, leader);
+      }
+      if (ncls == 1) {
+        umma_commit(acc_full + acc_set, leader);
+        if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
+      } else {
+        cphase ^= 1;
+      }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+    halo_epilogue<X3, DBG>(h, acc_full, acc_empty, tmem_base, warp, lane, dflags, dbgp);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWeightWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <bool X3, int NT, int NB>
+int launch_halo_tma_t(const HaloArgs& h, const HaloTma& tm, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(tapconv_halo_tma_kernel<X3, NT, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+      return B200NP_E_LAUNCH;
+    configured = smem;
+  }
+  int grid = h.tiles_total < kNumSMs ? h.tiles_total : kNumSMs;
+  tapconv_halo_tma_kernel<X3, NT, NB, false><<<grid, kThreadsTma, smem, st>>>(h, tm);
+  return launch_status();
+}
+
 template <bool X3, int MAXT>
 int launch_halo_t(const HaloArgs& h, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
@@ -541,6 +842,35 @@ int launch_halo_t(const HaloArgs& h, size_t smem, cudaStream_t st) {
   if (h.dbg || h.dbg_flags) tapconv_halo_kernel<X3, MAXT, true><<<grid, kThreads, smem, st>>>(h);
   else tapconv_halo_kernel<X3, MAXT, false><<<grid, kThreads, smem, st>>>(h);
   return launch_status();
+}
+
+// B200NP_HALO_TMA=0 keeps the register-staged kernel (the TMA-fed one is the default where its tensor maps can be built)
+static bool halo_tma_enabled() {
+  static const bool on = [] { const char* e = getenv("B200NP_HALO_TMA"); return e ? e[0] != '0' : true; }();
+  return on;
+}
+
+// One tensor map per plane (see HaloTma).  false: some plane cannot be expressed (odd extent under a stride-2 view,
+// driver without tensor-map support) -- the caller falls back to the register-staged kernel.
+static bool build_plane_maps(const HaloArgs& h, HaloTma& tm) {
+  for (int p = 0; p < h.nplanes; ++p) {
+    const Plane& P = h.pl[p];
+    const uint64_t W = (uint64_t)P.srcW, H = (uint64_t)P.srcH, N = (uint64_t)h.t.N;
+    const float* base = P.src;
+    uint64_t dims[4] = {64, W, H, N};
+    uint64_t strides[3] = {256, W * 256, H * W * 256};
+    if (P.scale == 2) {
+      if ((W | H) & 1) return false;
+      base += ((long long)P.py * P.srcW + P.px) * 64;
+      dims[1] = W / 2; dims[2] = H / 2;
+      strides[0] = 512; strides[1] = 2 * W * 256;
+    } else if (P.scale != 1) {
+      return false;
+    }
+    const uint32_t box[4] = {32, (uint32_t)P.HC, (uint32_t)P.HR, 1};
+    if (!tma::encode_f32_4d(&tm.plane[p], base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+  }
+  return true;
 }
 
 template <bool X3>
@@ -560,6 +890,18 @@ int launch_halo(HaloArgs& h, cudaStream_t st) {
   h.bar_off = h.b_off + nb * bslot;
   const size_t smem = h.bar_off + tail;
   const int tasks = (h.total_slots + kSlotsPerPass - 1) / kSlotsPerPass;
+  if (halo_tma_enabled() && !h.dbg && !h.dbg_flags && (h.t.ntaps == 9 || h.t.ntaps == 10)) {
+    // the TMA-fed kernel wants a weight ring whose depth divides the 2 * ntaps K-blocks of a tile (compile-time slots)
+    const int want = h.t.ntaps == 10 ? 4 : (nb >= 6 ? 6 : 3);
+    HaloTma tm;
+    if (nb >= want && build_plane_maps(h, tm)) {
+      h.nb = want;
+      h.bar_off = h.b_off + want * bslot;
+      const size_t smem_t = h.bar_off + tail;
+      if (h.t.ntaps == 10) return launch_halo_tma_t<X3, 10, 4>(h, tm, smem_t, st);
+      return want == 6 ? launch_halo_tma_t<X3, 9, 6>(h, tm, smem_t, st) : launch_halo_tma_t<X3, 9, 3>(h, tm, smem_t, st);
+    }
+  }
   if (tasks <= 10) return launch_halo_t<X3, 10>(h, smem, st);
   if (tasks <= 18) return launch_halo_t<X3, 18>(h, smem, st);
   return B200NP_E_UNSUPPORTED;

@@ -20,7 +20,10 @@
 // kernel's, so the same reduction follows.  Role 0 also sums dY for the bias gradient.
 // Measured as a prototype (tools/probe/wgrad_halo_proto.cu, 12 tap-products): 0.69 ms against 0.80 ms for the 9 taps +
 // reduction of the gather kernel at 1140 images.
+#include <cstdlib>
+
 #include "tapconv.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 
 namespace b200np {
@@ -248,6 +251,274 @@ __global__ void __launch_bounds__(kThreads, 1) tapwgrad_halo_kernel(const HaloWg
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// TMA-fed, warp-specialised variant (default).  Same planes, descriptors, roles, accumulators and partial layout as
+// tapwgrad_halo_kernel; what changes is who moves the data and who waits for whom:
+//   warp 8      loader: per tile one cp.async.bulk.tensor per (row, 32-channel block) of the x halo, the skip rows and
+//               the dY tile drops the raw fp32 pixels into the `hi` regions of a stage (4-D maps [channel][x][y][image],
+//               box 32 x pixels x 1 x 1, SWIZZLE_128B_ATOM_32B = the MN-major operand swizzle; image borders arrive as
+//               zeros) -- no global load, no address arithmetic in any thread;
+//   warps 0-7   split warps, shared memory -> shared memory: hi = rn_tf32(x) in place, lo = x - hi to the `lo` region
+//               (the same operand bits as the register-staged kernel), and the dY column sums for the bias gradient;
+//   warp 9      MMA issuer only: full/empty mbarriers hand stages over, so the tensor core works on tile i while the
+//               loader and the split warps prepare tile i+1 (in the block-synchronous kernel warp 0 issued a tile's 48
+//               MMAs and then helped stage the next one: T_tile = T_issue + T_store).
+// ------------------------------------------------------------------------------------------------------------
+struct HaloWgradTma {
+  tma::Map x;     // [64][W][H][N]  box 32 x 18 x 1 x 1
+  tma::Map dy;    // [64][W][H][N]  box 32 x 16 x 1 x 1
+  tma::Map xs;    // parity-(0,0) view of the skip source [64][W][H][N] (strides doubled), box 32 x 16 x 1 x 1
+};
+constexpr int kSplitThreads = 256, kLoadWarp = 8, kIssueWarp = 9, kThreadsTma = 320;
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void mbar_arrive_(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+template <bool X3, int ROLE>
+__device__ __forceinline__ void run_role_tma(const HaloWgradArgs& a, const HaloWgradTma& tm, uint8_t* smem, uint64_t* bars,
+                                             uint32_t tmem) {
+  constexpr int XT = ROLE == 0 ? XT0 : XT1;
+  constexpr uint32_t A_PLANE = ROLE == 0 ? A0_PLANE : A1_PLANE;
+  constexpr uint32_t ROW_A = ROLE == 0 ? 2 * S_A : 4 * S_A;
+  uint64_t* t_full = bars;        // [2] tensor copies landed              (count 1 + tx)
+  uint64_t* s_full = bars + 2;    // [2] split warps done                  (count 256)
+  uint64_t* s_empty = bars + 4;   // [2] the MMAs that read the stage retired (tcgen05.commit)
+  uint64_t* done = bars + 6;      // all MMAs of the chunk retired
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x;
+  const int H = a.H, W = a.W;
+  const int tiles_x = W / TW, tiles_img = tiles_x * (H / RT);
+  const long long t_begin = chunk * a.per, t_end = t_begin + a.per < a.tiles ? t_begin + a.per : a.tiles;
+  float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if (ROLE == 1) {
+    // columns 0 and 17 of the skip blocks are never written; the unused second halves of the dx = -1 / +1 pairs read
+    // them, so they must not hold NaN / Inf garbage: zero both stages once (before any tensor copy is issued)
+    for (uint32_t o = tid * 16; o < 2 * STAGE; o += kThreadsTma * 16) *reinterpret_cast<float4*>(smem + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();
+    __syncthreads();
+  }
+
+  if (warp == kLoadWarp) {
+    // ===================== loader =====================
+    const uint32_t leader = elect_one_sync();
+    const bool skip = ROLE == 1 && a.xs != nullptr;
+    const uint32_t kTx = ROLE == 0 ? ((RT + 1) * 2 * HW + RT * 2 * TW) * 128u
+                                   : (RT * 2 * HW + RT * 2 * TW + (skip ? RT * 2 * TW : 0)) * 128u;
+    long long it = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int s = (int)(it & 1);
+      const int n = (int)(tile / tiles_img), rem = (int)(tile - (long long)n * tiles_img);
+      const int oy0 = (rem / tiles_x) * RT, ox0 = (rem % tiles_x) * TW;
+      if (it >= 2) mbar_wait(s_empty + s, (uint32_t)(((it >> 1) - 1) & 1));
+      if (leader) mbar_expect_tx_(t_full + s, kTx);
+      const uint32_t st = smem_u32(smem + s * STAGE), bar = smem_u32(t_full + s);
+      const uint32_t b0 = st + 2 * A_PLANE;
+      if (ROLE == 0) {
+#pragma unroll
+        for (int hr = 0; hr <= RT; ++hr)
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb)
+            tma::load_4d(st + (uint32_t)(hr * 2 + cb) * S_A, &tm.x, bar, cb * 32, ox0 - 1, oy0 + hr - 1, n, leader);
+      } else {
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb) {
+            tma::load_4d(st + (uint32_t)(r * 4 + cb) * S_A, &tm.x, bar, cb * 32, ox0 - 1, oy0 + r + 1, n, leader);
+            // skip pixel k sits at column k + 1 of its block (the dx = 0 pair, start column 1, reads it)
+            tma::load_4d(st + (uint32_t)(r * 4 + 2 + cb) * S_A + 128u, &tm.xs, bar, cb * 32, ox0, oy0 + r, n, skip ? leader : 0u);
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb)
+          tma::load_4d(b0 + (uint32_t)(r * 4 + cb) * S_B, &tm.dy, bar, cb * 32, ox0, oy0 + r, n, leader);
+    }
+  } else if (warp == kIssueWarp) {
+    // ===================== MMA issuer =====================
+    const uint32_t leader = elect_one_sync();
+    long long it = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int s = (int)(it & 1);
+      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      mbar_wait(t_full + s, par);
+      mbar_wait(s_full + s, par);
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(smem + s * STAGE), a_lo = a_hi + A_PLANE, b0 = a_hi + 2 * A_PLANE;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const uint64_t bd = mn_desc(b0 + r * 4 * S_B + hf * 8 * 128, S_B);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {   // dx = j - 1: the (halo) column of output pixel k is hf*8 + k + j
+            const uint32_t aoff = r * ROW_A + (hf * 8 + j) * 128;
+            const uint32_t d = tmem + j * 128;
+            const uint32_t acc = (it == 0 && r == 0 && hf == 0) ? 0u : 1u;
+            if (X3) {
+              umma_tf32(d, mn_desc(a_hi + aoff, S_A), bd, kIdesc128x128, acc, leader);
+              umma_tf32(d + 64, mn_desc(a_lo + aoff, S_A), bd, kIdesc128x64, 1u, leader);
+            } else {
+              umma_tf32(d, mn_desc(a_hi + aoff, S_A), bd, kIdesc128x64, acc, leader);
+            }
+          }
+        }
+      }
+      umma_commit(s_empty + s, leader);
+      if (tile + 1 == t_end) umma_commit(done, leader);
+    }
+  } else {
+    // ===================== split warps: smem -> smem =====================
+    const int c16 = tid & 15, cb = c16 >> 3, ch = c16 & 7;
+    long long it = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int s = (int)(it & 1);
+      mbar_wait(t_full + s, (uint32_t)((it >> 1) & 1));
+      const uint32_t a_hi = smem_u32(smem + s * STAGE), a_lo = a_hi + A_PLANE, b = a_hi + 2 * A_PLANE;
+      uint32_t xo[XT];
+      float4 xv[XT], yv[YT];
+#pragma unroll
+      for (int i = 0; i < XT; ++i) {
+        const int px = (tid + i * kSplitThreads) >> 4;
+        xo[i] = 0xffffffffu;
+        if (ROLE == 0) {
+          const int hr = px / HW, pc = px - hr * HW;
+          if (px < (RT + 1) * HW) xo[i] = swz((uint32_t)(hr * 2 + cb) * S_A + pc * 128, ch);
+        } else if (px < RT * HW) {
+          const int r = px / HW, pc = px - r * HW;
+          xo[i] = swz((uint32_t)(r * 4 + cb) * S_A + pc * 128, ch);
+        } else if (px < RT * (HW + TW)) {
+          const int q = px - RT * HW, r = q / TW, k = q - r * TW;
+          xo[i] = swz((uint32_t)(r * 4 + 2 + cb) * S_A + (k + 1) * 128, ch);
+        }
+        if (xo[i] != 0xffffffffu) xv[i] = lds128(a_hi + xo[i]);
+      }
+      uint32_t yo[YT];
+#pragma unroll
+      for (int i = 0; i < YT; ++i) {
+        const int px = (tid + i * kSplitThreads) >> 4;
+        const int r = px / TW, pc = px - r * TW;
+        yo[i] = swz((uint32_t)(r * 4 + cb) * S_B + pc * 128, ch);
+        yv[i] = lds128(b + yo[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < XT; ++i)
+        if (xo[i] != 0xffffffffu) split_store(smem + s * STAGE, smem + s * STAGE + A_PLANE, xo[i], xv[i], X3);
+#pragma unroll
+      for (int i = 0; i < YT; ++i) {
+        split_store(smem + s * STAGE + 2 * A_PLANE, smem + s * STAGE + 2 * A_PLANE + 2 * S_B, yo[i], yv[i], X3);
+        if (ROLE == 0) { dbs.x += yv[i].x; dbs.y += yv[i].y; dbs.z += yv[i].z; dbs.w += yv[i].w; }
+      }
+      fence_proxy_async();
+      mbar_arrive_(s_full + s);
+    }
+  }
+  // every chunk has at least one tile (the host sizes `per` that way)
+  mbar_wait(done, 0);
+  tc_fence_after();
+  __syncthreads();
+  if (ROLE == 0 && a.part_db) {   // all MMAs have retired: the stages are free for the 16-row reduction of the dY sums
+    float* red = reinterpret_cast<float*>(smem);
+    if (tid < kSplitThreads) *reinterpret_cast<float4*>(red + (tid >> 4) * 64 + (tid & 15) * 4) = dbs;
+    __syncthreads();
+    if (tid < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t += red[r * 64 + tid];
+      a.part_db[(long long)chunk * 64 + tid] = t;
+    }
+  }
+  if (warp >= 8) return;
+  // rows m = 32 q + lane = half_tap * 64 + ci; warps w and w + 4 share lane quarter q = w % 4 and take 32 co each
+  const int q = warp & 3, half = warp >> 2, second = q >> 1, ci = (q & 1) * 32 + lane;
+#pragma unroll 1
+  for (int j = 0; j < 3; ++j) {
+    int tap;
+    if (ROLE == 0) tap = second * 3 + j;                                // (dy = -1 | 0, dx = j - 1)
+    else tap = second ? ((j == 1 && a.ntaps > 9) ? 9 : -1) : 6 + j;     // (dy = +1, dx = j - 1) | the skip tap
+    uint32_t r0[32], r1[32];
+    const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + j * 128 + half * 32;
+    tmem_ld32(ta, r0);
+    if (X3) tmem_ld32(ta + 64, r1);
+    if (tap >= 0) {
+      float* po = a.part + ((long long)chunk * a.ntaps + tap) * 64 * 64 + ci;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        po[(half * 32 + i) * 64] = (X3 ? __uint_as_float(r1[i]) : 0.f) + __uint_as_float(r0[i]);
+    }
+  }
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(kThreadsTma, 1) tapwgrad_halo_tma_kernel(const HaloWgradArgs a,
+                                                                            const __grid_constant__ HaloWgradTma tm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(bars + s, 1); mbar_init(bars + 2 + s, kSplitThreads); mbar_init(bars + 4 + s, 1); }
+    mbar_init(bars + 6, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (blockIdx.y == 0) run_role_tma<X3, 0>(a, tm, smem, bars, tmem);
+  else run_role_tma<X3, 1>(a, tm, smem, bars, tmem);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+static bool wgrad_tma_enabled() {
+  static const bool on = [] { const char* e = getenv("B200NP_WGRAD_TMA"); return e ? e[0] != '0' : true; }();
+  return on;
+}
+
+template <bool X3>
+int launch_tma(const HaloWgradArgs& h, int chunks, cudaStream_t st) {
+  HaloWgradTma tm;
+  const uint64_t W = (uint64_t)h.W, H = (uint64_t)h.H, N = (uint64_t)h.N;
+  const uint64_t dims[4] = {64, W, H, N};
+  const uint64_t strides[3] = {256, W * 256, H * W * 256};
+  const uint32_t box_x[4] = {32, HW, 1, 1}, box_y[4] = {32, TW, 1, 1};
+  if (!tma::encode_f32_4d(&tm.x, h.x, dims, strides, box_x, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return B200NP_E_UNSUPPORTED;
+  if (!tma::encode_f32_4d(&tm.dy, h.dy, dims, strides, box_y, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return B200NP_E_UNSUPPORTED;
+  if (h.xs) {   // xs[2 y][2 x]: the parity-(0,0) view of [N, 2H, 2W, 64]
+    const uint64_t s2[3] = {512, 2 * (2 * W) * 256, (2 * H) * (2 * W) * 256};
+    if (!tma::encode_f32_4d(&tm.xs, h.xs, dims, s2, box_y, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return B200NP_E_UNSUPPORTED;
+  } else {
+    tm.xs = tm.dy;   // never dereferenced meaningfully: role 1 then multiplies the zeroed skip blocks
+  }
+  const size_t smem = 2 * STAGE + 1024 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tapwgrad_halo_tma_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return B200NP_E_LAUNCH;
+    configured = true;
+  }
+  tapwgrad_halo_tma_kernel<X3><<<dim3(chunks, 2), kThreadsTma, smem, st>>>(h, tm);
+  return launch_status();
+}
+
 template <bool X3>
 int launch(const HaloWgradArgs& h, int chunks, cudaStream_t st) {
   const size_t smem = 2 * STAGE + 1024 + 1024;
@@ -288,6 +559,10 @@ int launch_tapwgrad_halo(TapWgradArgs& a, int precision, cudaStream_t st) {
   h.tiles = (long long)a.N * (a.OH / RT) * (a.OW / TW);
   h.per = ceil_div(h.tiles, kNumSMs);
   a.chunks = chunks;
+  if (wgrad_tma_enabled()) {
+    const int rc = precision == B200NP_PREC_TF32 ? launch_tma<false>(h, chunks, st) : launch_tma<true>(h, chunks, st);
+    if (rc != B200NP_E_UNSUPPORTED) return rc;
+  }
   return precision == B200NP_PREC_TF32 ? launch<false>(h, chunks, st) : launch<true>(h, chunks, st);
 }
 
