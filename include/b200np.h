@@ -286,6 +286,33 @@ int b200np_adam_step_dev(float* p, const float* g, float* m, float* v, long long
                          void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * MMAML conv nets: GatedConvModel (networks/gated_conv_net.py:167-212: 3x3 stride-2 conv ->
+ * batch-statistics BatchNorm, training=True always -> FiLM x*(1+gamma)+beta (:154-159) -> ReLU) and
+ * ConvEmbeddingModel (networks/conv_embedding_model.py:99-184, affine BatchNorm), any channel count.
+ *
+ * The convolution is im2col + b200np_gemm: col[m][ci*9 + r*3 + s] = x[n, 2oy+r-1, 2ox+s-1, ci] uses the flattening
+ * of torch's [Cout, Cin, 3, 3] weight, so forward (col x W^T), weight gradient (dY^T x col) and data gradient
+ * (dY x W, then col2im) read the parameter tensor as it is.  x NHWC [N,H,W,C], H and W even.
+ * col2im gathers (deterministic); `mask` (nullable, dx geometry) gates the result with (mask > 0).
+ *
+ * bn_act: per channel over all `rows` = N*H*W rows of x [rows, C]: mean, biased variance (Welford, two-level,
+ * deterministic), y = relu?((x - mean) * rstd * (scale + plus_one) + shift); scale / shift nullable ([C]).  FiLM passes
+ * scale = gamma, plus_one = 1, shift = beta; affine BatchNorm scale = weight, plus_one = 0, shift = bias.  mean / rstd
+ * are saved for the backward; run_mean / run_var (nullable) get F.batch_norm's running update (unbiased variance).
+ * Backward: dshift = sum g, dscale = sum g * xhat (g = dy gated by y > 0 when relu), dx = the usual batch-norm data
+ * gradient.  Workspace: b200np_bn_workspace(rows, C) bytes.
+ * ------------------------------------------------------------------------------------------ */
+int b200np_im2col3x3s2(const float* x, float* col, int N, int H, int W, int C, void* stream);
+int b200np_col2im3x3s2(const float* dcol, const float* mask, float* dx, int N, int H, int W, int C, void* stream);
+size_t b200np_bn_workspace(long long rows, int C);
+int b200np_bn_act_fwd(const float* x, const float* scale, const float* shift, float plus_one, float eps, float* y,
+                      float* mean, float* rstd, float* run_mean, float* run_var, float momentum, long long rows, int C,
+                      int relu, void* ws, size_t ws_bytes, void* stream);
+int b200np_bn_act_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
+                      const float* scale, float plus_one, float* dx, float* dscale, float* dshift, long long rows, int C,
+                      int relu, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Diagnostics (tools/ only; never called on the product path).  They switch global state of the
  * library and are NOT thread-safe.
  *   b200np_debug_set_wgrad_waves   pixel chunks per weight-gradient launch = waves * resident CTAs

@@ -69,6 +69,11 @@ SIGNATURES = {
     "b200np_loss_fwd_bwd": (_i, [_p, _p, _p, _p, _ll, _i, _i, _i, _p]),
     "b200np_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
     "b200np_adam_step_dev": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _f, _p]),
+    "b200np_im2col3x3s2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "b200np_col2im3x3s2": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "b200np_bn_workspace": (_sz, [_ll, _i]),
+    "b200np_bn_act_fwd": (_i, [_p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _f, _ll, _i, _i, _p, _sz, _p]),
+    "b200np_bn_act_bwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _ll, _i, _i, _p, _sz, _p]),
     "b200np_debug_set_wgrad_waves": (None, [_i]),
     "b200np_debug_set_halo_flags": (None, [_i]),
     "b200np_debug_set_halo_min_taps": (None, [_i]),

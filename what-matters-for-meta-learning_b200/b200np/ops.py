@@ -371,3 +371,53 @@ def adam_step(p, g, m, v, n, lr, b1, b2, eps, wd, step, grad_scale=1.0):
 def adam_step_dev(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, grad_scale=1.0):
     check(LIB.b200np_adam_step_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, _ptr(step_dev),
                                    grad_scale, _stream()), "adam_step_dev")
+
+
+# ----------------------------------------------------------------------------------------------
+# MMAML conv nets: im2col / col2im for 3x3 stride-2 convs, batch-stat norm + scale/shift + ReLU
+# ----------------------------------------------------------------------------------------------
+def im2col3x3s2(x):
+    """x NHWC [N,H,W,C] -> col [N*(H/2)*(W/2), C*9] with k = ci*9 + r*3 + s (torch's weight flattening)."""
+    _chk(x, "x")
+    N, H, W, Cc = x.shape
+    col = empty((N * (H // 2) * (W // 2), Cc * 9), x)
+    check(LIB.b200np_im2col3x3s2(_ptr(x), _ptr(col), N, H, W, Cc, _stream()), "im2col3x3s2")
+    return col
+
+
+def col2im3x3s2(dcol, x_shape, mask=None):
+    _chk(dcol, "dcol"), _chk(mask, "mask")
+    N, H, W, Cc = x_shape
+    dx = empty(tuple(x_shape), dcol)
+    check(LIB.b200np_col2im3x3s2(_ptr(dcol), _ptr(mask), _ptr(dx), N, H, W, Cc, _stream()), "col2im3x3s2")
+    return dx
+
+
+def bn_act_fwd(x, scale, shift, plus_one, relu=True, eps=1e-5, run_mean=None, run_var=None, momentum=0.1):
+    """x [..., C] (rows = everything but the last dim) -> (y, mean [C], rstd [C])."""
+    _chk(x, "x"), _chk(scale, "scale"), _chk(shift, "shift")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    y = torch.empty_like(x)
+    mean, rstd = empty((Cc,), x), empty((Cc,), x)
+    ws_bytes = LIB.b200np_bn_workspace(rows, Cc)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=x.device, dtype=F32)
+    check(LIB.b200np_bn_act_fwd(_ptr(x), _ptr(scale), _ptr(shift), float(plus_one), float(eps), _ptr(y), _ptr(mean),
+                                _ptr(rstd), _ptr(run_mean), _ptr(run_var), float(momentum), rows, Cc, int(relu),
+                                _ptr(ws), ws_bytes, _stream()), "bn_act_fwd")
+    return y, mean, rstd
+
+
+def bn_act_bwd(dy, y, x, mean, rstd, scale, plus_one, relu=True):
+    """-> (dx, dscale [C], dshift [C])."""
+    _chk(dy, "dy")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    dx = torch.empty_like(x)
+    dscale, dshift = empty((Cc,), x), empty((Cc,), x)
+    ws_bytes = LIB.b200np_bn_workspace(rows, Cc)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=x.device, dtype=F32)
+    check(LIB.b200np_bn_act_bwd(_ptr(dy), _ptr(y), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(scale), float(plus_one), _ptr(dx),
+                                _ptr(dscale), _ptr(dshift), rows, Cc, int(relu), _ptr(ws), ws_bytes, _stream()),
+          "bn_act_bwd")
+    return dx, dscale, dshift

@@ -1,0 +1,265 @@
+// Building blocks of the MMAML conv nets: networks/gated_conv_net.py:167-212 (GatedConvModel:
+// 3x3 stride-2 conv -> batch-statistics BatchNorm (training=True always, no affine) -> FiLM x*(1+gamma)+beta -> ReLU,
+// 32/64/128/256 channels) and networks/conv_embedding_model.py:99-184 (same stack with affine BatchNorm).
+//
+//   * im2col / col2im for 3x3 stride-2 pad-1 convolutions on NHWC tensors with the column order k = ci*9 + tap, i.e.
+//     the flattening of torch's [Cout, Cin, 3, 3] weight: forward, weight gradient and data gradient are then plain
+//     strided GEMMs on the tcgen05 kernel (b200np_gemm) reading the parameter tensors as they are -- any channel count;
+//   * batch statistics per channel over all N*H*W rows (two-level, deterministic; Welford merge, so no E[x^2]-E[x]^2
+//     cancellation), the fused normalise + scale/shift + ReLU, and its backward (two more column reductions + one
+//     elementwise pass).  scale/shift cover both users: FiLM (scale = 1 + gamma, shift = beta) and affine BatchNorm
+//     (scale = weight, shift = bias).
+#include "common.cuh"
+
+namespace b200np {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// im2col: x [N, H, W, C] -> col [N*OH*OW, C*9], col[m][ci*9 + r*3 + s] = x[n, 2*oy + r - 1, 2*ox + s - 1, ci]
+// thread = (pixel m, channel ci): 9 loads coalesced over ci, 36 contiguous bytes stored.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void im2col3x3s2_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2;
+  const long long total = (long long)N * OH * OW * C;
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += st) {
+    const int ci = (int)(i % C);
+    const long long m = i / C;
+    const int ox = (int)(m % OW);
+    const long long q = m / OW;
+    const int oy = (int)(q % OH), n = (int)(q / OH);
+    float v[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iy = 2 * oy + r - 1, ix = 2 * ox + s - 1;
+        v[r * 3 + s] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((long long)n * H + iy) * W + ix) * C + ci) : 0.f;
+      }
+    float* o = col + (m * C + ci) * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) o[t] = v[t];
+  }
+}
+// col2im (gather form, deterministic): dx[n, y, x, ci] = sum over the taps (r, s) and outputs (oy, ox) with
+// 2*oy + r - 1 == y, 2*ox + s - 1 == x of dcol[m(n, oy, ox)][ci*9 + r*3 + s]; optional gate (mask > 0).
+__global__ void col2im3x3s2_kernel(const float* __restrict__ dcol, const float* __restrict__ mask, float* __restrict__ dx,
+                                   int N, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2;
+  const long long total = (long long)N * H * W * C;
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += st) {
+    const int ci = (int)(i % C);
+    const long long p = i / C;
+    const int xx = (int)(p % W);
+    const long long q = p / W;
+    const int yy = (int)(q % H), n = (int)(q / H);
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ty = yy + 1 - r;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= OH) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int tx = xx + 1 - s;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= OW) continue;
+        acc += __ldg(dcol + ((((long long)n * OH + oy) * OW + ox) * C + ci) * 9 + r * 3 + s);
+      }
+    }
+    if (mask && !(__ldg(mask + i) > 0.f)) acc = 0.f;
+    dx[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column statistics of a [R, C] matrix.  Level 1: block (32 channels x 8 row lanes) over a row slice -> (count, mean,
+// M2) per channel, merged across the 8 lanes in shared memory; level 2: one thread per channel merges the slices in
+// order (Chan et al.), writes mean / rstd and updates the running statistics like F.batch_norm(training=True) does.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStatLanes = 8;
+__global__ void __launch_bounds__(256) bn_stats_l1_kernel(const float* __restrict__ x, float* __restrict__ part, long long R,
+                                                          int C, long long rows_per_slice) {
+  __shared__ float s_n[kStatLanes][32], s_m[kStatLanes][32], s_q[kStatLanes][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const long long r0 = (long long)blockIdx.y * rows_per_slice;
+  const long long r1 = r0 + rows_per_slice < R ? r0 + rows_per_slice : R;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  if (c < C)
+    for (long long r = r0 + rl; r < r1; r += kStatLanes) {
+      const float v = __ldg(x + r * C + c);
+      n += 1.f;
+      const float d = v - mean;
+      mean += d / n;
+      m2 = fmaf(d, v - mean, m2);
+    }
+  s_n[rl][cl] = n; s_m[rl][cl] = mean; s_q[rl][cl] = m2;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float N0 = s_n[0][cl], M0 = s_m[0][cl], Q0 = s_q[0][cl];
+#pragma unroll
+    for (int k = 1; k < kStatLanes; ++k) {
+      const float nb = s_n[k][cl];
+      if (nb > 0.f) {
+        const float tot = N0 + nb, d = s_m[k][cl] - M0;
+        M0 += d * (nb / tot);
+        Q0 += s_q[k][cl] + d * d * (N0 * nb / tot);
+        N0 = tot;
+      }
+    }
+    float* o = part + ((long long)blockIdx.y * C + c) * 3;
+    o[0] = N0; o[1] = M0; o[2] = Q0;
+  }
+}
+__global__ void bn_stats_l2_kernel(const float* __restrict__ part, int slices, int C, float eps, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ run_mean, float* __restrict__ run_var,
+                                   float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float N0 = 0.f, M0 = 0.f, Q0 = 0.f;
+  for (int s = 0; s < slices; ++s) {
+    const float* p = part + ((long long)s * C + c) * 3;
+    const float nb = p[0];
+    if (nb > 0.f) {
+      const float tot = N0 + nb, d = p[1] - M0;
+      M0 += d * (nb / tot);
+      Q0 += p[2] + d * d * (N0 * nb / tot);
+      N0 = tot;
+    }
+  }
+  const float var = Q0 / N0;   // biased, as used for normalisation
+  mean[c] = M0;
+  rstd[c] = rsqrtf(var + eps);
+  if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * M0;
+  if (run_var) run_var[c] = (1.f - momentum) * run_var[c] + momentum * (N0 > 1.f ? Q0 / (N0 - 1.f) : var);
+}
+
+// y = relu?( (x - mean) * rstd * scale' + shift ),  scale' = scale + plus_one  (FiLM: 1 + gamma)
+__global__ void bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                  const float* __restrict__ scale, const float* __restrict__ shift, float plus_one,
+                                  float* __restrict__ y, long long total, int C, int relu) {
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += st) {
+    const int c = (int)(i % C);
+    const float sc = (scale ? __ldg(scale + c) : 0.f) + plus_one;
+    float v = (__ldg(x + i) - __ldg(mean + c)) * __ldg(rstd + c) * sc + (shift ? __ldg(shift + c) : 0.f);
+    y[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+// backward, level 1: per slice and channel  sum g  and  sum g * xhat,  g = dy * (y > 0 | !relu)
+__global__ void __launch_bounds__(256) bn_act_bwd_l1_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                            const float* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ part,
+                                                            long long R, int C, long long rows_per_slice, int relu) {
+  __shared__ float s_a[kStatLanes][32], s_b[kStatLanes][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const long long r0 = (long long)blockIdx.y * rows_per_slice;
+  const long long r1 = r0 + rows_per_slice < R ? r0 + rows_per_slice : R;
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+    for (long long r = r0 + rl; r < r1; r += kStatLanes) {
+      const long long i = r * C + c;
+      float g = __ldg(dy + i);
+      if (relu && !(__ldg(y + i) > 0.f)) g = 0.f;
+      a += g;
+      b = fmaf(g, (__ldg(x + i) - mu) * rs, b);
+    }
+  }
+  s_a[rl][cl] = a; s_b[rl][cl] = b;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < kStatLanes; ++k) { a += s_a[k][cl]; b += s_b[k][cl]; }
+    float* o = part + ((long long)blockIdx.y * C + c) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+__global__ void bn_act_bwd_l2_kernel(const float* __restrict__ part, int slices, int C, float* __restrict__ dshift,
+                                     float* __restrict__ dscale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int s = 0; s < slices; ++s) { a += part[((long long)s * C + c) * 2]; b += part[((long long)s * C + c) * 2 + 1]; }
+  dshift[c] = a;
+  dscale[c] = b;
+}
+// dx = rstd * sc * ( g - mean_r(g) - xhat * mean_r(g * xhat) ),  sc = scale + plus_one
+__global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
+                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                        const float* __restrict__ scale, float plus_one, const float* __restrict__ dshift,
+                                        const float* __restrict__ dscale, float* __restrict__ dx, long long total, int C,
+                                        float inv_rows, int relu) {
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += st) {
+    const int c = (int)(i % C);
+    float g = __ldg(dy + i);
+    if (relu && !(__ldg(y + i) > 0.f)) g = 0.f;
+    const float rs = __ldg(rstd + c);
+    const float xh = (__ldg(x + i) - __ldg(mean + c)) * rs;
+    const float sc = (scale ? __ldg(scale + c) : 0.f) + plus_one;
+    dx[i] = rs * sc * (g - __ldg(dshift + c) * inv_rows - xh * __ldg(dscale + c) * inv_rows);
+  }
+}
+
+int stat_slices(long long R) {
+  long long s = ceil_div(R, 512);
+  if (s > 4 * kNumSMs) s = 4 * kNumSMs;
+  return (int)(s < 1 ? 1 : s);
+}
+
+}  // namespace
+}  // namespace b200np
+
+using namespace b200np;
+
+extern "C" int b200np_im2col3x3s2(const float* x, float* col, int N, int H, int W, int C, void* stream) {
+  if (!x || !col || N <= 0 || C <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1)) return B200NP_E_BADARG;
+  const long long total = (long long)N * (H / 2) * (W / 2) * C;
+  im2col3x3s2_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(x, col, N, H, W, C);
+  return launch_status();
+}
+extern "C" int b200np_col2im3x3s2(const float* dcol, const float* mask, float* dx, int N, int H, int W, int C,
+                                  void* stream) {
+  if (!dcol || !dx || N <= 0 || C <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1)) return B200NP_E_BADARG;
+  const long long total = (long long)N * H * W * C;
+  col2im3x3s2_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(dcol, mask, dx, N, H, W, C);
+  return launch_status();
+}
+extern "C" size_t b200np_bn_workspace(long long rows, int C) {
+  return (size_t)stat_slices(rows) * (size_t)C * 3 * sizeof(float);
+}
+extern "C" int b200np_bn_act_fwd(const float* x, const float* scale, const float* shift, float plus_one, float eps,
+                                 float* y, float* mean, float* rstd, float* run_mean, float* run_var, float momentum,
+                                 long long rows, int C, int relu, void* ws, size_t ws_bytes, void* stream) {
+  if (!x || !y || !mean || !rstd || rows <= 0 || C <= 0 || !ws) return B200NP_E_BADARG;
+  if (ws_bytes < b200np_bn_workspace(rows, C)) return B200NP_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int slices = stat_slices(rows);
+  const long long per = ceil_div(rows, slices);
+  bn_stats_l1_kernel<<<dim3((C + 31) / 32, slices), 256, 0, st>>>(x, (float*)ws, rows, C, per);
+  bn_stats_l2_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, slices, C, eps, mean, rstd, run_mean, run_var, momentum);
+  const long long total = rows * C;
+  bn_act_fwd_kernel<<<ew_grid(total, 256), 256, 0, st>>>(x, mean, rstd, scale, shift, plus_one, y, total, C, relu);
+  return launch_status(3);
+}
+extern "C" int b200np_bn_act_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
+                                 const float* scale, float plus_one, float* dx, float* dscale, float* dshift,
+                                 long long rows, int C, int relu, void* ws, size_t ws_bytes, void* stream) {
+  if (!dy || !y || !x || !mean || !rstd || !dx || !dscale || !dshift || rows <= 0 || C <= 0 || !ws) return B200NP_E_BADARG;
+  if (ws_bytes < b200np_bn_workspace(rows, C)) return B200NP_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int slices = stat_slices(rows);
+  const long long per = ceil_div(rows, slices);
+  bn_act_bwd_l1_kernel<<<dim3((C + 31) / 32, slices), 256, 0, st>>>(dy, y, x, mean, rstd, (float*)ws, rows, C, per, relu);
+  bn_act_bwd_l2_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, slices, C, dshift, dscale);
+  const long long total = rows * C;
+  bn_act_bwd_apply_kernel<<<ew_grid(total, 256), 256, 0, st>>>(dy, y, x, mean, rstd, scale, plus_one, dshift, dscale, dx,
+                                                               total, C, 1.f / (float)rows, relu);
+  return launch_status(3);
+}

@@ -215,7 +215,8 @@ static bool wgrad_halo_enabled() {
   return on;
 }
 static int halo_chunks_for(int N, int OH, int OW, int Cin, int Cout, int R, int stride) {
-  return (wgrad_halo_enabled() && Cin == 64 && Cout == 64 && R == 3 && stride == 1) ? tapwgrad_halo_chunks(N, OH, OW) : 0;
+  if (!(wgrad_halo_enabled() && Cin == 64 && Cout == 64 && R == 3)) return 0;
+  return stride == 1 ? tapwgrad_halo_chunks(N, OH, OW) : stride == 2 ? tapwgrad_halo_s2_chunks(N, OH, OW) : 0;
 }
 
 extern "C" size_t b200np_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int stride) {

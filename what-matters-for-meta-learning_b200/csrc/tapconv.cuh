@@ -71,6 +71,7 @@ int launch_tapwgrad_umma(const TapWgradArgs& a, int precision, cudaStream_t st);
 // halo formulation of the 3x3 stride-1 (+ skip) weight gradient (tapwgrad_halo.cu): chunk count for the workspace
 // (0: shape does not fit) and the launch, which sets a.chunks
 int tapwgrad_halo_chunks(int N, int OH, int OW);
+int tapwgrad_halo_s2_chunks(int N, int OH, int OW);   // stride-2 variant (2 x 16 pixel tiles)
 int launch_tapwgrad_halo(TapWgradArgs& a, int precision, cudaStream_t st);
 // Several outputs from one staged input ("classes"): tap t accumulates into output class tap_cls[t] (taps sorted
 // by class), class c is written at dst pixel (oy*dst_s + oy_c, ox*dst_s + ox_c).  The four input-parity classes

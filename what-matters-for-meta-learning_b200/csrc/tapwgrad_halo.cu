@@ -488,6 +488,275 @@ __global__ void __launch_bounds__(kThreadsTma, 1) tapwgrad_halo_tma_kernel(const
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Stride-2 3x3 weight gradient (conv1 of a BasicBlock: x [N, 2H, 2W, 64], dY [N, H, W, 64]) in the same TMA-fed form.
+// Tap (dy, dx) reads x[2 oy + dy][2 ox + dx] = parity plane (dy & 1, dx & 1) at shift ((dy - (dy & 1)) / 2, ...): the
+// four parity views of x are four tensor maps (base shifted, strides doubled), each plane a dense stride-1 stencil source.
+//   role 0: the vertical pairs (dy = -1 | dy = +1) for dx = -1, 0, +1: consecutive rows of the ODD-row planes are the two
+//           halves of M = 128 (region Q: plane (1,1), 18 pixel slots per row, dx = -1 / +1 are starts 0 / 1; region P:
+//           plane (1,0), dx = 0)                                                                           (6 taps)
+//   role 1: dy = 0: (0,-1) | (0,+1) are one pair -- the even-row plane (0,1) is loaded twice, the second copy one pixel
+//           further right, so one descriptor start serves both halves; (0,0) is a single whose second half is not used
+//                                                                                                          (3 taps)
+// Tiles are 2 x 16 output pixels (three x rows per tile and role fit three stages of 67 KB).
+// ------------------------------------------------------------------------------------------------------------
+namespace s2 {
+constexpr int RT2 = 2, NST = 3;
+constexpr uint32_t Q_BYTES = (RT2 + 1) * 2 * S_A;        // 13824
+constexpr uint32_t P_BYTES = (RT2 + 1) * 2 * S_B;        // 12288
+constexpr uint32_t E_BYTES = RT2 * 4 * S_B;              // 16384: [row][copy][block][pixel]
+constexpr uint32_t Z_BYTES = RT2 * 2 * S_B;              //  8192
+constexpr uint32_t A_PLANE = Q_BYTES + P_BYTES;          // 26112 >= E_BYTES + Z_BYTES (24576)
+constexpr uint32_t B_TILE2 = RT2 * 4 * S_B;              // 16384
+constexpr uint32_t STAGE2 = 2 * A_PLANE + B_TILE2;       // 68608
+constexpr int XP0 = (RT2 + 1) * (HW + TW), XP1 = RT2 * 3 * TW;      // pixel slots to split per role: 102 / 96
+constexpr int XT0s = (XP0 * 16 + kSplitThreads - 1) / kSplitThreads, XT1s = (XP1 * 16 + kSplitThreads - 1) / kSplitThreads;
+constexpr int YT2 = RT2 * TW * 16 / kSplitThreads;       // 2
+static_assert(Q_BYTES % 512 == 0 && A_PLANE % 512 == 0 && E_BYTES % 512 == 0 && STAGE2 % 1024 == 0 && E_BYTES + Z_BYTES <= A_PLANE, "layout");
+}  // namespace s2
+
+struct HaloWgradS2Tma {
+  tma::Map x[4];  // parity views (py * 2 + px) of x: [64][W][H][N], box 32 x 18 (px = 1) | 16 (px = 0) x 1 x 1
+  tma::Map dy;    // [64][W][H][N], box 32 x 16 x 1 x 1
+};
+
+template <bool X3, int ROLE>
+__device__ __forceinline__ void run_role_s2(const HaloWgradArgs& a, const HaloWgradS2Tma& tm, uint8_t* smem, uint64_t* bars,
+                                            uint32_t tmem) {
+  using namespace s2;
+  constexpr int XT = ROLE == 0 ? XT0s : XT1s;
+  constexpr int NPAIR = ROLE == 0 ? 3 : 2;
+  uint64_t* t_full = bars;             // [NST]
+  uint64_t* s_full = bars + NST;       // [NST]
+  uint64_t* s_empty = bars + 2 * NST;  // [NST]
+  uint64_t* done = bars + 3 * NST;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x;
+  const int H = a.H, W = a.W;          // dY geometry
+  const int tiles_x = W / TW, tiles_img = tiles_x * (H / RT2);
+  const long long t_begin = chunk * a.per, t_end = t_begin + a.per < a.tiles ? t_begin + a.per : a.tiles;
+  float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if (ROLE == 1) {   // the unused second half of the (0,0) single reads beyond region Z: keep it finite
+    for (uint32_t o = tid * 16; o < NST * STAGE2; o += kThreadsTma * 16) *reinterpret_cast<float4*>(smem + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();
+    __syncthreads();
+  }
+
+  if (warp == kLoadWarp) {
+    const uint32_t leader = elect_one_sync();
+    constexpr uint32_t kTx = ROLE == 0 ? ((RT2 + 1) * 2 * (HW + TW) + RT2 * 2 * TW) * 128u : (RT2 * 6 * TW + RT2 * 2 * TW) * 128u;
+    long long it = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int s = (int)(it % NST);
+      const int n = (int)(tile / tiles_img), rem = (int)(tile - (long long)n * tiles_img);
+      const int oy0 = (rem / tiles_x) * RT2, ox0 = (rem % tiles_x) * TW;
+      if (it >= NST) mbar_wait(s_empty + s, (uint32_t)((it / NST - 1) & 1));
+      if (leader) mbar_expect_tx_(t_full + s, kTx);
+      const uint32_t st = smem_u32(smem + s * STAGE2), bar = smem_u32(t_full + s);
+      const uint32_t b0 = st + 2 * A_PLANE;
+      if (ROLE == 0) {
+#pragma unroll
+        for (int hr = 0; hr <= RT2; ++hr)
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb) {
+            tma::load_4d(st + (uint32_t)(hr * 2 + cb) * S_A, &tm.x[3], bar, cb * 32, ox0 - 1, oy0 - 1 + hr, n, leader);
+            tma::load_4d(st + Q_BYTES + (uint32_t)(hr * 2 + cb) * S_B, &tm.x[2], bar, cb * 32, ox0, oy0 - 1 + hr, n, leader);
+          }
+      } else {
+#pragma unroll
+        for (int r = 0; r < RT2; ++r)
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb) {
+            tma::load_4d(st + (uint32_t)(r * 4 + cb) * S_B, &tm.x[1], bar, cb * 32, ox0 - 1, oy0 + r, n, leader);       // dx = -1
+            tma::load_4d(st + (uint32_t)(r * 4 + 2 + cb) * S_B, &tm.x[1], bar, cb * 32, ox0, oy0 + r, n, leader);       // dx = +1
+            tma::load_4d(st + E_BYTES + (uint32_t)(r * 2 + cb) * S_B, &tm.x[0], bar, cb * 32, ox0, oy0 + r, n, leader); // (0, 0)
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < RT2; ++r)
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb)
+          tma::load_4d(b0 + (uint32_t)(r * 4 + cb) * S_B, &tm.dy, bar, cb * 32, ox0, oy0 + r, n, leader);
+    }
+  } else if (warp == kIssueWarp) {
+    const uint32_t leader = elect_one_sync();
+    long long it = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int s = (int)(it % NST);
+      const uint32_t par = (uint32_t)((it / NST) & 1);
+      mbar_wait(t_full + s, par);
+      mbar_wait(s_full + s, par);
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(smem + s * STAGE2), a_lo = a_hi + A_PLANE, b0 = a_hi + 2 * A_PLANE;
+#pragma unroll
+      for (int r = 0; r < RT2; ++r) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const uint64_t bd = mn_desc(b0 + r * 4 * S_B + hf * 8 * 128, S_B);
+#pragma unroll
+          for (int j = 0; j < NPAIR; ++j) {
+            uint32_t aoff, lbo;
+            if (ROLE == 0) {
+              if (j == 1) { aoff = Q_BYTES + r * 2 * S_B + hf * 8 * 128; lbo = S_B; }              // dx = 0: plane (1,0)
+              else { aoff = r * 2 * S_A + (hf * 8 + (j == 2 ? 1 : 0)) * 128; lbo = S_A; }          // dx = -1 | +1: plane (1,1)
+            } else {
+              if (j == 0) { aoff = r * 4 * S_B + hf * 8 * 128; lbo = S_B; }                        // (0,-1) | (0,+1)
+              else { aoff = E_BYTES + r * 2 * S_B + hf * 8 * 128; lbo = S_B; }                     // (0, 0) | unused
+            }
+            const uint32_t d = tmem + j * 128;
+            const uint32_t acc = (it == 0 && r == 0 && hf == 0) ? 0u : 1u;
+            if (X3) {
+              umma_tf32(d, mn_desc(a_hi + aoff, lbo), bd, kIdesc128x128, acc, leader);
+              umma_tf32(d + 64, mn_desc(a_lo + aoff, lbo), bd, kIdesc128x64, 1u, leader);
+            } else {
+              umma_tf32(d, mn_desc(a_hi + aoff, lbo), bd, kIdesc128x64, acc, leader);
+            }
+          }
+        }
+      }
+      umma_commit(s_empty + s, leader);
+      if (tile + 1 == t_end) umma_commit(done, leader);
+    }
+  } else {
+    const int c16 = tid & 15, cb = c16 >> 3, ch = c16 & 7;
+    long long it = 0;
+    for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int s = (int)(it % NST);
+      mbar_wait(t_full + s, (uint32_t)((it / NST) & 1));
+      const uint32_t a_hi = smem_u32(smem + s * STAGE2);
+      uint8_t* const stg = smem + s * STAGE2;
+      uint32_t xo[XT], yo[YT2];
+      float4 xv[XT], yv[YT2];
+#pragma unroll
+      for (int i = 0; i < XT; ++i) {
+        const int px = (tid + i * kSplitThreads) >> 4;
+        xo[i] = 0xffffffffu;
+        if (ROLE == 0) {
+          if (px < (RT2 + 1) * HW) {
+            const int hr = px / HW, pc = px - hr * HW;
+            xo[i] = swz((uint32_t)(hr * 2 + cb) * S_A + pc * 128, ch);
+          } else if (px < XP0) {
+            const int q = px - (RT2 + 1) * HW, hr = q / TW, pc = q - hr * TW;
+            xo[i] = swz(Q_BYTES + (uint32_t)(hr * 2 + cb) * S_B + pc * 128, ch);
+          }
+        } else if (px < XP1) {
+          const int blk = px / TW, pc = px - blk * TW;      // blk: E rows x copies (0..3), then Z rows (4..5)
+          if (blk < RT2 * 2) xo[i] = swz((uint32_t)((blk >> 1) * 4 + (blk & 1) * 2 + cb) * S_B + pc * 128, ch);
+          else xo[i] = swz(E_BYTES + (uint32_t)((blk - RT2 * 2) * 2 + cb) * S_B + pc * 128, ch);
+        }
+        if (xo[i] != 0xffffffffu) xv[i] = lds128(a_hi + xo[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < YT2; ++i) {
+        const int px = (tid + i * kSplitThreads) >> 4;
+        const int r = px / TW, pc = px - r * TW;
+        yo[i] = swz((uint32_t)(r * 4 + cb) * S_B + pc * 128, ch);
+        yv[i] = lds128(a_hi + 2 * A_PLANE + yo[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < XT; ++i)
+        if (xo[i] != 0xffffffffu) split_store(stg, stg + A_PLANE, xo[i], xv[i], X3);
+#pragma unroll
+      for (int i = 0; i < YT2; ++i) {
+        split_store(stg + 2 * A_PLANE, stg + 2 * A_PLANE + 2 * S_B, yo[i], yv[i], X3);
+        if (ROLE == 0) { dbs.x += yv[i].x; dbs.y += yv[i].y; dbs.z += yv[i].z; dbs.w += yv[i].w; }
+      }
+      fence_proxy_async();
+      mbar_arrive_(s_full + s);
+    }
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  __syncthreads();
+  if (ROLE == 0 && a.part_db) {
+    float* red = reinterpret_cast<float*>(smem);
+    if (tid < kSplitThreads) *reinterpret_cast<float4*>(red + (tid >> 4) * 64 + (tid & 15) * 4) = dbs;
+    __syncthreads();
+    if (tid < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t += red[r * 64 + tid];
+      a.part_db[(long long)chunk * 64 + tid] = t;
+    }
+  }
+  if (warp >= 8) return;
+  const int q = warp & 3, half = warp >> 2, second = q >> 1, ci = (q & 1) * 32 + lane;
+#pragma unroll 1
+  for (int j = 0; j < NPAIR; ++j) {
+    int tap;
+    if (ROLE == 0) tap = second ? 6 + j : j;                    // (dy = +1 | -1, dx = j - 1)
+    else tap = j == 0 ? (second ? 5 : 3) : (second ? -1 : 4);   // (0, +1 | -1)  |  (0, 0)
+    uint32_t r0[32], r1[32];
+    const uint32_t ta = tmem + (static_cast<uint32_t>(q * 32) << 16) + j * 128 + half * 32;
+    tmem_ld32(ta, r0);
+    if (X3) tmem_ld32(ta + 64, r1);
+    if (tap >= 0) {
+      float* po = a.part + ((long long)chunk * a.ntaps + tap) * 64 * 64 + ci;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        po[(half * 32 + i) * 64] = (X3 ? __uint_as_float(r1[i]) : 0.f) + __uint_as_float(r0[i]);
+    }
+  }
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(kThreadsTma, 1) tapwgrad_halo_s2_kernel(const HaloWgradArgs a,
+                                                                           const __grid_constant__ HaloWgradS2Tma tm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + s2::NST * s2::STAGE2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * s2::NST + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < s2::NST; ++s) {
+      mbar_init(bars + s, 1);
+      mbar_init(bars + s2::NST + s, kSplitThreads);
+      mbar_init(bars + 2 * s2::NST + s, 1);
+    }
+    mbar_init(bars + 3 * s2::NST, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (blockIdx.y == 0) run_role_s2<X3, 0>(a, tm, smem, bars, tmem);
+  else run_role_s2<X3, 1>(a, tm, smem, bars, tmem);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+template <bool X3>
+int launch_s2(const HaloWgradArgs& h, int chunks, cudaStream_t st) {
+  HaloWgradS2Tma tm;
+  const uint64_t W = (uint64_t)h.W, H = (uint64_t)h.H, N = (uint64_t)h.N;   // dY geometry; x is [N, 2H, 2W, 64]
+  const uint64_t dims[4] = {64, W, H, N};
+  const uint64_t sy[3] = {256, W * 256, H * W * 256};
+  const uint64_t sx[3] = {512, 2 * (2 * W) * 256, (2 * H) * (2 * W) * 256};
+  const uint32_t box18[4] = {32, HW, 1, 1}, box16[4] = {32, TW, 1, 1};
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px)
+      if (!tma::encode_f32_4d(&tm.x[py * 2 + px], h.x + ((long long)py * 2 * h.W + px) * 64, dims, sx,
+                              (py == 1 && px == 1) ? box18 : box16, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return B200NP_E_UNSUPPORTED;
+  if (!tma::encode_f32_4d(&tm.dy, h.dy, dims, sy, box16, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return B200NP_E_UNSUPPORTED;
+  const size_t smem = s2::NST * s2::STAGE2 + 1024 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tapwgrad_halo_s2_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return B200NP_E_LAUNCH;
+    configured = true;
+  }
+  tapwgrad_halo_s2_kernel<X3><<<dim3(chunks, 2), kThreadsTma, smem, st>>>(h, tm);
+  return launch_status();
+}
+
 static bool wgrad_tma_enabled() {
   static const bool on = [] { const char* e = getenv("B200NP_WGRAD_TMA"); return e ? e[0] != '0' : true; }();
   return on;
@@ -542,9 +811,35 @@ int tapwgrad_halo_chunks(int N, int OH, int OW) {
   return (int)ceil_div(tiles, per);
 }
 
-// 3x3 stride-1 taps in row-major order (+ one skip tap on src2 with stride 2); fills a.chunks
+// Stride-2 variant: tiles of 2 x 16 output pixels.
+int tapwgrad_halo_s2_chunks(int N, int OH, int OW) {
+  if (N <= 0 || OH % s2::RT2 || OW % TW) return 0;
+  const long long tiles = (long long)N * (OH / s2::RT2) * (OW / TW);
+  const long long per = ceil_div(tiles, kNumSMs);
+  return (int)ceil_div(tiles, per);
+}
+static int launch_tapwgrad_halo_s2(TapWgradArgs& a, int precision, cudaStream_t st) {
+  if (!wgrad_tma_enabled() || a.ntaps != 9 || a.srcH != 2 * a.OH || a.srcW != 2 * a.OW) return B200NP_E_UNSUPPORTED;
+  for (int t = 0; t < 9; ++t)
+    if (a.taps[t].src != 0 || a.taps[t].dy != t / 3 - 1 || a.taps[t].dx != t % 3 - 1) return B200NP_E_UNSUPPORTED;
+  const int chunks = tapwgrad_halo_s2_chunks(a.N, a.OH, a.OW);
+  if (chunks <= 0) return B200NP_E_UNSUPPORTED;
+  HaloWgradArgs h{};
+  h.x = a.src; h.dy = a.dy; h.xs = nullptr;
+  h.part = a.part; h.part_db = a.part_db;
+  h.N = a.N; h.H = a.OH; h.W = a.OW; h.ntaps = 9;
+  h.tiles = (long long)a.N * (a.OH / s2::RT2) * (a.OW / TW);
+  h.per = ceil_div(h.tiles, kNumSMs);
+  const int rc = precision == B200NP_PREC_TF32 ? launch_s2<false>(h, chunks, st) : launch_s2<true>(h, chunks, st);
+  if (rc == B200NP_OK) a.chunks = chunks;
+  return rc;
+}
+
+// 3x3 stride-1 taps in row-major order (+ one skip tap on src2 with stride 2), or plain 3x3 stride 2; fills a.chunks
 int launch_tapwgrad_halo(TapWgradArgs& a, int precision, cudaStream_t st) {
-  if (precision == B200NP_PREC_FP32_SIMT || a.Cin != 64 || a.Cout != 64 || a.in_s != 1) return B200NP_E_UNSUPPORTED;
+  if (precision == B200NP_PREC_FP32_SIMT || a.Cin != 64 || a.Cout != 64) return B200NP_E_UNSUPPORTED;
+  if (a.in_s == 2) return launch_tapwgrad_halo_s2(a, precision, st);
+  if (a.in_s != 1) return B200NP_E_UNSUPPORTED;
   if (a.ntaps != 9 && a.ntaps != 10) return B200NP_E_UNSUPPORTED;
   for (int t = 0; t < 9; ++t)
     if (a.taps[t].src != 0 || a.taps[t].dy != t / 3 - 1 || a.taps[t].dx != t % 3 - 1) return B200NP_E_UNSUPPORTED;
