@@ -196,32 +196,62 @@ class EncoderW0Fn(Function):
         for im, n in zip(imgs, Ns):
             ops.conv_small_fwd(im, w0, b0, out=x1[off:off + n], relu=True, prec=prec)
             off += n
-        wd2, wd5 = ops.pack_conv_weight(w2), ops.pack_conv_weight(w5)
-        x2 = ops.conv_fwd(x1, wd2, b2, 2, ACT_RELU, prec)
-        x3, pidx = ops.maxpool2x2_fwd(x2)
-        x4 = ops.conv_fwd(x3, wd5, b5, 2, ACT_RELU, prec)
+        if prec == PREC_FP32_SIMT:
+            wd2, wd5 = ops.pack_conv_weight(w2), ops.pack_conv_weight(w5)
+            x2 = ops.conv_fwd(x1, wd2, b2, 2, ACT_RELU, prec)
+            x3, pidx = ops.maxpool2x2_fwd(x2)
+            x4 = ops.conv_fwd(x3, wd5, b5, 2, ACT_RELU, prec)
+            col2 = col5 = None
+        else:
+            # 32 -> 48 and 48 -> 64 channels do not fill the 64 x 64 tap-convolution tiles: im2col (k = ci*9 + tap, the
+            # flattening of torch's weight) + the tcgen05 GEMM with a fused bias + ReLU epilogue; the backward is two more
+            # GEMMs on the same column matrix (82 % of encoder_w0's FLOPs used to run on CUDA cores)
+            wd2 = wd5 = None
+            col2 = ops.im2col3x3s2(x1)
+            x2 = ops.empty((N, H // 4, W // 4, w2.shape[0]), imgs[0])
+            ops.gemm(_p(col2), _p(w2), _p(x2), col2.shape[0], w2.shape[0], col2.shape[1], col2.shape[1], 1, 1,
+                     col2.shape[1], w2.shape[0], bias=_p(b2), act=ACT_RELU, prec=prec)
+            x3, pidx = ops.maxpool2x2_fwd(x2)
+            col5 = ops.im2col3x3s2(x3)
+            x4 = ops.empty((N, H // 16, W // 16, w5.shape[0]), imgs[0])
+            ops.gemm(_p(col5), _p(w5), _p(x4), col5.shape[0], w5.shape[0], col5.shape[1], col5.shape[1], 1, 1,
+                     col5.shape[1], w5.shape[0], bias=_p(b5), act=ACT_RELU, prec=prec)
         outs, off = [], 0
         for n in Ns:
             outs.append(ops.nhwc_to_nchw_flat(x4[off:off + n]))
             off += n
         ctx.prec, ctx.Ns, ctx.imgs = prec, Ns, imgs
-        ctx.saved = (x1, x2, x3, x4, pidx, wd2, wd5, tuple(w0.shape))
+        ctx.saved = (x1, x2, x3, x4, pidx, wd2, wd5, tuple(w0.shape), col2, col5, w2, w5)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *douts):
         prec, Ns = ctx.prec, ctx.Ns
-        x1, x2, x3, x4, pidx, wd2, wd5, w0_shape = ctx.saved
+        x1, x2, x3, x4, pidx, wd2, wd5, w0_shape, col2, col5, w2, w5 = ctx.saved
         d4 = torch.empty_like(x4)
         off = 0
         for n, do in zip(Ns, douts):
             ops.nchw_flat_to_nhwc(do.contiguous(), x4[off:off + n], d4[off:off + n])
             off += n
-        dw5, db5, _ = ops.conv_wgrad(x3, d4, 3, 2, prec)
-        d3 = ops.conv_dgrad(d4, wd5, x3.shape, 2, prec, mask_src=None)
-        d2 = ops.maxpool2x2_bwd(d3, pidx, x2)
-        dw2, db2, _ = ops.conv_wgrad(x1, d2, 3, 2, prec)
-        d1 = ops.conv_dgrad(d2, wd2, x1.shape, 2, prec, mask_src=x1)
+        if col2 is None:
+            dw5, db5, _ = ops.conv_wgrad(x3, d4, 3, 2, prec)
+            d3 = ops.conv_dgrad(d4, wd5, x3.shape, 2, prec, mask_src=None)
+            d2 = ops.maxpool2x2_bwd(d3, pidx, x2)
+            dw2, db2, _ = ops.conv_wgrad(x1, d2, 3, 2, prec)
+            d1 = ops.conv_dgrad(d2, wd2, x1.shape, 2, prec, mask_src=x1)
+        else:
+            def conv_bwd(col, w, dy, x_shape, mask):
+                M, K = col.shape
+                Co = w.shape[0]
+                dw = ops.empty(tuple(w.shape), w)
+                ops.gemm(_p(dy), _p(col), _p(dw), Co, K, M, 1, Co, K, 1, K, prec=prec)             # dW = dY^T col
+                db = ops.colsum(dy, M, Co, Co)
+                dcol = ops.empty((M, K), dy)
+                ops.gemm(_p(dy), _p(w), _p(dcol), M, K, Co, Co, 1, K, 1, K, prec=prec)             # dcol = dY W
+                return dw, db, ops.col2im3x3s2(dcol, x_shape, mask=mask)
+            dw5, db5, d3 = conv_bwd(col5, w5, d4, x3.shape, None)
+            d2 = ops.maxpool2x2_bwd(d3, pidx, x2)
+            dw2, db2, d1 = conv_bwd(col2, w2, d2, x1.shape, x1)
         off, dw0, db0 = 0, None, None
         for im, n in zip(ctx.imgs, Ns):
             dw, db = ops.conv_small_wgrad(im, d1[off:off + n], w0_shape, prec)
@@ -421,9 +451,11 @@ class FavorAttentionFn(Function):
         dg = ops.reduce(dg_part, 1)
         tie_total = ties
         if dist.world_size() > 1:
-            tie_total = ties.clone()
-            dist.all_reduce_sum(dg)       # d loss / d g sums over every rank's keys
-            dist.all_reduce_sum(tie_total)
+            # d loss / d g and the tie count both sum over every rank's keys: ONE 8-byte all-reduce, not two
+            pair = ops.empty((2,), xq)
+            ops.multi_copy(pair, [(dg, 0, 1), (ties, 1, 1)])
+            dist.all_reduce_sum(pair)
+            dg, tie_total = pair[0:1], pair[1:2]
         ops.check(ops.LIB.b200np_favor_key_fixup(ops._ptr(dW), ops._ptr(W), ops._ptr(g), ops._ptr(dg),
                                                  ops._ptr(tie_total), Rk, M, ldu, ops._stream()), "favor_key_fixup")
         dxq, dxk = torch.empty_like(xq), torch.empty_like(xk)
