@@ -313,6 +313,20 @@ int b200np_bn_act_bwd(const float* dy, const float* y, const float* x, const flo
                       int relu, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Bayes-by-backprop weight sampling + KL (networks/bbb/BBBConv.py:83-105, BBBLinear.py):
+ *   sigma = log1p(exp(rho)), w = mu + eps * sigma, kl = calculate_kl(prior_mu, prior_sigma, mu, sigma) (:32-34,:102-105)
+ * eps [n] is drawn by the caller (the reference draws it on the host, :86).  kl_part receives b200np_bbb_kl_blocks(n)
+ * partial sums (sum them in order with b200np_reduce: deterministic).  Backward: dw [n] (nullable) and the device
+ * scalar dkl (nullable) -> dmu, drho.
+ * ------------------------------------------------------------------------------------------ */
+int b200np_bbb_kl_blocks(long long n);
+int b200np_bbb_sample_kl_fwd(const float* mu, const float* rho, const float* eps, float prior_mu, float prior_sigma,
+                             float* w, float* sigma, float* kl_part, long long n, void* stream);
+int b200np_bbb_sample_kl_bwd(const float* dw, const float* dkl, const float* mu, const float* rho, const float* eps,
+                             const float* sigma, float prior_mu, float prior_sigma, float* dmu, float* drho,
+                             long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Diagnostics (tools/ only; never called on the product path).  They switch global state of the
  * library and are NOT thread-safe.
  *   b200np_debug_set_wgrad_waves   pixel chunks per weight-gradient launch = waves * resident CTAs

@@ -40,9 +40,14 @@ for method in ("ANPDistractor", "ANP", "ANPShapeNet1D", "CNPDistractor", "CondNe
     m = importlib.import_module(f"networks.{method}")          # train.py:42-43
     assert inside(m.__name__, pkg), m.__file__
     assert getattr(m, method).__mro__[1].__module__ == "networks._families"
-for other in ("models", "ResNet", "fast_attention", "MAMLShapeNet1D", "gated_conv_net"):
+for other in ("models", "ResNet", "fast_attention", "MAMLShapeNet1D", "MMAMLShapeNet1D", "CNPMR"):
     m = importlib.import_module(f"networks.{other}")
     assert inside(m.__name__, ref), m.__file__
+# shadowed on purpose, but handing out the reference's own classes unless B200NP_MMAML=1 / B200NP_BBB=1
+from networks.gated_conv_net import GatedConvModel
+from networks.bbb import BBBConv2d, BBBLinear
+assert GatedConvModel.__module__ == "networks._reference_gated_conv_net"
+assert BBBConv2d.__module__ == "networks.bbb._reference_BBBConv" and BBBLinear.__module__ == "networks.bbb._reference_BBBLinear"
 print("OK")
 """
 

@@ -7,18 +7,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "what-matters-for-meta-learning_b200")]
 import torch
 from torch.profiler import ProfilerActivity, profile
-from bench import NC, NT, TASKS_PER_GPU, make_cfg
+import importlib
+from bench import MODELS, make_cfg
 from b200np import engine
 from b200np.optim import FlatParams, FusedAdam
-from networks.ANPDistractor import ANPDistractor
 from oracle import synth
 from trainer.losses import LossFunc
 
 engine.set_precision(sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "tf32x3")
-T = TASKS_PER_GPU
-model = ANPDistractor(make_cfg(T, "cuda:0")).to("cuda:0")
-flat = FlatParams(model); opt = FusedAdam(flat, lr=1e-4); lossf = LossFunc("mse", "distractor")
-b = [torch.from_numpy(a).cuda() for a in synth.task_batch("distractor", T, NC, NT, seed=1)]
+MODEL = os.environ.get("PROFILE_MODEL", "ANPDistractor")      # any key of bench.MODELS
+task, _, _, _, T, views = MODELS[MODEL]
+NC = 15
+NT = views - NC if task == "distractor" else 15
+model = getattr(importlib.import_module(f"networks.{MODEL}"), MODEL)(make_cfg(T, "cuda:0", MODEL)).to("cuda:0")
+flat = FlatParams(model); opt = FusedAdam(flat, lr=1e-4); lossf = LossFunc("mse", task)
+b = [torch.from_numpy(a).cuda() for a in synth.task_batch(task, T, NC, NT, seed=1)]
+print(f"# {MODEL} T={T} nc={NC} nt={NT}")
 
 
 def step():

@@ -421,3 +421,25 @@ def bn_act_bwd(dy, y, x, mean, rstd, scale, plus_one, relu=True):
                                 _ptr(dscale), _ptr(dshift), rows, Cc, int(relu), _ptr(ws), ws_bytes, _stream()),
           "bn_act_bwd")
     return dx, dscale, dshift
+
+
+# ----------------------------------------------------------------------------------------------
+# Bayes-by-backprop weight sampling + KL
+# ----------------------------------------------------------------------------------------------
+def bbb_sample_kl_fwd(mu, rho, eps, prior_mu, prior_sigma):
+    """-> (w = mu + eps * softplus(rho), sigma, kl [1])."""
+    _chk(mu, "mu"), _chk(rho, "rho"), _chk(eps, "eps")
+    n = mu.numel()
+    w, sigma = torch.empty_like(mu), torch.empty_like(mu)
+    part = empty((LIB.b200np_bbb_kl_blocks(n),), mu)
+    check(LIB.b200np_bbb_sample_kl_fwd(_ptr(mu), _ptr(rho), _ptr(eps), float(prior_mu), float(prior_sigma), _ptr(w),
+                                       _ptr(sigma), _ptr(part), n, _stream()), "bbb_sample_kl_fwd")
+    return w, sigma, reduce(part, 1)
+
+
+def bbb_sample_kl_bwd(dw, dkl, mu, rho, eps, sigma, prior_mu, prior_sigma):
+    n = mu.numel()
+    dmu, drho = torch.empty_like(mu), torch.empty_like(mu)
+    check(LIB.b200np_bbb_sample_kl_bwd(_ptr(dw), _ptr(dkl), _ptr(mu), _ptr(rho), _ptr(eps), _ptr(sigma), float(prior_mu),
+                                       float(prior_sigma), _ptr(dmu), _ptr(drho), n, _stream()), "bbb_sample_kl_bwd")
+    return dmu, drho

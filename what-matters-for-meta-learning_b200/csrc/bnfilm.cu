@@ -263,3 +263,66 @@ extern "C" int b200np_bn_act_bwd(const float* dy, const float* y, const float* x
                                                                total, C, 1.f / (float)rows, relu);
   return launch_status(3);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bayes-by-backprop layers of the "MR" variants (networks/bbb/BBBConv.py:83-105, BBBLinear.py):
+//   sigma = log1p(exp(rho)),  w = mu + eps * sigma                         (eps: the host draws it, :86 / :92)
+//   kl = 0.5 * sum( 2 log(sigma / ps) - 1 + (ps / sigma)^2 + ((mu - pm) / sigma)^2 )      (calculate_kl, :32-34, with
+//        the argument order kl_loss uses at :102-105: q = prior, p = posterior)
+// One pass writes w and sigma and the per-block KL partial sums (deterministic: the caller sums them in order with
+// b200np_reduce); the backward turns dL/dw and the scalar dL/dkl into dL/dmu and dL/drho.
+// ---------------------------------------------------------------------------------------------------------------
+namespace b200np {
+namespace {
+__global__ void __launch_bounds__(256) bbb_sample_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ rho,
+                                                                const float* __restrict__ eps, float pm, float ps,
+                                                                float* __restrict__ w, float* __restrict__ sigma,
+                                                                float* __restrict__ kl_part, long long n) {
+  __shared__ float red[32];
+  const long long st = (long long)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += st) {
+    const float r = __ldg(rho + i), m = __ldg(mu + i);
+    const float s = log1pf(expf(r));
+    sigma[i] = s;
+    w[i] = fmaf(__ldg(eps + i), s, m);
+    const float a = ps / s, b = (m - pm) / s;
+    acc += 0.5f * (2.f * logf(s / ps) - 1.f + a * a + b * b);
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) kl_part[blockIdx.x] = tot;
+}
+__global__ void bbb_sample_kl_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ dkl,
+                                         const float* __restrict__ mu, const float* __restrict__ rho,
+                                         const float* __restrict__ eps, const float* __restrict__ sigma, float pm, float ps,
+                                         float* __restrict__ dmu, float* __restrict__ drho, long long n) {
+  const long long st = (long long)gridDim.x * blockDim.x;
+  const float gk = dkl ? __ldg(dkl) : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += st) {
+    const float s = __ldg(sigma + i), m = __ldg(mu + i), g = dw ? __ldg(dw + i) : 0.f;
+    const float d = m - pm, s2 = s * s;
+    dmu[i] = g + gk * d / s2;
+    const float dsig = g * __ldg(eps + i) + gk * (1.f / s - (ps * ps + d * d) / (s2 * s));
+    drho[i] = dsig / (1.f + expf(-__ldg(rho + i)));     // d softplus / d rho = sigmoid(rho)
+  }
+}
+}  // namespace
+}  // namespace b200np
+
+extern "C" int b200np_bbb_kl_blocks(long long n) { return ew_grid(n, 256); }
+extern "C" int b200np_bbb_sample_kl_fwd(const float* mu, const float* rho, const float* eps, float prior_mu,
+                                        float prior_sigma, float* w, float* sigma, float* kl_part, long long n,
+                                        void* stream) {
+  if (!mu || !rho || !eps || !w || !sigma || !kl_part || n <= 0 || !(prior_sigma > 0.f)) return B200NP_E_BADARG;
+  bbb_sample_kl_fwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(mu, rho, eps, prior_mu, prior_sigma, w, sigma,
+                                                                          kl_part, n);
+  return launch_status();
+}
+extern "C" int b200np_bbb_sample_kl_bwd(const float* dw, const float* dkl, const float* mu, const float* rho,
+                                        const float* eps, const float* sigma, float prior_mu, float prior_sigma,
+                                        float* dmu, float* drho, long long n, void* stream) {
+  if (!mu || !rho || !eps || !sigma || !dmu || !drho || n <= 0) return B200NP_E_BADARG;
+  bbb_sample_kl_bwd_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(dw, dkl, mu, rho, eps, sigma, prior_mu,
+                                                                          prior_sigma, dmu, drho, n);
+  return launch_status();
+}

@@ -542,10 +542,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapconv_halo_kernel(const HaloArg
 //   warp  14    plane loader: per (tile, channel half) ONE cp.async.bulk.tensor per plane (HaloTma) lands the raw fp32
 //               pixels in the `hi` plane of the stage -- no global-load / address arithmetic in any thread, out-of-bounds
 //               pixels zero-filled by the copy engine;
-//   warps 0-7   split warps: shared memory -> shared memory.  They round the landed values to tf32 in place
-//               (hi = rn_tf32(x)) and, fp32-grade mode, write lo = x - hi to the `lo` plane: bit-identical operands to
-//               the register-staged kernel, at one LDS + one or two STS per 16 bytes instead of LDG + address decode +
-//               two STS (the L1 data pipe, which the tensor core's operand reads share, was 95 % busy);
+//   warps 0-7   split warps: shared memory -> shared memory, one LDS + one STS per 16 bytes (the register-staged
+//               producers spent LDG + address decode + two STS; the L1 data pipe, which the tensor core's operand reads
+//               share, was 95 % busy).  fp32-grade mode: the landed raw plane is used as the `hi` operand as it is -- the
+//               tensor core truncates fp32 to tf32 -- and only lo = x - trunc_tf32(x) is written to the `lo` plane;
+//               single-pass mode: the landed values are rounded to nearest in place;
 //   warp  9     MMA issuer with the tap loop unrolled (NT = 9 or 10 taps): every per-tap descriptor word is a
 //               loop-invariant uniform register, and the `weights landed` probe of tap t+1 is issued before the MMAs of
 //               tap t, so its ~90-cycle latency hides behind the issue of eight MMAs.
@@ -627,14 +628,8 @@ __global__ void __launch_bounds__(kThreadsTma, 1) tapconv_halo_tma_kernel(const 
           for (int j = 0; j < 4; ++j) {
             const uint32_t u = u0 + j * kProducerThreads;
             if (u < units) {
-              float4 r;
-              r.x = to_tf32(v[j].x); r.y = to_tf32(v[j].y); r.z = to_tf32(v[j].z); r.w = to_tf32(v[j].w);
-              sts128(hi + u * 16u, r);
-              if (X3) {
-                float4 l;
-                l.x = lo_part(v[j].x, r.x); l.y = lo_part(v[j].y, r.y); l.z = lo_part(v[j].z, r.z); l.w = lo_part(v[j].w, r.w);
-                sts128(lo + u * 16u, l);
-              }
+              if (X3) sts128(lo + u * 16u, lo_of_truncated(v[j]));   // the raw plane is the hi operand (hardware truncation)
+              else sts128(hi + u * 16u, to_tf32_4(v[j]));            // single pass: round to nearest in place
             }
           }
         }

@@ -283,10 +283,57 @@ __device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// Split warps of the TMA-fed kernels: linear sweeps over the landed raw fp32 regions, one LDS + one STS per 16 bytes.
+// fp32-grade mode: the raw region is the `hi` operand as it is (the tensor core truncates fp32 to tf32) and only
+// lo = x - trunc_tf32(x) is written; single-pass mode rounds to nearest in place.  A: `a_units` 16-byte units whose lo
+// copy sits A_PLANE bytes further; B: per row [hi cb0 | hi cb1 | lo cb0 | lo cb1] blocks of S_B bytes.
+// Thread `tid` (< 256) of the B sweep always sees the same 16-byte position of a 128-byte row and the same swizzle
+// phase, hence the same four channels: `dbs` accumulates their dY sums (bias gradient) when DB is set.
+template <bool X3, bool DB>
+__device__ __forceinline__ void split_sweep(uint32_t a_hi, uint32_t a_plane, uint32_t a_units, uint32_t b, int rows,
+                                            int tid, float4& dbs) {
+  for (uint32_t u0 = tid; u0 < a_units; u0 += 4 * kSplitThreads) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t u = u0 + j * kSplitThreads;
+      if (u < a_units) v[j] = lds128(a_hi + u * 16u);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t u = u0 + j * kSplitThreads;
+      if (u < a_units) {
+        if (X3) sts128(a_hi + a_plane + u * 16u, lo_of_truncated(v[j]));
+        else sts128(a_hi + u * 16u, to_tf32_4(v[j]));
+      }
+    }
+  }
+  // B: unit u = r * 256 + w, w < 256 = the two hi blocks of row r (2 * S_B / 16 units)
+  static_assert(2 * S_B / 16 == kSplitThreads, "one B row per sweep pass");
+  float4 y[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (r < rows) y[r] = lds128(b + (uint32_t)r * 4u * S_B + (uint32_t)tid * 16u);
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (r < rows) {
+      const uint32_t addr = b + (uint32_t)r * 4u * S_B + (uint32_t)tid * 16u;
+      if (X3) sts128(addr + 2u * S_B, lo_of_truncated(y[r]));
+      else sts128(addr, to_tf32_4(y[r]));
+      if (DB) { dbs.x += y[r].x; dbs.y += y[r].y; dbs.z += y[r].z; dbs.w += y[r].w; }
+    }
+}
+// channel quadruple and reduction slot of thread `tid` in split_sweep's B pass (see there)
+__device__ __forceinline__ void db_slot(int tid, int& channel, int& slot) {
+  const int p = tid & 7, phase = (tid >> 3) & 3, cb = tid >> 7;
+  const int chunk = (((p >> 1) ^ phase) << 1) | (p & 1);
+  channel = cb * 32 + chunk * 4;
+  slot = ((tid >> 5) & 3) * 4 + phase;
+}
+
 template <bool X3, int ROLE>
 __device__ __forceinline__ void run_role_tma(const HaloWgradArgs& a, const HaloWgradTma& tm, uint8_t* smem, uint64_t* bars,
                                              uint32_t tmem) {
-  constexpr int XT = ROLE == 0 ? XT0 : XT1;
   constexpr uint32_t A_PLANE = ROLE == 0 ? A0_PLANE : A1_PLANE;
   constexpr uint32_t ROW_A = ROLE == 0 ? 2 * S_A : 4 * S_A;
   uint64_t* t_full = bars;        // [2] tensor copies landed              (count 1 + tx)
@@ -380,46 +427,12 @@ __device__ __forceinline__ void run_role_tma(const HaloWgradArgs& a, const HaloW
     }
   } else {
     // ===================== split warps: smem -> smem =====================
-    const int c16 = tid & 15, cb = c16 >> 3, ch = c16 & 7;
     long long it = 0;
     for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
       const int s = (int)(it & 1);
       mbar_wait(t_full + s, (uint32_t)((it >> 1) & 1));
-      const uint32_t a_hi = smem_u32(smem + s * STAGE), a_lo = a_hi + A_PLANE, b = a_hi + 2 * A_PLANE;
-      uint32_t xo[XT];
-      float4 xv[XT], yv[YT];
-#pragma unroll
-      for (int i = 0; i < XT; ++i) {
-        const int px = (tid + i * kSplitThreads) >> 4;
-        xo[i] = 0xffffffffu;
-        if (ROLE == 0) {
-          const int hr = px / HW, pc = px - hr * HW;
-          if (px < (RT + 1) * HW) xo[i] = swz((uint32_t)(hr * 2 + cb) * S_A + pc * 128, ch);
-        } else if (px < RT * HW) {
-          const int r = px / HW, pc = px - r * HW;
-          xo[i] = swz((uint32_t)(r * 4 + cb) * S_A + pc * 128, ch);
-        } else if (px < RT * (HW + TW)) {
-          const int q = px - RT * HW, r = q / TW, k = q - r * TW;
-          xo[i] = swz((uint32_t)(r * 4 + 2 + cb) * S_A + (k + 1) * 128, ch);
-        }
-        if (xo[i] != 0xffffffffu) xv[i] = lds128(a_hi + xo[i]);
-      }
-      uint32_t yo[YT];
-#pragma unroll
-      for (int i = 0; i < YT; ++i) {
-        const int px = (tid + i * kSplitThreads) >> 4;
-        const int r = px / TW, pc = px - r * TW;
-        yo[i] = swz((uint32_t)(r * 4 + cb) * S_B + pc * 128, ch);
-        yv[i] = lds128(b + yo[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < XT; ++i)
-        if (xo[i] != 0xffffffffu) split_store(smem + s * STAGE, smem + s * STAGE + A_PLANE, xo[i], xv[i], X3);
-#pragma unroll
-      for (int i = 0; i < YT; ++i) {
-        split_store(smem + s * STAGE + 2 * A_PLANE, smem + s * STAGE + 2 * A_PLANE + 2 * S_B, yo[i], yv[i], X3);
-        if (ROLE == 0) { dbs.x += yv[i].x; dbs.y += yv[i].y; dbs.z += yv[i].z; dbs.w += yv[i].w; }
-      }
+      const uint32_t a_hi = smem_u32(smem + s * STAGE);
+      split_sweep<X3, ROLE == 0>(a_hi, A_PLANE, A_PLANE / 16, a_hi + 2 * A_PLANE, RT, tid, dbs);
       fence_proxy_async();
       mbar_arrive_(s_full + s);
     }
@@ -430,7 +443,11 @@ __device__ __forceinline__ void run_role_tma(const HaloWgradArgs& a, const HaloW
   __syncthreads();
   if (ROLE == 0 && a.part_db) {   // all MMAs have retired: the stages are free for the 16-row reduction of the dY sums
     float* red = reinterpret_cast<float*>(smem);
-    if (tid < kSplitThreads) *reinterpret_cast<float4*>(red + (tid >> 4) * 64 + (tid & 15) * 4) = dbs;
+    if (tid < kSplitThreads) {
+      int channel, slot;
+      db_slot(tid, channel, slot);
+      *reinterpret_cast<float4*>(red + slot * 64 + channel) = dbs;
+    }
     __syncthreads();
     if (tid < 64) {
       float t = 0.f;
@@ -509,9 +526,6 @@ constexpr uint32_t Z_BYTES = RT2 * 2 * S_B;              //  8192
 constexpr uint32_t A_PLANE = Q_BYTES + P_BYTES;          // 26112 >= E_BYTES + Z_BYTES (24576)
 constexpr uint32_t B_TILE2 = RT2 * 4 * S_B;              // 16384
 constexpr uint32_t STAGE2 = 2 * A_PLANE + B_TILE2;       // 68608
-constexpr int XP0 = (RT2 + 1) * (HW + TW), XP1 = RT2 * 3 * TW;      // pixel slots to split per role: 102 / 96
-constexpr int XT0s = (XP0 * 16 + kSplitThreads - 1) / kSplitThreads, XT1s = (XP1 * 16 + kSplitThreads - 1) / kSplitThreads;
-constexpr int YT2 = RT2 * TW * 16 / kSplitThreads;       // 2
 static_assert(Q_BYTES % 512 == 0 && A_PLANE % 512 == 0 && E_BYTES % 512 == 0 && STAGE2 % 1024 == 0 && E_BYTES + Z_BYTES <= A_PLANE, "layout");
 }  // namespace s2
 
@@ -524,7 +538,6 @@ template <bool X3, int ROLE>
 __device__ __forceinline__ void run_role_s2(const HaloWgradArgs& a, const HaloWgradS2Tma& tm, uint8_t* smem, uint64_t* bars,
                                             uint32_t tmem) {
   using namespace s2;
-  constexpr int XT = ROLE == 0 ? XT0s : XT1s;
   constexpr int NPAIR = ROLE == 0 ? 3 : 2;
   uint64_t* t_full = bars;             // [NST]
   uint64_t* s_full = bars + NST;       // [NST]
@@ -619,49 +632,12 @@ __device__ __forceinline__ void run_role_s2(const HaloWgradArgs& a, const HaloWg
       if (tile + 1 == t_end) umma_commit(done, leader);
     }
   } else {
-    const int c16 = tid & 15, cb = c16 >> 3, ch = c16 & 7;
     long long it = 0;
     for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
       const int s = (int)(it % NST);
       mbar_wait(t_full + s, (uint32_t)((it / NST) & 1));
       const uint32_t a_hi = smem_u32(smem + s * STAGE2);
-      uint8_t* const stg = smem + s * STAGE2;
-      uint32_t xo[XT], yo[YT2];
-      float4 xv[XT], yv[YT2];
-#pragma unroll
-      for (int i = 0; i < XT; ++i) {
-        const int px = (tid + i * kSplitThreads) >> 4;
-        xo[i] = 0xffffffffu;
-        if (ROLE == 0) {
-          if (px < (RT2 + 1) * HW) {
-            const int hr = px / HW, pc = px - hr * HW;
-            xo[i] = swz((uint32_t)(hr * 2 + cb) * S_A + pc * 128, ch);
-          } else if (px < XP0) {
-            const int q = px - (RT2 + 1) * HW, hr = q / TW, pc = q - hr * TW;
-            xo[i] = swz(Q_BYTES + (uint32_t)(hr * 2 + cb) * S_B + pc * 128, ch);
-          }
-        } else if (px < XP1) {
-          const int blk = px / TW, pc = px - blk * TW;      // blk: E rows x copies (0..3), then Z rows (4..5)
-          if (blk < RT2 * 2) xo[i] = swz((uint32_t)((blk >> 1) * 4 + (blk & 1) * 2 + cb) * S_B + pc * 128, ch);
-          else xo[i] = swz(E_BYTES + (uint32_t)((blk - RT2 * 2) * 2 + cb) * S_B + pc * 128, ch);
-        }
-        if (xo[i] != 0xffffffffu) xv[i] = lds128(a_hi + xo[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < YT2; ++i) {
-        const int px = (tid + i * kSplitThreads) >> 4;
-        const int r = px / TW, pc = px - r * TW;
-        yo[i] = swz((uint32_t)(r * 4 + cb) * S_B + pc * 128, ch);
-        yv[i] = lds128(a_hi + 2 * A_PLANE + yo[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < XT; ++i)
-        if (xo[i] != 0xffffffffu) split_store(stg, stg + A_PLANE, xo[i], xv[i], X3);
-#pragma unroll
-      for (int i = 0; i < YT2; ++i) {
-        split_store(stg + 2 * A_PLANE, stg + 2 * A_PLANE + 2 * S_B, yo[i], yv[i], X3);
-        if (ROLE == 0) { dbs.x += yv[i].x; dbs.y += yv[i].y; dbs.z += yv[i].z; dbs.w += yv[i].w; }
-      }
+      split_sweep<X3, ROLE == 0>(a_hi, A_PLANE, (ROLE == 0 ? A_PLANE : E_BYTES + Z_BYTES) / 16, a_hi + 2 * A_PLANE, RT2, tid, dbs);
       fence_proxy_async();
       mbar_arrive_(s_full + s);
     }
@@ -671,7 +647,11 @@ __device__ __forceinline__ void run_role_s2(const HaloWgradArgs& a, const HaloWg
   __syncthreads();
   if (ROLE == 0 && a.part_db) {
     float* red = reinterpret_cast<float*>(smem);
-    if (tid < kSplitThreads) *reinterpret_cast<float4*>(red + (tid >> 4) * 64 + (tid & 15) * 4) = dbs;
+    if (tid < kSplitThreads) {
+      int channel, slot;
+      db_slot(tid, channel, slot);
+      *reinterpret_cast<float4*>(red + slot * 64 + channel) = dbs;
+    }
     __syncthreads();
     if (tid < 64) {
       float t = 0.f;

@@ -122,6 +122,21 @@ __device__ __forceinline__ float lo_part(float x, float hi) { return B200NP_LO_R
 __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// Split for operands that a TMA copy has already placed in shared memory as RAW fp32: the tensor core truncates its
+// fp32 operands to tf32 (finding 1), so the raw plane IS a valid `hi` operand (hi = trunc_tf32(x)); only the
+// remainder lo = x - trunc_tf32(x) has to be written (exact in fp32: it is the low 13 mantissa bits; the tensor core's
+// truncation of it leaves a residual <= 3 * 2^-23 |x|, against 2^-23 |x| for the round-to-nearest split).
+__device__ __forceinline__ float4 lo_of_truncated(float4 v) {
+  float4 l;
+  l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+  l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+  l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+  l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+  return l;
+}
+__device__ __forceinline__ float4 to_tf32_4(float4 v) {
+  return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+}
 __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v, bool x3) {
   float4 h;
   h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
