@@ -341,7 +341,8 @@ __device__ __forceinline__ void run_role_tma(const HaloWgradArgs& a, const HaloW
   uint64_t* s_empty = bars + 4;   // [2] the MMAs that read the stage retired (tcgen05.commit)
   uint64_t* done = bars + 6;      // all MMAs of the chunk retired
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = blockIdx.x;
+  const int chunk = blockIdx.x >> 1;   // the two roles of a chunk are neighbouring CTAs: they run at the same time, and
+                                       // the second reader of the chunk's x / dY pixels finds them in L2
   const int H = a.H, W = a.W;
   const int tiles_x = W / TW, tiles_img = tiles_x * (H / RT);
   const long long t_begin = chunk * a.per, t_end = t_begin + a.per < a.tiles ? t_begin + a.per : a.tiles;
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) tapwgrad_halo_tma_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (blockIdx.y == 0) run_role_tma<X3, 0>(a, tm, smem, bars, tmem);
+  if ((blockIdx.x & 1) == 0) run_role_tma<X3, 0>(a, tm, smem, bars, tmem);
   else run_role_tma<X3, 1>(a, tm, smem, bars, tmem);
   tc_fence_before();
   __syncthreads();
@@ -544,7 +545,7 @@ __device__ __forceinline__ void run_role_s2(const HaloWgradArgs& a, const HaloWg
   uint64_t* s_empty = bars + 2 * NST;  // [NST]
   uint64_t* done = bars + 3 * NST;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = blockIdx.x;
+  const int chunk = blockIdx.x >> 1;   // roles interleaved (see run_role_tma)
   const int H = a.H, W = a.W;          // dY geometry
   const int tiles_x = W / TW, tiles_img = tiles_x * (H / RT2);
   const long long t_begin = chunk * a.per, t_end = t_begin + a.per < a.tiles ? t_begin + a.per : a.tiles;
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) tapwgrad_halo_s2_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (blockIdx.y == 0) run_role_s2<X3, 0>(a, tm, smem, bars, tmem);
+  if ((blockIdx.x & 1) == 0) run_role_s2<X3, 0>(a, tm, smem, bars, tmem);
   else run_role_s2<X3, 1>(a, tm, smem, bars, tmem);
   tc_fence_before();
   __syncthreads();
@@ -733,7 +734,7 @@ int launch_s2(const HaloWgradArgs& h, int chunks, cudaStream_t st) {
       return B200NP_E_LAUNCH;
     configured = true;
   }
-  tapwgrad_halo_s2_kernel<X3><<<dim3(chunks, 2), kThreadsTma, smem, st>>>(h, tm);
+  tapwgrad_halo_s2_kernel<X3><<<2 * chunks, kThreadsTma, smem, st>>>(h, tm);
   return launch_status();
 }
 
@@ -764,7 +765,7 @@ int launch_tma(const HaloWgradArgs& h, int chunks, cudaStream_t st) {
       return B200NP_E_LAUNCH;
     configured = true;
   }
-  tapwgrad_halo_tma_kernel<X3><<<dim3(chunks, 2), kThreadsTma, smem, st>>>(h, tm);
+  tapwgrad_halo_tma_kernel<X3><<<2 * chunks, kThreadsTma, smem, st>>>(h, tm);
   return launch_status();
 }
 
