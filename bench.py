@@ -569,10 +569,18 @@ def hbm_bound_kernels(dev, T, nc, nt, n_params):
     return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at exactly the size
-# timed below, from `ncu --set full` of `bench.py --roofline-only` (profiles/ncu_tapwgrad_r1.txt,
-# profiles/ncu_tapconv_halo_r1.txt).
-NCU_TRAFFIC_BYTES = {"tapwgrad": 921.6e6, "tapconv_halo": 862.4e6}
+def ncu_traffic(key, images, precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of a roofline kernel, from profiles/ncu_traffic.json
+    (filled in from the committed `ncu --set full` captures of `bench.py --roofline-only`); None when the file is
+    missing or was captured at another size / precision -- a stale constant must not pass for a measurement."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("images") != images or t.get("precision") != precision:
+            return None
+        return float(t[key]["bytes"])
+    except Exception:
+        return None
 
 
 def _time_kernel(run, reps=10):
@@ -589,15 +597,16 @@ def _time_kernel(run, reps=10):
 
 
 def dominant_kernel_roofline(args, dev):
-    """Times the dominant kernel of the step alone, with CUDA events on the launching stream (torch's current
-    stream, which is the one the C ABI is given).  By CUPTI kernel time (profiles/profile_step_r1.txt) the
-    dominant kernel is the tcgen05 weight gradient `tapwgrad_umma_kernel` (28% of the step); it is timed on its
-    largest instance, the fused `conv2 3x3 + 1x1 s2 skip` weight gradient of layer1 at the step's own size
-    (all 1140 images of a 20-task ANP step: contraction over M = 1140*32*32 pixels, 64 x 640 outputs).
-    Algorithmic FLOPs = 2*M*64*640 per launch (75.5 + 8.4 MFLOP/image).
+    """Times the dominant kernels of the step alone, with CUDA events on the launching stream (torch's current
+    stream, which is the one the C ABI is given).  By CUPTI kernel time (profiles/profile_step_r2.txt) the dominant
+    kernel is the TMA-fed halo convolution `tapconv_halo_tma_kernel` (21 % of the step in its 10-tap instance alone, 39 %
+    over its three instances); it is timed on its largest instance, the fused `conv2 3x3 + 1x1 s2 skip + bias + ReLU`
+    forward of layer1 at the step's own size (all 1140 images of a 20-task ANP step: M = 1140*32*32 pixels, N = 64,
+    K = 640).  Algorithmic FLOPs = 2*M*64*640 per launch (75.5 + 8.4 MFLOP/image); algorithmic
+    HBM bytes = input h + every second pixel of every second row of x (the stride-2 skip) + the output.
     Peak = measured dense bf16 / 2 (tf32 issues at half the bf16 rate); the fp32-grade 3xTF32 split spends
-    3 MMAs per algorithmic MAC, so its ceiling on this scale is 1/3.  The forward kernel of the same layer
-    (`tapconv_halo_kernel`, second by time) is reported beside it."""
+    3 MMAs per algorithmic MAC, so its ceiling on this scale is 1/3.  The weight gradient of the same layer
+    (`tapwgrad_halo_tma_kernel`, second by time; round 1's dominant kernel) is reported beside it (`second_kernel`)."""
     from b200np import ops
     from b200np.lib import PREC_FP32_SIMT, PREC_TF32, PREC_TF32X3
     prec = {"tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "fp32": PREC_FP32_SIMT}[args.precision]
@@ -622,7 +631,8 @@ def dominant_kernel_roofline(args, dev):
         ach = flops / sec / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "peak_source": f"{pk['src']} bf16 burst {pk['bf16']} TFLOP/s / 2 (tf32 rate)",
-                "traffic": NCU_TRAFFIC_BYTES[key], "launch_ms": sec * 1e3,
+                "traffic": ncu_traffic(key, N, args.precision), "launch_ms": sec * 1e3,
+                "algorithmic_flop": flops,
                 "hbm_view": {"algorithmic_GB": alg_bytes / 1e9, "achieved_GBps": alg_bytes / sec / 1e9,
                              "peak_GBps": pk["hbm"], "frac": alg_bytes / sec / 1e9 / pk["hbm"]}}
 
@@ -631,10 +641,10 @@ def dominant_kernel_roofline(args, dev):
     else:
         t_w = _time_kernel(lambda: ops.conv_wgrad(h, dy, 3, 1, prec, skip=(x, 2)))
     t_f = _time_kernel(lambda: ops.conv_fwd(h, wf2, b, 1, 1, prec, skip=(x, wfs, b, 2)))
-    out = entry("tapwgrad_umma (layer1 conv2 3x3 + 1x1 skip weight gradient, pixel contraction on tcgen05)",
-                "tapwgrad", t_w)
-    out["second_kernel"] = entry("tapconv_halo (layer1 conv2 3x3 + 1x1 skip + bias + ReLU forward, implicit GEMM "
-                                 "on tcgen05)", "tapconv_halo", t_f)
+    out = entry("tapconv_halo_tma (layer1 conv2 3x3 + 1x1 skip + bias + ReLU forward, implicit GEMM on tcgen05, planes by "
+                "TMA tensor maps)", "tapconv_halo", t_f)
+    out["second_kernel"] = entry("tapwgrad_halo_tma (layer1 conv2 3x3 + 1x1 skip weight gradient, pixel contraction on "
+                                 "tcgen05, operands by TMA tensor maps)", "tapwgrad", t_w)
     return out
 
 

@@ -56,6 +56,7 @@ struct HaloWgradArgs {
   float* part_db;      // nullable: [chunks][64]
   int N, H, W, ntaps;  // ntaps = 9 or 10 (with skip)
   long long tiles, per;
+  int only_role;       // diagnostics (B200NP_WGRAD_ONLY_ROLE=0|1: time one role alone, results incomplete); -1 = both
 };
 
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo) {
@@ -341,8 +342,9 @@ __device__ __forceinline__ void run_role_tma(const HaloWgradArgs& a, const HaloW
   uint64_t* s_empty = bars + 4;   // [2] the MMAs that read the stage retired (tcgen05.commit)
   uint64_t* done = bars + 6;      // all MMAs of the chunk retired
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = blockIdx.x >> 1;   // the two roles of a chunk are neighbouring CTAs: they run at the same time, and
-                                       // the second reader of the chunk's x / dY pixels finds them in L2
+  const int chunk = blockIdx.x;        // roles are blockIdx.y: two successive waves (0.28 + 0.29 ms alone).  Interleaving
+                                       // the roles as neighbouring CTAs, so that the second reader of a chunk hits L2,
+                                       // was measured at 0.58 -> 0.92 ms and reverted.
   const int H = a.H, W = a.W;
   const int tiles_x = W / TW, tiles_img = tiles_x * (H / RT);
   const long long t_begin = chunk * a.per, t_end = t_begin + a.per < a.tiles ? t_begin + a.per : a.tiles;
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) tapwgrad_halo_tma_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if ((blockIdx.x & 1) == 0) run_role_tma<X3, 0>(a, tm, smem, bars, tmem);
+  if ((a.only_role < 0 ? (int)blockIdx.y : a.only_role) == 0) run_role_tma<X3, 0>(a, tm, smem, bars, tmem);
   else run_role_tma<X3, 1>(a, tm, smem, bars, tmem);
   tc_fence_before();
   __syncthreads();
@@ -545,7 +547,7 @@ __device__ __forceinline__ void run_role_s2(const HaloWgradArgs& a, const HaloWg
   uint64_t* s_empty = bars + 2 * NST;  // [NST]
   uint64_t* done = bars + 3 * NST;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = blockIdx.x >> 1;   // roles interleaved (see run_role_tma)
+  const int chunk = blockIdx.x;        // roles are blockIdx.y (see run_role_tma)
   const int H = a.H, W = a.W;          // dY geometry
   const int tiles_x = W / TW, tiles_img = tiles_x * (H / RT2);
   const long long t_begin = chunk * a.per, t_end = t_begin + a.per < a.tiles ? t_begin + a.per : a.tiles;
@@ -706,7 +708,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) tapwgrad_halo_s2_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if ((blockIdx.x & 1) == 0) run_role_s2<X3, 0>(a, tm, smem, bars, tmem);
+  if (blockIdx.y == 0) run_role_s2<X3, 0>(a, tm, smem, bars, tmem);
   else run_role_s2<X3, 1>(a, tm, smem, bars, tmem);
   tc_fence_before();
   __syncthreads();
@@ -734,7 +736,7 @@ int launch_s2(const HaloWgradArgs& h, int chunks, cudaStream_t st) {
       return B200NP_E_LAUNCH;
     configured = true;
   }
-  tapwgrad_halo_s2_kernel<X3><<<2 * chunks, kThreadsTma, smem, st>>>(h, tm);
+  tapwgrad_halo_s2_kernel<X3><<<dim3(chunks, 2), kThreadsTma, smem, st>>>(h, tm);
   return launch_status();
 }
 
@@ -765,7 +767,7 @@ int launch_tma(const HaloWgradArgs& h, int chunks, cudaStream_t st) {
       return B200NP_E_LAUNCH;
     configured = true;
   }
-  tapwgrad_halo_tma_kernel<X3><<<2 * chunks, kThreadsTma, smem, st>>>(h, tm);
+  tapwgrad_halo_tma_kernel<X3><<<dim3(chunks, h.only_role < 0 ? 2 : 1), kThreadsTma, smem, st>>>(h, tm);
   return launch_status();
 }
 
@@ -808,7 +810,7 @@ static int launch_tapwgrad_halo_s2(TapWgradArgs& a, int precision, cudaStream_t 
   HaloWgradArgs h{};
   h.x = a.src; h.dy = a.dy; h.xs = nullptr;
   h.part = a.part; h.part_db = a.part_db;
-  h.N = a.N; h.H = a.OH; h.W = a.OW; h.ntaps = 9;
+  h.N = a.N; h.H = a.OH; h.W = a.OW; h.ntaps = 9; h.only_role = -1;
   h.tiles = (long long)a.N * (a.OH / s2::RT2) * (a.OW / TW);
   h.per = ceil_div(h.tiles, kNumSMs);
   const int rc = precision == B200NP_PREC_TF32 ? launch_s2<false>(h, chunks, st) : launch_s2<true>(h, chunks, st);
@@ -834,6 +836,8 @@ int launch_tapwgrad_halo(TapWgradArgs& a, int precision, cudaStream_t st) {
   h.N = a.N; h.H = a.OH; h.W = a.OW; h.ntaps = a.ntaps;
   h.tiles = (long long)a.N * (a.OH / RT) * (a.OW / TW);
   h.per = ceil_div(h.tiles, kNumSMs);
+  static const int only_role = [] { const char* e = getenv("B200NP_WGRAD_ONLY_ROLE"); return (e && e[0]) ? atoi(e) : -1; }();
+  h.only_role = only_role;
   a.chunks = chunks;
   if (wgrad_tma_enabled()) {
     const int rc = precision == B200NP_PREC_TF32 ? launch_tma<false>(h, chunks, st) : launch_tma<true>(h, chunks, st);
