@@ -808,6 +808,378 @@ __global__ void __launch_bounds__(kThreadsTma, 1) tapconv_halo_tma_kernel(const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// 2-SM variant: a CTA PAIR (thread-block cluster of two, one per SM of a TPC) works on two tiles with ONE
+// tcgen05.mma.cta_group::2 stream: M = 256 (128 pixels from each CTA's own planes), the B operand -- the stacked
+// [W_hi ; W_lo] weight K-block -- split along N between the two CTAs.  Per SM that halves the weight-ring fill
+// (8 KB instead of 16 KB per K-block) and the tensor core's B-operand reads, the two largest items of the L1 data
+// pipe budget after the A reads (DESIGN.md finding 17).  Loaders, split warps and epilogue are per CTA and unchanged;
+// the leader CTA's MMA warp issues for the pair, the peer's forwards its barrier completions to the leader
+// (remote mbarrier arrives), and every tcgen05.commit is multicast to the same barrier in both CTAs.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `target` of the cluster (`issue`: lane predicate)
+__device__ __forceinline__ void remote_arrive(uint64_t* local_bar, uint32_t target, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b32 ra;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "@q mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(local_bar)), "r"(target), "r"(issue)
+      : "memory");
+}
+// wait for an arrival that came from the peer CTA.  Plain CTA-scope wait, as CUTLASS's ClusterBarrier does: what the
+// arrival orders is read by the PEER's tensor core from the peer's own shared memory, not by this CTA's threads (a
+// cluster-scope acquire here costs an L1 invalidation per wait: the first version of this kernel ran at half speed)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0xffffu) == 0) {
+      uint64_t t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 20000000000ull) __trap();
+    }
+  }
+}
+
+template <bool X3, int NT, int NB, bool DBG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTma, 1) tapconv_halo_tma2_kernel(const HaloArgs h, const __grid_constant__ HaloTma tm) {
+  constexpr uint32_t kBSlot = b_slot_bytes<X3>();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + h.bar_off);
+  uint64_t* a_full = bars;                  // [a_stages] split warps -> MMA          (count 256)
+  uint64_t* a_empty = bars + 2;             // [a_stages] MMA commit -> plane loader  (count 1)
+  uint64_t* acc_full = bars + 4;            // [4] MMA commit -> epilogue             (count 1)
+  uint64_t* acc_empty = bars + 8;           // [4] epilogue -> MMA                    (count 128)
+  uint64_t* b_full = bars + 12;             // [nb] bulk copy tx -> MMA               (count 1 + tx)
+  uint64_t* b_empty = b_full + kMaxBStages; // [nb] MMA commit -> weight warp         (count 1)
+  uint64_t* t_full = b_empty + kMaxBStages; // [a_stages] tensor copies tx -> split warps, MMA (count 1 + tx)
+  uint64_t* p_afull = t_full + 2;           // leader only, [a_stages]: the PEER's stage is ready        (count 1, relayed)
+  uint64_t* p_accempty = p_afull + 2;       // leader only, [4]: the PEER's epilogue has drained the set     (count 1, relayed)
+  uint64_t* p_bfull = p_accempty + 4;       // leader only, [nb]: the PEER's half of the weight slot landed (count 1, relayed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_bfull + kMaxBStages);
+  const int nb = h.nb, a_stages = h.a_stages;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+
+  const TapConvArgs& a = h.t;
+  const int dflags = DBG ? h.dbg_flags : 0;
+  long long* const dbgp = DBG ? h.dbg : nullptr;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t kAccCols = X3 ? 256u : 128u;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
+  constexpr uint32_t kBlkCols = X3 ? 128u : 64u;
+  const int ncls = h.ncls;
+
+  if (tid == 0) {
+    for (int s = 0; s < a_stages; ++s) {
+      mbar_init(a_full + s, kProducerThreads);
+      mbar_init(a_empty + s, 1);
+      mbar_init(t_full + s, 1);
+    }
+    for (int s = 0; s < nb; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 128); mbar_init(p_accempty + s, 1); }
+    for (int s = 0; s < 2; ++s) mbar_init(p_afull + s, 1);
+    for (int s = 0; s < nb; ++s) mbar_init(p_bfull + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWeightWarp) {
+    // one warp of EACH CTA of the pair, same warp index, same destination offset (cute::TMEM::Allocator2Sm)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    for (int p = 0; p < h.nplanes; ++p) tma::prefetch_map(&tm.plane[p]);
+  }
+  tc_fence_before();
+  cluster_sync_all();        // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kProducerWarps) {
+    // ===================== split warps: smem -> smem =====================
+    Ring st;
+    const uint32_t units = (uint32_t)h.total_slots * 8u;      // 16-byte units of one plane copy
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x)
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(t_full + st.idx, st.phase);                  // the tensor copies of this stage have landed
+        const uint32_t hi = smem_u32(smem + st.idx * h.stage_bytes), lo = hi + h.plane_bytes;
+        for (uint32_t u0 = tid; u0 < units; u0 += 4 * kProducerThreads) {
+          float4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t u = u0 + j * kProducerThreads;
+            if (u < units) v[j] = lds128(hi + u * 16u);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t u = u0 + j * kProducerThreads;
+            if (u < units) {
+              if (X3) sts128(lo + u * 16u, lo_of_truncated(v[j]));   // the raw plane is the hi operand (hardware truncation)
+              else sts128(hi + u * 16u, to_tf32_4(v[j]));            // single pass: round to nearest in place
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(a_full + st.idx);
+        st.advance(a_stages);
+      }
+  } else if (warp == kTmaWarp) {
+    // ===================== plane loader (TMA) =====================
+    const uint32_t leader = elect_one_sync();
+    Ring st;
+    uint32_t stage_tx = 0;
+    for (int p = 0; p < h.nplanes; ++p) stage_tx += (uint32_t)(h.pl[p].HR * h.pl[p].HC) * 128u;
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x) {
+      const int xt = tile % h.tiles_x, rb = tile / h.tiles_x;
+      const int r0 = rb * kTileRows;
+      const int n = r0 / a.OH, oy0 = r0 - n * a.OH, ox0 = xt * kTileCols;
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(a_empty + st.idx, st.phase ^ 1);             // the MMAs that read this stage have retired
+        if (leader) mbar_expect_tx(t_full + st.idx, stage_tx);
+        const uint32_t stage = smem_u32(smem + st.idx * h.stage_bytes);
+        for (int p = 0; p < h.nplanes; ++p)
+          tma::load_4d(stage + (uint32_t)h.pl[p].slot0 * 128u, &tm.plane[p], smem_u32(t_full + st.idx), half * 32,
+                       ox0 + h.pl[p].dx_min, oy0 + h.pl[p].dy_min, n, leader);
+        st.advance(a_stages);
+      }
+    }
+  } else if (warp == kWeightWarp) {
+    // ===================== weight producer =====================
+    const bool leader = elect_one_sync();
+    Ring bs;
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x)
+      for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const Tap tp = a.taps[t];
+          // this CTA's half of the B operand: fp32-grade  rank 0 = W_hi (rows 0-63 of [W_hi ; W_lo]), rank 1 = W_lo;
+          // single pass  rows 32 r .. 32 r + 31 of W_hi (K-major SWIZZLE_128B tile: 1024 B per 8 rows)
+          const float* src = h.bp[tp.src] + ((long long)half * h.nslabs[tp.src] + tp.slab) * (kBSlotBytes / 4) +
+                             cta_rank * (kBSlot / 8);
+          mbar_wait(b_empty + bs.idx, bs.phase ^ 1);
+          if (leader) {
+            mbar_expect_tx(b_full + bs.idx, kBSlot / 2);
+            bulk_g2s(smem + h.b_off + bs.idx * kBSlot, src, kBSlot / 2, b_full + bs.idx);
+          }
+          bs.advance(nb);
+        }
+  } else if (warp == kMmaWarp && cta_rank != 0 && (h.dbg_flags & 256)) {
+    // diagnostics: no relay (results undefined)
+  } else if (warp == kMmaWarp && cta_rank != 0) {
+    // ===================== peer CTA: relay =====================
+    // The leader issues the pair's MMAs, so it must know when THIS CTA's operands and accumulators are ready.  This
+    // warp waits on the local barriers in exactly the order the leader consumes them and forwards each completion to
+    // the leader's p_* barrier of the same index (remote mbarrier arrive, cluster scope).
+    static_assert((2 * NT) % NB == 0, "ring depth must divide the K-blocks of a tile");
+    constexpr uint32_t kWraps = 2 * NT / NB;
+    const uint32_t leader = elect_one_sync();
+    int acc_set = 0;
+    uint32_t acc_phase = 0, cphase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x, ++it) {
+      if (ncls == 1) {
+        mbar_wait(acc_empty + acc_set, acc_phase ^ 1);
+        remote_arrive(p_accempty + acc_set, 0, leader);
+      }
+      const uint32_t ring_par0 = it * kWraps;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t sidx = a_stages == 2 ? (uint32_t)half : 0u;
+        const uint32_t spar = a_stages == 2 ? (it & 1u) : ((2u * it + half) & 1u);
+        mbar_wait(t_full + sidx, spar);
+        mbar_wait(a_full + sidx, spar);
+        remote_arrive(p_afull + sidx, 0, leader);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int kb = half * NT + t;
+          const uint32_t slot = (uint32_t)(kb % NB), pass = (uint32_t)(kb / NB);
+          if (ncls > 1) {
+            const int cls = h.tap_cls[t];
+            const bool cls_first = t == 0 || h.tap_cls[t > 0 ? t - 1 : 0] != cls;
+            if (half == 0 && cls_first) {
+              mbar_wait(acc_empty + cls, cphase ^ 1);
+              remote_arrive(p_accempty + cls, 0, leader);
+            }
+          }
+          mbar_wait(b_full + slot, (ring_par0 + pass) & 1u);
+          remote_arrive(p_bfull + slot, 0, leader);
+        }
+      }
+      if (ncls == 1) {
+        if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
+      } else {
+        cphase ^= 1;
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== leader CTA: MMA issuer for the pair (tcgen05.mma.cta_group::2) =====================
+    // M = 256: rows 0-127 are the leader's tile, rows 128-255 the peer's (each from its own shared memory, same
+    // descriptor); N = 128 = [W_hi ; W_lo], rows 0-63 in the leader's weight slot, 64-127 in the peer's: each CTA fills
+    // and its tensor core reads HALF of every weight K-block.  fp32-grade: A_hi x [W_hi ; W_lo] and A_lo x [W_hi ; W_lo]
+    // into the SAME 128 columns (columns 0-63 collect hi*hi + lo*hi, 64-127 hi*lo + lo*lo; the epilogue adds the halves
+    // as before) -- both instructions take the same B descriptor, which is what lets the N split work for both.
+    static_assert((2 * NT) % NB == 0, "ring depth must divide the K-blocks of a tile");
+    constexpr uint32_t kWraps = 2 * NT / NB;
+    const uint32_t leader = elect_one_sync();
+    int acc_set = 0;
+    uint32_t acc_phase = 0, cphase = 0;
+    const uint32_t plane16 = h.plane_bytes >> 4;
+    const uint32_t lbo_bits = 1u << 16;
+    const uint32_t b_hi_word = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t b_base16 = ((smem_u32(smem + h.b_off) & 0x3FFFFu) >> 4) | lbo_bits;
+    const uint32_t smem16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
+    const uint32_t stage16_step = h.stage_bytes >> 4;
+    const uint32_t b_full_a = smem_u32(b_full), b_empty_a = smem_u32(b_empty);
+    constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (((X3 ? 128u : 64u) >> 3) << 17) | ((256u >> 4) << 24);
+    uint32_t a_off16[NT], a_hiw[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      a_off16[t] = (uint32_t)h.tap_off[t] * 8u;
+      a_hiw[t] = (((uint32_t)h.tap_hc[t] * 128u) >> 4) | (1u << 14) | (2u << 29);
+    }
+    auto mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t acc) {
+      asm volatile(
+          "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+          "mov.b64 da, {%1, %2};\n\t"
+          "mov.b64 db, {%3, %4};\n\t"
+          "setp.ne.b32 p, %6, 0;\n\t"
+          "setp.ne.b32 q, %7, 0;\n\t"
+          "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}"
+          ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi_word), "r"(kIdesc2), "r"(acc), "r"(leader)
+          : "memory");
+    };
+    auto commit2 = [&](uint32_t bar_addr) {   // arrives on the barrier at this offset in BOTH CTAs
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+          "setp.ne.b32 q, %1, 0;\n\t"
+          "mov.b16 m, 3;\n\t"
+          "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+          ::"r"(bar_addr), "r"(leader)
+          : "memory");
+    };
+    auto probe = [&](uint32_t bar_addr, uint32_t parity) -> bool {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity)
+          : "memory");
+      return ok != 0;
+    };
+    bool b_ready = false;
+    const bool norelay = (h.dbg_flags & 256) != 0;           // diagnostics: do not wait for the peer (results undefined)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < h.tiles_total; tile += gridDim.x, ++it) {
+      if (ncls == 1) {
+        mbar_wait(acc_empty + acc_set, acc_phase ^ 1);       // own epilogue has drained this set ...
+        if (!norelay) mbar_wait_cluster(p_accempty + acc_set, acc_phase);  // ... and so has the peer's
+        tc_fence_after();
+      }
+      const uint32_t d0 = tmem_base + acc_set * kAccCols;
+      const uint32_t ring_par0 = it * kWraps;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t sidx = a_stages == 2 ? (uint32_t)half : 0u;
+        const uint32_t spar = a_stages == 2 ? (it & 1u) : ((2u * it + half) & 1u);
+        mbar_wait(t_full + sidx, spar);
+        mbar_wait(a_full + sidx, spar);
+        if (!norelay) mbar_wait_cluster(p_afull + sidx, spar);
+        const uint32_t stage16 = (smem16 + sidx * stage16_step) | lbo_bits;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int kb = half * NT + t;
+          const uint32_t slot = (uint32_t)(kb % NB), pass = (uint32_t)(kb / NB);
+          const uint32_t kbn = (uint32_t)((kb + 1) % (2 * NT));
+          const uint32_t slot_n = kbn % NB, pass_n = kbn / NB + (kb + 1 == 2 * NT ? kWraps : 0u);
+          uint32_t d_blk = d0 + (uint32_t)(kb % kRot) * kBlkCols;
+          uint32_t acc_first = kb >= kRot;
+          int cls = 0;
+          bool cls_last = false;
+          if (ncls > 1) {
+            cls = h.tap_cls[t];
+            const bool cls_first = t == 0 || h.tap_cls[t > 0 ? t - 1 : 0] != cls;
+            cls_last = t == NT - 1 || h.tap_cls[t < NT - 1 ? t + 1 : t] != cls;
+            if (half == 0 && cls_first) {
+              mbar_wait(acc_empty + cls, cphase ^ 1);
+              if (!norelay) mbar_wait_cluster(p_accempty + cls, cphase);
+              tc_fence_after();
+            }
+            d_blk = tmem_base + cls * kBlkCols;
+            acc_first = !(half == 0 && cls_first);
+          }
+          if (!b_ready) {
+            mbar_wait(b_full + slot, (ring_par0 + pass) & 1u);
+            if (!norelay) mbar_wait_cluster(p_bfull + slot, (ring_par0 + pass) & 1u);
+          }
+          {   // probe the NEXT slot in both CTAs now, use the answer after these MMAs
+            const bool own = probe(b_full_a + slot_n * 8u, (ring_par0 + pass_n) & 1u);
+            const bool peer = norelay || probe(smem_u32(p_bfull) + slot_n * 8u, (ring_par0 + pass_n) & 1u);
+            b_ready = own && peer;
+          }
+          const uint32_t ah = stage16 + a_off16[t], al = ah + plane16;
+          const uint32_t bh = b_base16 + slot * (kBSlot >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma(d_blk, ah + 2 * k, a_hiw[t], bh + 2 * k, k == 0 ? acc_first : 1u);
+          if (X3 && !(h.dbg_flags & 512)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma(d_blk, al + 2 * k, a_hiw[t], bh + 2 * k, 1u);
+          }
+          commit2(b_empty_a + slot * 8u);
+          if (ncls > 1 && half == 1 && cls_last) commit2(smem_u32(acc_full + cls));
+        }
+        commit2(smem_u32(a_empty + sidx));
+      }
+      if (ncls == 1) {
+        commit2(smem_u32(acc_full + acc_set));
+        if (++acc_set == 2) { acc_set = 0; acc_phase ^= 1; }
+      } else {
+        cphase ^= 1;
+      }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+    halo_epilogue<X3, DBG>(h, acc_full, acc_empty, tmem_base, warp, lane, dflags, dbgp);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();        // the pair's MMAs and multicast commits touch both CTAs: leave together
+  if (warp == kWeightWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <bool X3, int NT, int NB>
+int launch_halo_tma2_t(const HaloArgs& h, const HaloTma& tm, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(tapconv_halo_tma2_kernel<X3, NT, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+      return B200NP_E_LAUNCH;
+    configured = smem;
+  }
+  int grid = (h.tiles_total < kNumSMs ? h.tiles_total : kNumSMs) & ~1;   // whole CTA pairs
+  tapconv_halo_tma2_kernel<X3, NT, NB, false><<<grid, kThreadsTma, smem, st>>>(h, tm);
+  return launch_status();
+}
+
 template <bool X3, int NT, int NB>
 int launch_halo_tma_t(const HaloArgs& h, const HaloTma& tm, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
@@ -842,6 +1214,12 @@ int launch_halo_t(const HaloArgs& h, size_t smem, cudaStream_t st) {
 // B200NP_HALO_TMA=0 keeps the register-staged kernel (the TMA-fed one is the default where its tensor maps can be built)
 static bool halo_tma_enabled() {
   static const bool on = [] { const char* e = getenv("B200NP_HALO_TMA"); return e ? e[0] != '0' : true; }();
+  return on;
+}
+
+// B200NP_HALO_CG2=1 selects the 2-SM (cta_group::2) form of the TMA-fed kernel
+static bool halo_cg2_enabled() {
+  static const bool on = [] { const char* e = getenv("B200NP_HALO_CG2"); return (e && e[0]) ? e[0] != '0' : false; }();
   return on;
 }
 
@@ -885,7 +1263,7 @@ int launch_halo(HaloArgs& h, cudaStream_t st) {
   h.bar_off = h.b_off + nb * bslot;
   const size_t smem = h.bar_off + tail;
   const int tasks = (h.total_slots + kSlotsPerPass - 1) / kSlotsPerPass;
-  if (halo_tma_enabled() && !h.dbg && !h.dbg_flags && (h.t.ntaps == 9 || h.t.ntaps == 10)) {
+  if (halo_tma_enabled() && !h.dbg && !(h.dbg_flags & 255) && (h.t.ntaps == 9 || h.t.ntaps == 10)) {
     // the TMA-fed kernel wants a weight ring whose depth divides the 2 * ntaps K-blocks of a tile (compile-time slots)
     const int want = h.t.ntaps == 10 ? 4 : (nb >= 6 ? 6 : 3);
     HaloTma tm;
@@ -893,6 +1271,10 @@ int launch_halo(HaloArgs& h, cudaStream_t st) {
       h.nb = want;
       h.bar_off = h.b_off + want * bslot;
       const size_t smem_t = h.bar_off + tail;
+      if (halo_cg2_enabled() && h.tiles_total >= 2 && !(h.tiles_total & 1)) {   // CTA pairs (2-SM MMA)
+        if (h.t.ntaps == 10) return launch_halo_tma2_t<X3, 10, 4>(h, tm, smem_t, st);
+        return want == 6 ? launch_halo_tma2_t<X3, 9, 6>(h, tm, smem_t, st) : launch_halo_tma2_t<X3, 9, 3>(h, tm, smem_t, st);
+      }
       if (h.t.ntaps == 10) return launch_halo_tma_t<X3, 10, 4>(h, tm, smem_t, st);
       return want == 6 ? launch_halo_tma_t<X3, 9, 6>(h, tm, smem_t, st) : launch_halo_tma_t<X3, 9, 3>(h, tm, smem_t, st);
     }
