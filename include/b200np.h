@@ -243,6 +243,7 @@ int b200np_reduce(const float* x, long long n, float* out, int op, void* stream)
  * backward; out [T,nt,d,H] (feature-major, head-minor: the order `_W` consumes,
  * networks/ANPDistractor.py:98-99).  g = device scalar holding the (all-reduced) key max.
  * ties (device float, accumulated) counts elements of W equal to g (torch.max() tie rule). */
+/* nt * nc <= 1024 (the training and evaluation shapes reach 36 x 25 = 900); larger tiles return B200NP_E_UNSUPPORTED. */
 int b200np_favor_attn_fwd(const float* U, const float* W, const float* sq, const float* mq,
                           const float* tk, const float* g, const float* v, float* out, float* A,
                           float* Dn, float* ties, int T, int H, int nt, int nc, int d, int M,

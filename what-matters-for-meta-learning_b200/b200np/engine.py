@@ -34,6 +34,25 @@ def _p(t, off=0):
     return t.data_ptr() + 4 * off
 
 
+# NVTX ranges around the segments of the step (B200NP_NVTX=1): names show up in Nsight Systems / ncu --nvtx timelines
+# next to the kernels of each segment.  Off by default: a push/pop pair per segment costs ~1 us of host time.
+NVTX = os.environ.get("B200NP_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 # The decoder's CNN (networks/models.py:160-180) depends on the target images only, so it runs on a second stream
 # beside the encoder CNN / attention / MLP chain of the main stream and joins where `fc_mu` consumes it.  Autograd runs
 # each backward node on its forward stream, so the two trunks' backward passes overlap the same way; inside a captured
@@ -71,6 +90,11 @@ def _side_stream(key, priority=0):
 class TrunkFn(Function):
     @staticmethod
     def forward(ctx, img_agg, prec, n_src, *tensors):
+        with nvtx_range("b200np.trunk.forward"):
+            return TrunkFn._forward(ctx, img_agg, prec, n_src, *tensors)
+
+    @staticmethod
+    def _forward(ctx, img_agg, prec, n_src, *tensors):
         imgs, params = tensors[:n_src], tensors[n_src:]
         assert len(params) == 26
         if img_agg not in ("max", "baco", "reshape"):
@@ -122,6 +146,11 @@ class TrunkFn(Function):
 
     @staticmethod
     def backward(ctx, *douts):
+        with nvtx_range("b200np.trunk.backward"):
+            return TrunkFn._backward(ctx, *douts)
+
+    @staticmethod
+    def _backward(ctx, *douts):
         prec, Ns = ctx.prec, ctx.Ns
         y_last = ctx.acts[3][2]
         dy = torch.empty_like(y_last)
@@ -405,6 +434,11 @@ class FavorAttentionFn(Function):
 
     @staticmethod
     def forward(ctx, prec, T, H, nt, nc, xq, xk, v, proj):
+        with nvtx_range("b200np.favor.forward"):
+            return FavorAttentionFn._forward(ctx, prec, T, H, nt, nc, xq, xk, v, proj)
+
+    @staticmethod
+    def _forward(ctx, prec, T, H, nt, nc, xq, xk, v, proj):
         if prec == PREC_TF32:
             prec = PREC_TF32X3  # the feature pre-activations go through exp(): always fp32-grade
         xq, xk, v = xq.contiguous(), xk.contiguous(), v.contiguous()
@@ -613,6 +647,7 @@ def _forward_shapenet1d_family(m, ctx_x, ctx_y, tgt_x):
 
 def forward(model, ctx_x, ctx_y, tgt_x):
     _check_inputs(model, ctx_x, ctx_y, tgt_x)
-    if model.family == "resnet":
-        return _forward_resnet_family(model, ctx_x, ctx_y, tgt_x)
-    return _forward_shapenet1d_family(model, ctx_x, ctx_y, tgt_x)
+    with nvtx_range(f"b200np.forward[{type(model).__name__}]"):
+        if model.family == "resnet":
+            return _forward_resnet_family(model, ctx_x, ctx_y, tgt_x)
+        return _forward_shapenet1d_family(model, ctx_x, ctx_y, tgt_x)

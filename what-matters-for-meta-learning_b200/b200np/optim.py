@@ -80,6 +80,11 @@ class FusedAdam:
         self.flat.zero_grad()
 
     def step(self):
+        from .engine import nvtx_range
+        with nvtx_range("b200np.adam.step"):
+            self._step()
+
+    def _step(self):
         f = self.flat
         f.gather_grads()
         world = dist.world_size()

@@ -327,7 +327,7 @@ size_t bwd_smem(int nt, int nc, int d) {
   return (size_t)((nt + nc) * PITCH + (nt + nc) * (d + 1) + 2 * nt * nc + 4 * nt + nc + 4 * (nt + nc)) * sizeof(float);
 }
 bool dims_ok(int T, int H, int nt, int nc, int d, int M, long long ldu) {
-  return T > 0 && H > 0 && nt > 0 && nc > 0 && d > 0 && M > 0 && ldu >= M && nt * nc <= 1024;
+  return T > 0 && H > 0 && nt > 0 && nc > 0 && d > 0 && M > 0 && ldu >= M;
 }
 
 }  // namespace
@@ -351,6 +351,7 @@ extern "C" int b200np_favor_attn_fwd(const float* U, const float* W, const float
                                      long long ldu, void* stream) {
   if (!U || !W || !sq || !mq || !tk || !g || !v || !out || !A || !Dn || !ties) return B200NP_E_BADARG;
   if (!dims_ok(T, H, nt, nc, d, M, ldu)) return B200NP_E_BADARG;
+  if (nt * nc > 1024) return B200NP_E_UNSUPPORTED;   // the 4 x 256 accumulator layout of the A = Q'K'^T tile (evaluation: 36 x 25 = 900)
   size_t smem = fwd_smem(nt, nc);
   if (smem > 220 * 1024) return B200NP_E_UNSUPPORTED;
   if (smem > 48 * 1024 &&
@@ -370,6 +371,7 @@ extern "C" int b200np_favor_attn_bwd(const float* d_out, const float* U, const f
       !ds_c2 || !dt_c2 || !dg_part)
     return B200NP_E_BADARG;
   if (!dims_ok(T, H, nt, nc, d, M, ldu)) return B200NP_E_BADARG;
+  if (nt * nc > 1024) return B200NP_E_UNSUPPORTED;   // the 4 x 256 accumulator layout of the A = Q'K'^T tile (evaluation: 36 x 25 = 900)
   size_t smem = bwd_smem(nt, nc, d);
   if (smem > 220 * 1024) return B200NP_E_UNSUPPORTED;
   if (smem > 48 * 1024 &&
