@@ -297,6 +297,26 @@ def test_losses_against_reference_golden(task, kind, golden):
         assert abs(float(lt) - ref_t) < 1e-4 * abs(ref_t)
 
 
+@pytest.mark.parametrize("kind", [0, 2])
+@pytest.mark.parametrize("R,L", [(40000, 2), (40001, 2), (33333, 3), (3_000_001, 2)])
+def test_loss_large_batches(kind, R, L):
+    """Beyond 16384 rows the loss runs multi-block (last-block reduction); two-wide labels take the 16-byte form with an
+    odd tail row, wider labels the scalar-row form.  Reference: trainer/losses.py:35-36 (distractor), :59-61 (azimuth)."""
+    ops = _ops()
+    mu = rnd(R, 2, seed=5).float().cuda()
+    y = rnd(R, L, seed=6).float().cuda()
+    for _ in range(2):  # the ticket counter must be re-armed by the first call
+        loss, dmu = ops.loss_fwd_bwd(mu, y, kind)
+    m64 = mu.double().requires_grad_()
+    e = y[:, :2].double() - m64
+    ref = e.norm(dim=1).mean() if kind == 0 else (e * e).sum(1).mean()
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 2e-6 * abs(float(ref))
+    assert rel(dmu, m64.grad) < 1e-6
+    lo, none = ops.loss_fwd_bwd(mu, y, kind, want_grad=False)
+    assert none is None and abs(float(lo) - float(ref)) < 2e-6 * abs(float(ref))
+
+
 def test_adam_matches_torch():
     ops = _ops()
     n = 10007

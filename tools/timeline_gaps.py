@@ -36,12 +36,18 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 
 ev = []
+streams = {}
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA and "Memcpy" not in e.name and "Memset" not in e.name:
         t0 = e.time_range.start
         ev.append((t0, t0 + (e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total),
                    e.name.replace("b200np::<unnamed>::", "").replace("(anonymous namespace)::", "").replace("void ", "")[:70]))
+        streams[(t0, ev[-1][2])] = getattr(e, "device_resource_id", -1)
 ev.sort()
+if os.environ.get("TIMELINE_TRACE"):   # chronological listing: start (us from the first kernel), duration, stream, name
+    with open(os.environ["TIMELINE_TRACE"], "w") as fh:
+        for s_, e_, k_ in ev:
+            fh.write(f"{s_ - ev[0][0]:9.1f} {e_ - s_:8.1f} s{streams.get((s_, k_), -1)} {k_}\n")
 t_begin, t_end = ev[0][0], max(e[1] for e in ev)
 span = t_end - t_begin
 # sweep: time with 0 / 1 / >= 2 kernels in flight; solo time per kernel name

@@ -538,6 +538,21 @@ __global__ void loss_kernel(const float* __restrict__ mu, const float* __restric
 constexpr int kLossBlocks = 4 * kNumSMs;
 __device__ float g_loss_part[kLossBlocks];
 __device__ unsigned int g_loss_ticket = 0;
+__device__ __forceinline__ void loss_finish(float acc, float* red, bool* last, float* __restrict__ loss, float invR) {
+  float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    g_loss_part[blockIdx.x] = tot;
+    __threadfence();
+    *last = atomicAdd(&g_loss_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!*last) return;
+  __threadfence();
+  float s = 0.f;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(g_loss_part + b);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) { loss[0] = s * invR; g_loss_ticket = 0; }
+}
 __global__ void __launch_bounds__(256) loss_multi_kernel(const float* __restrict__ mu, const float* __restrict__ y,
                                                          float* __restrict__ loss, float* __restrict__ dmu, long long R,
                                                          int out, int L, int kind) {
@@ -548,19 +563,35 @@ __global__ void __launch_bounds__(256) loss_multi_kernel(const float* __restrict
   const long long st = (long long)gridDim.x * blockDim.x;
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += st)
     acc += loss_row(mu + r * out, y + r * L, dmu ? dmu + r * out : nullptr, L, kind, invR);
-  float tot = block_sum(acc, red);
-  if (threadIdx.x == 0) {
-    g_loss_part[blockIdx.x] = tot;
-    __threadfence();
-    last = atomicAdd(&g_loss_ticket, 1u) == gridDim.x - 1;
+  loss_finish(acc, red, &last, loss, invR);
+}
+// Two-wide rows with two-wide labels (distractor / azimuth with L = 2): a thread takes TWO consecutive rows, so every
+// access is 16 bytes and a warp instruction covers 512 contiguous bytes (the scalar-row form reaches 64 % of the HBM peak).
+__global__ void __launch_bounds__(256) loss_multi_vec_kernel(const float* __restrict__ mu, const float* __restrict__ y,
+                                                             float* __restrict__ loss, float* __restrict__ dmu, long long R,
+                                                             int kind) {
+  __shared__ float red[32];
+  __shared__ bool last;
+  float acc = 0.f;
+  const float invR = 1.f / (float)R;
+  const long long st = (long long)gridDim.x * blockDim.x, pairs = R >> 1;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < pairs; q += st) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + q), t = __ldg(reinterpret_cast<const float4*>(y) + q);
+    const float a0 = t.x - m.x, a1 = t.y - m.y, b0 = t.z - m.z, b1 = t.w - m.w;
+    float4 d;
+    if (kind == 0) {
+      const float na = sqrtf(a0 * a0 + a1 * a1), nb = sqrtf(b0 * b0 + b1 * b1);
+      acc += na + nb;
+      d = make_float4(-a0 / na * invR, -a1 / na * invR, -b0 / nb * invR, -b1 / nb * invR);
+    } else {
+      acc += a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1;
+      d = make_float4(-2.f * a0 * invR, -2.f * a1 * invR, -2.f * b0 * invR, -2.f * b1 * invR);
+    }
+    if (dmu) reinterpret_cast<float4*>(dmu)[q] = d;
   }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  float s = 0.f;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(g_loss_part + b);
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) { loss[0] = s * invR; g_loss_ticket = 0; }
+  if ((R & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+    acc += loss_row(mu + (R - 1) * 2, y + (R - 1) * 2, dmu ? dmu + (R - 1) * 2 : nullptr, 2, kind, invR);
+  loss_finish(acc, red, &last, loss, invR);
 }
 extern "C" int b200np_loss_fwd_bwd(const float* mu, const float* y, float* loss, float* dmu, long long R,
                                    int out, int L, int kind, void* stream) {
@@ -573,7 +604,10 @@ extern "C" int b200np_loss_fwd_bwd(const float* mu, const float* y, float* loss,
   if (R > 16384) {
     long long blocks = ceil_div(R, 256 * 4);
     if (blocks > kLossBlocks) blocks = kLossBlocks;
-    loss_multi_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(mu, y, loss, dmu, R, out, L, kind);
+    if ((kind == 0 || kind == 2) && L == 2 && aligned16(mu) && aligned16(y) && (!dmu || aligned16(dmu)))
+      loss_multi_vec_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(mu, y, loss, dmu, R, kind);
+    else
+      loss_multi_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(mu, y, loss, dmu, R, out, L, kind);
     return launch_status();
   }
   loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(mu, y, loss, dmu, R, out, L, kind);
