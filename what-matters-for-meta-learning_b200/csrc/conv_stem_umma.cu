@@ -14,6 +14,8 @@
 //   wgrad    A = [dY_hi ; dY_lo] stacked along M, B = [Xcol_hi | Xcol_lo] stacked along N: ONE M=128, N=64
 //            MMA per 8 pixels yields all four products; the epilogue adds the quadrants.  K index 25 of
 //            Xcol is a constant 1, so column 25 of the result is the bias gradient.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -381,7 +383,13 @@ __global__ void __launch_bounds__(128, 4)
 }
 
 int stem_wgrad_chunks(long long M) {
-  long long want = 8LL * kNumSMs, maxc = ceil_div(M, 64);
+  // CTAs per SM over the whole launch (4 are resident at a time); every CTA leaves a 16 KB partial for the reducer
+  static const int per_sm = [] {
+    const char* e = getenv("B200NP_STEM_WGRAD_CTAS");
+    const int v = (e && e[0]) ? atoi(e) : 4;   // one resident wave; 8: +38 us per step in reducer traffic, 2: tail
+    return v >= 1 && v <= 32 ? v : 4;
+  }();
+  long long want = (long long)per_sm * kNumSMs, maxc = ceil_div(M, 64);
   if (want > maxc) want = maxc;
   return (int)(want < 1 ? 1 : want);
 }

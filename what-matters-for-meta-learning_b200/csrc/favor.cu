@@ -9,6 +9,7 @@
 //             that feed the diag / max terms, and the row-argmax routing for queries.
 // Layouts: xq/xk/v rows are (t, i, h); out / d_out are [T, nt, d, H] (index e*H + h).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -19,6 +20,26 @@ namespace {
 constexpr int FC = 128;       // features per chunk
 constexpr int PITCH = FC + 1; // odd pitch: conflict-free row-strided reads
 constexpr float kEps = 1e-4f; // fast_attention.py:74
+
+// Feature split over a thread-block cluster: the chunk loops below are latency-bound (load chunk -> exp -> barrier ->
+// small products -> barrier, 12 chunks for M = 1419), so the S CTAs of a cluster take M/S features of ONE (task, head)
+// each and combine their partial tiles / row sums through distributed shared memory, in rank order (deterministic).
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the float at the same shared-memory offset as `p` in CTA `rank` of this cluster
+__device__ __forceinline__ float ld_cluster(const float* p, uint32_t rank) {
+  uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(p)), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
 
 // one warp per row
 __global__ void favor_rowstats_kernel(const float* __restrict__ x, const float* __restrict__ U,
@@ -71,7 +92,7 @@ __global__ void __launch_bounds__(256) favor_attn_fwd_kernel(
     const float* __restrict__ U, const float* __restrict__ W, const float* __restrict__ sq,
     const float* __restrict__ mq, const float* __restrict__ tk, const float* __restrict__ g,
     const float* __restrict__ v, float* __restrict__ out, float* __restrict__ A, float* __restrict__ Dn,
-    float* __restrict__ ties, int H, int nt, int nc, int d, int M, long long ldu) {
+    float* __restrict__ ties, int H, int nt, int nc, int d, int M, long long ldu, int S) {
   extern __shared__ float sm[];
   float* Qs = sm;                    // [nt][PITCH]
   float* Ks = Qs + nt * PITCH;       // [nc][PITCH]
@@ -81,7 +102,11 @@ __global__ void __launch_bounds__(256) favor_attn_fwd_kernel(
   float* s2 = s1 + nt;               // [nt] mq
   float* s3 = s2 + nt;               // [nc] tk
   const int tid = threadIdx.x;
-  const int t = blockIdx.x / H, h = blockIdx.x % H;
+  const uint32_t rank = S > 1 ? cluster_rank() : 0u;
+  const int pair = blockIdx.x / S;
+  const int t = pair / H, h = pair % H;
+  const int nchunk = (M + FC - 1) / FC, per = (nchunk + S - 1) / S;
+  const int f_lo = (int)rank * per * FC, f_hi = min(M, ((int)rank + 1) * per * FC);   // this CTA's features
   const float gmax = __ldg(g);
   const float rho = rsqrtf((float)M);
   for (int i = tid; i < nt; i += 256) {
@@ -93,8 +118,8 @@ __global__ void __launch_bounds__(256) favor_attn_fwd_kernel(
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int tie_local = 0;
   __syncthreads();
-  for (int f0 = 0; f0 < M; f0 += FC) {
-    const int fc = M - f0 < FC ? M - f0 : FC;
+  for (int f0 = f_lo; f0 < f_hi; f0 += FC) {
+    const int fc = f_hi - f0 < FC ? f_hi - f0 : FC;
     // the chunk's U / W values are fetched eight at a time before the exponentials: one exposed load latency per
     // batch instead of one per element (this loop was the kernel's critical path)
     for (int base = tid; base < (nt + nc) * FC; base += 256 * 8) {
@@ -155,17 +180,37 @@ __global__ void __launch_bounds__(256) favor_attn_fwd_kernel(
     for (int o = 16; o > 0; o >>= 1) tl += __shfl_xor_sync(0xffffffffu, tl, o);
     if ((tid & 31) == 0 && tl) atomicAdd(ties, (float)tl);
   }
+  if (S > 1) {
+    cluster_sync();                    // every rank's partial tile is in its shared memory
+    float full[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {      // every rank forms the whole tile, summing the partials in rank order
+      const int p = tid + q * 256;
+      full[q] = 0.f;
+      if (p < nt * nc)
+        for (int r = 0; r < S; ++r) full[q] += ld_cluster(As + p, (uint32_t)r);
+    }
+    cluster_sync();                    // all remote reads are done: As may be overwritten (and CTAs may exit)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = tid + q * 256;
+      if (p < nt * nc) As[p] = full[q];
+    }
+  }
   __syncthreads();
   for (int i = tid; i < nt; i += 256) {
     float s = 0.f;
     for (int j = 0; j < nc; ++j) s += As[i * nc + j];
     Ds[i] = s;
-    Dn[((long long)t * H + h) * nt + i] = s;
+    if (rank == 0) Dn[((long long)t * H + h) * nt + i] = s;
   }
-  for (int p = tid; p < nt * nc; p += 256) A[((long long)t * H + h) * nt * nc + p] = As[p];
+  if (rank == 0)
+    for (int p = tid; p < nt * nc; p += 256) A[((long long)t * H + h) * nt * nc + p] = As[p];
   __syncthreads();
-  for (int idx = tid; idx < nt * d; idx += 256) {
-    const int i = idx / d, e = idx - i * d;
+  // out rows i = rank, rank + S, ...: the ranks share the A v product
+  const int ni = (nt - (int)rank + S - 1) / S;
+  for (int idx = tid; idx < ni * d; idx += 256) {
+    const int ii = idx / d, e = idx - ii * d, i = (int)rank + ii * S;
     float o = 0.f;
     for (int j = 0; j < nc; ++j) o = fmaf(As[i * nc + j], v[(((long long)t * nc + j) * H + h) * d + e], o);
     out[(((long long)t * nt + i) * d + e) * H + h] = o / Ds[i];
@@ -322,6 +367,15 @@ __global__ void favor_key_fixup_kernel(float* __restrict__ dW, const float* __re
   }
 }
 
+// B200NP_FAVOR_SPLIT = 1 | 2 | 4 | 8 (default 4): CTAs per (task, head) of the forward kernel
+int favor_split() {
+  static const int v = [] {
+    const char* e = getenv("B200NP_FAVOR_SPLIT");
+    const int s = (e && e[0]) ? atoi(e) : 4;
+    return (s == 1 || s == 2 || s == 4 || s == 8) ? s : 4;
+  }();
+  return v;
+}
 size_t fwd_smem(int nt, int nc) { return (size_t)((nt + nc) * PITCH + nt * nc + 3 * nt + nc) * sizeof(float); }
 size_t bwd_smem(int nt, int nc, int d) {
   return (size_t)((nt + nc) * PITCH + (nt + nc) * (d + 1) + 2 * nt * nc + 4 * nt + nc + 4 * (nt + nc)) * sizeof(float);
@@ -357,8 +411,24 @@ extern "C" int b200np_favor_attn_fwd(const float* U, const float* W, const float
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(favor_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return B200NP_E_LAUNCH;
-  favor_attn_fwd_kernel<<<T * H, 256, smem, as_stream(stream)>>>(U, W, sq, mq, tk, g, v, out, A, Dn, ties, H, nt, nc, d,
-                                                                 M, ldu);
+  // S CTAs (one thread-block cluster) per (task, head), each with 1/S of the features
+  int S = favor_split();
+  while (S > 1 && (M + FC - 1) / FC < S) S >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(T * H * S));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = S > 1 ? 1 : 0;
+  if (cudaLaunchKernelEx(&cfg, favor_attn_fwd_kernel, U, W, sq, mq, tk, g, v, out, A, Dn, ties, H, nt, nc, d, M, ldu, S) !=
+      cudaSuccess)
+    return B200NP_E_LAUNCH;
   return launch_status();
 }
 

@@ -229,10 +229,64 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     }
   }
 }
+__device__ __forceinline__ void reduce_store(float* __restrict__ out, int j, float t, const b200np::ReduceMap& map) {
+  if (map.kind == 0) {
+    out[j] = t;
+  } else if (map.kind == 1) {
+    const int ci = j % map.c, r = j / map.c;
+    const int co = r % map.b, tp = r / map.b;
+    if (tp < map.a) out[((long long)co * map.c + ci) * map.a + tp] = t;
+    else map.out2[(long long)co * map.c + ci] = t;
+  } else {
+    const int co = j / map.b, k = j - co * map.b;
+    if (k < map.a) out[co * map.a + k] = t;
+    else if (k == map.a && map.out2) map.out2[co] = t;
+  }
+}
+// Four columns per thread (16-byte loads, 512 contiguous bytes per warp instruction) and LANES partial-lanes per column
+// group: lane ty sums partials ty, ty + LANES, ... in order, then the lanes are folded 0..LANES-1 -- a fixed order, so the
+// result is deterministic.  The partials were written a moment ago and sit in L2; these reducers are serialised between
+// the weight-gradient kernels at the end of the step, so what counts is bytes in flight per SM: n / 128 blocks is only
+// ~2 per SM, hence 32 lanes (1024 threads) once there are enough partials.
+template <int LANES>
+__global__ void __launch_bounds__(32 * LANES) reduce_partials_vec4_kernel(const float* __restrict__ part,
+                                                                           float* __restrict__ out, int nparts, int n,
+                                                                           b200np::ReduceMap map) {
+  __shared__ float4 sm[LANES][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = (blockIdx.x * 32 + tx) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < n) {
+#pragma unroll 4
+    for (int p = ty; p < nparts; p += LANES) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (long long)p * n + j));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < n) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < LANES; ++k) {
+      const float4 v = sm[k][tx];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reduce_store(out, j, t.x, map);
+    reduce_store(out, j + 1, t.y, map);
+    reduce_store(out, j + 2, t.z, map);
+    reduce_store(out, j + 3, t.w, map);
+  }
+}
 namespace b200np {
 int launch_reduce_partials(const float* part, float* out, int nparts, int n, ReduceMap map, cudaStream_t st) {
   if (n <= 0) return B200NP_OK;
-  reduce_partials_kernel<<<(n + 31) / 32, 256, 0, st>>>(part, out, nparts, n, map);
+  if ((n & 3) == 0 && aligned16(part) && nparts >= 128)
+    reduce_partials_vec4_kernel<32><<<(n / 4 + 31) / 32, 1024, 0, st>>>(part, out, nparts, n, map);
+  else if ((n & 3) == 0 && aligned16(part) && nparts >= 16)
+    reduce_partials_vec4_kernel<8><<<(n / 4 + 31) / 32, 256, 0, st>>>(part, out, nparts, n, map);
+  else
+    reduce_partials_kernel<<<(n + 31) / 32, 256, 0, st>>>(part, out, nparts, n, map);
   return launch_status();
 }
 }  // namespace b200np
