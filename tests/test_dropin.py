@@ -54,8 +54,11 @@ print("OK")
 
 @needs_ref
 def test_train_py_import_block_resolves_under_the_launcher_recipe():
+    # other test modules opt into the B200 MMAML / BBB classes through os.environ in this process: the probe checks
+    # the DEFAULT resolution, so the child must not inherit those switches
+    env = {k: v for k, v in os.environ.items() if k not in ("B200NP_MMAML", "B200NP_BBB")}
     r = subprocess.run([sys.executable, "-c", _IMPORT_PROBE, ROOT, PKG, ref_shims.REFERENCE_ROOT],
-                       capture_output=True, text=True, timeout=300)
+                       capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
 
 
