@@ -296,10 +296,14 @@ int b200np_adam_step_dev(float* p, const float* g, float* m, float* v, long long
  * (dY x W, then col2im) read the parameter tensor as it is.  x NHWC [N,H,W,C], H and W even.
  * col2im gathers (deterministic); `mask` (nullable, dx geometry) gates the result with (mask > 0).
  *
- * bn_act: per channel over all `rows` = N*H*W rows of x [rows, C]: mean, biased variance (Welford, two-level,
+ * bn_act: per channel over all `rows` = N*H*W rows of x [rows, C]: mean, biased variance (fp64 sums, two-level,
  * deterministic), y = relu?((x - mean) * rstd * (scale + plus_one) + shift); scale / shift nullable ([C]).  FiLM passes
  * scale = gamma, plus_one = 1, shift = beta; affine BatchNorm scale = weight, plus_one = 0, shift = bias.  mean / rstd
  * are saved for the backward; run_mean / run_var (nullable) get F.batch_norm's running update (unbiased variance).
+ * The statistics are accumulated in fp64 and `mean` is an array of 2*C floats: mean[c] + mean[C + c] is the batch mean
+ * as a (hi, lo) pair, and every kernel forms x - mean as (x - hi) - lo, so that the sign of a pre-activation near zero
+ * -- the ReLU gate, which the backward and the second-order backward multiply by -- does not depend on the rounding of
+ * the mean when |mean| >> std.
  * Backward: dshift = sum g, dscale = sum g * xhat (g = dy gated by y > 0 when relu), dx = the usual batch-norm data
  * gradient.  Workspace: b200np_bn_workspace(rows, C) bytes.
  * ------------------------------------------------------------------------------------------ */
@@ -312,6 +316,17 @@ int b200np_bn_act_fwd(const float* x, const float* scale, const float* shift, fl
 int b200np_bn_act_bwd(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
                       const float* scale, float plus_one, float* dx, float* dscale, float* dshift, long long rows, int C,
                       int relu, void* ws, size_t ws_bytes, void* stream);
+/* Second order (the reference's MMAML trainer differentiates through the inner-loop gradient,
+ * trainer/meta_learner_reg.py:116-130, train.py:99 first_order=False): gradients of
+ * <vx, dx> + <vs, dscale> + <vt, dshift> -- the three outputs of b200np_bn_act_bwd -- with respect to x (gx), dy (gdy)
+ * and scale (gscale); vx / vs / vt and the outputs are nullable.  Workspace: b200np_bn_workspace2(rows, C). */
+size_t b200np_bn_workspace2(long long rows, int C);
+int b200np_bn_act_bwd2(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
+                       const float* scale, float plus_one, const float* vx, const float* vs, const float* vt, float* gx,
+                       float* gdy, float* gscale, long long rows, int C, int relu, void* ws, size_t ws_bytes,
+                       void* stream);
+/* out = alpha * a * b * c, elementwise (b, c nullable): second-order products (tanh, MSE loss) */
+int b200np_mul3(const float* a, const float* b, const float* c, float alpha, float* out, long long n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Bayes-by-backprop weight sampling + KL (networks/bbb/BBBConv.py:83-105, BBBLinear.py):

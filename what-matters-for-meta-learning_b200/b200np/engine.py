@@ -300,8 +300,8 @@ class LinearFn(Function):
     """y = act([x, x2] @ w^T + b): nn.Linear (+ torch.cat of two inputs, + ReLU/Tanh) in one kernel."""
 
     @staticmethod
-    def forward(ctx, act, prec, x, x2, w, b):
-        x = x.contiguous()
+    def forward(ctx, act, prec, x_in, x2, w, b):
+        x = x_in.contiguous()
         K1 = x.shape[-1]
         rows = x.numel() // K1
         N, Kt = w.shape
@@ -317,6 +317,7 @@ class LinearFn(Function):
             ops.gemm(_p(x2), _p(w, K1), _p(y), rows, N, K2, K2, 1, 1, Kt, N, bias=_p(b), beta=1.0, act=act,
                      prec=prec)
         ctx.act, ctx.prec, ctx.rows = act, prec, rows
+        ctx.x_is_input = x is x_in
         ctx.save_for_backward(x, x2, w, y)
         return y
 
@@ -324,6 +325,12 @@ class LinearFn(Function):
     def backward(ctx, dy):
         x, x2, w, y = ctx.saved_tensors
         act, prec, rows = ctx.act, ctx.prec, ctx.rows
+        if torch.is_grad_enabled():      # create_graph=True (second-order MAML): differentiable backward ops
+            from . import second_order
+            if x2 is not None or not ctx.x_is_input:
+                raise NotImplementedError("second-order gradients of a dense layer need one contiguous input")
+            dx, dw, db = second_order.linear_backward(act, prec, x, w, y, dy, ctx.needs_input_grad[2])
+            return None, None, dx, None, dw, db
         dy = dy.contiguous()
         dz = ops.act_bwd(dy, y, act) if act != ACT_NONE else dy
         N, Kt = w.shape
@@ -394,6 +401,11 @@ class AggregateFn(Function):
     @staticmethod
     def backward(ctx, dout):
         T, nc, D = ctx.shape
+        if torch.is_grad_enabled():      # create_graph=True
+            from . import second_order
+            if ctx.mode != 0:
+                raise NotImplementedError("second-order gradients are implemented for the mean aggregation only")
+            return None, second_order.MeanBwdP.apply(dout, nc)
         return None, ops.ctx_aggregate_bwd(dout.contiguous(), ctx.idx, T, nc, D, ctx.mode)
 
 

@@ -74,6 +74,9 @@ SIGNATURES = {
     "b200np_bn_workspace": (_sz, [_ll, _i]),
     "b200np_bn_act_fwd": (_i, [_p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _f, _ll, _i, _i, _p, _sz, _p]),
     "b200np_bn_act_bwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _ll, _i, _i, _p, _sz, _p]),
+    "b200np_bn_workspace2": (_sz, [_ll, _i]),
+    "b200np_bn_act_bwd2": (_i, [_p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _p, _sz, _p]),
+    "b200np_mul3": (_i, [_p, _p, _p, _f, _p, _ll, _p]),
     "b200np_bbb_kl_blocks": (_i, [_ll]),
     "b200np_bbb_sample_kl_fwd": (_i, [_p, _p, _p, _f, _f, _p, _p, _p, _ll, _p]),
     "b200np_bbb_sample_kl_bwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _ll, _p]),

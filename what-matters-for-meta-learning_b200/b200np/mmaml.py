@@ -8,16 +8,17 @@ samples, one Linear head per FiLM layer.
 
 Every op is an ``autograd.Function`` over C-ABI kernels: the convolution is im2col + the tcgen05 GEMM (forward, weight
 gradient and data gradient read torch's ``[Cout, Cin, 3, 3]`` weight as it is, any channel count), normalisation +
-scale/shift + ReLU is one fused kernel after a deterministic two-level statistics pass.  FIRST ORDER ONLY: the
-backward functions are ``once_differentiable``, so a caller that asks for ``create_graph=True``
-(trainer/meta_learner_reg.py:116-122 with ``first_order=False``) gets a loud error instead of silently dropped
-second-order terms.
+scale/shift + ReLU is one fused kernel after a deterministic two-level statistics pass.
+
+Second order: the reference's MMAML learner differentiates through the inner-loop gradient
+(trainer/meta_learner_reg.py:116-122, ``first_order=False`` at train.py:99).  Under ``create_graph=True`` autograd runs
+``backward`` with gradients enabled; the Functions below then return their gradients through the differentiable
+backward ops of ``b200np/second_order.py`` (same kernels, closed under differentiation) instead of the fused
+single-pass kernels, so the outer gradient contains the second-order terms.
 """
 import torch
 from torch.autograd import Function
-from torch.autograd.function import once_differentiable
-
-from . import engine, ops
+from . import engine, ops, second_order
 from .engine import _p
 from .lib import ACT_NONE, ACT_RELU, ACT_TANH
 
@@ -26,8 +27,8 @@ class Conv3x3S2Fn(Function):
     """x NHWC [N,H,W,Cin], w [Cout,Cin,3,3], b [Cout] -> NHWC [N,H/2,W/2,Cout] (stride 2, padding 1)."""
 
     @staticmethod
-    def forward(ctx, prec, x, w, b):
-        x, w = x.contiguous(), w.contiguous()
+    def forward(ctx, prec, x_in, w_in, b):
+        x, w = x_in.contiguous(), w_in.contiguous()
         N, H, W, Cin = x.shape
         Cout = w.shape[0]
         K = Cin * 9
@@ -36,14 +37,16 @@ class Conv3x3S2Fn(Function):
         y = ops.empty((N, H // 2, W // 2, Cout), x)
         ops.gemm(_p(col), _p(w), _p(y), M, Cout, K, K, 1, 1, K, Cout, bias=_p(b), prec=prec)
         ctx.prec, ctx.xshape = prec, tuple(x.shape)
-        ctx.save_for_backward(col, w)
+        ctx.save_for_backward(col, w, x_in, w_in)      # the inputs themselves: they carry the graph in second-order mode
         return y
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dy):
-        col, w = ctx.saved_tensors
+        col, w, x_in, w_in = ctx.saved_tensors
         prec = ctx.prec
+        if torch.is_grad_enabled():                     # create_graph=True
+            dx, dw, db = second_order.conv3x3s2_backward(prec, x_in, w_in, dy, ctx.needs_input_grad[1])
+            return None, dx, dw, db
         N, H, W, Cin = ctx.xshape
         Cout, K = w.shape[0], Cin * 9
         M = col.shape[0]
@@ -63,21 +66,24 @@ class BnActFn(Function):
     """relu?(batch_norm(x) * (scale + plus_one) + shift) over the last dim's channels; scale / shift [C] or None."""
 
     @staticmethod
-    def forward(ctx, x, scale, shift, plus_one, relu, eps, run_mean, run_var, momentum):
-        x = x.contiguous()
-        scale = None if scale is None else scale.contiguous()
+    def forward(ctx, x_in, scale_in, shift, plus_one, relu, eps, run_mean, run_var, momentum):
+        x = x_in.contiguous()
+        scale = None if scale_in is None else scale_in.contiguous()
         shift = None if shift is None else shift.contiguous()
         y, mean, rstd = ops.bn_act_fwd(x, scale, shift, plus_one, relu, eps, run_mean, run_var, momentum)
         ctx.cfg = (plus_one, relu, scale is not None, shift is not None)
-        ctx.save_for_backward(x, y, mean, rstd, scale)
+        ctx.save_for_backward(x_in, y, mean, rstd, scale_in)
         return y
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dy):
         x, y, mean, rstd, scale = ctx.saved_tensors
         plus_one, relu, has_scale, has_shift = ctx.cfg
-        dx, dscale, dshift = ops.bn_act_bwd(dy.contiguous(), y, x, mean, rstd, scale, plus_one, relu)
+        if torch.is_grad_enabled():                     # create_graph=True: the gate (y > 0) is a constant
+            dx, dscale, dshift = second_order.BnActBwdP.apply(x, dy, scale, y.detach(), mean, rstd, plus_one, relu)
+        else:
+            dx, dscale, dshift = ops.bn_act_bwd(dy.contiguous(), y, x.contiguous(), mean, rstd,
+                                                None if scale is None else scale.contiguous(), plus_one, relu)
         return dx, (dscale if has_scale else None), (dshift if has_shift else None), None, None, None, None, None, None
 
 

@@ -394,12 +394,13 @@ def col2im3x3s2(dcol, x_shape, mask=None):
 
 
 def bn_act_fwd(x, scale, shift, plus_one, relu=True, eps=1e-5, run_mean=None, run_var=None, momentum=0.1):
-    """x [..., C] (rows = everything but the last dim) -> (y, mean [C], rstd [C])."""
+    """x [..., C] (rows = everything but the last dim) -> (y, mean [2C], rstd [C]); `mean` holds the batch mean as a
+    (hi, lo) pair of floats per channel (hi = mean[:C]), see include/b200np.h."""
     _chk(x, "x"), _chk(scale, "scale"), _chk(shift, "shift")
     Cc = x.shape[-1]
     rows = x.numel() // Cc
     y = torch.empty_like(x)
-    mean, rstd = empty((Cc,), x), empty((Cc,), x)
+    mean, rstd = empty((2 * Cc,), x), empty((Cc,), x)
     ws_bytes = LIB.b200np_bn_workspace(rows, Cc)
     ws = torch.empty(max(ws_bytes // 4, 1), device=x.device, dtype=F32)
     check(LIB.b200np_bn_act_fwd(_ptr(x), _ptr(scale), _ptr(shift), float(plus_one), float(eps), _ptr(y), _ptr(mean),
@@ -421,6 +422,31 @@ def bn_act_bwd(dy, y, x, mean, rstd, scale, plus_one, relu=True):
                                 _ptr(dscale), _ptr(dshift), rows, Cc, int(relu), _ptr(ws), ws_bytes, _stream()),
           "bn_act_bwd")
     return dx, dscale, dshift
+
+
+def bn_act_bwd2(dy, y, x, mean, rstd, scale, plus_one, relu, vx, vs, vt, want_x=True, want_dy=True, want_scale=True):
+    """Second order: gradients of <vx, dx> + <vs, dscale> + <vt, dshift> (the outputs of bn_act_bwd) with respect to
+    x, dy and scale -> (gx, gdy, gscale); vx / vs / vt may be None (zero cotangent)."""
+    _chk(dy, "dy")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    gx = torch.empty_like(x) if want_x else None
+    gdy = torch.empty_like(x) if want_dy else None
+    gscale = empty((Cc,), x) if want_scale else None
+    ws_bytes = LIB.b200np_bn_workspace2(rows, Cc)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=x.device, dtype=F32)
+    check(LIB.b200np_bn_act_bwd2(_ptr(dy), _ptr(y), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(scale), float(plus_one), _ptr(vx),
+                                 _ptr(vs), _ptr(vt), _ptr(gx), _ptr(gdy), _ptr(gscale), rows, Cc, int(relu), _ptr(ws),
+                                 ws_bytes, _stream()), "bn_act_bwd2")
+    return gx, gdy, gscale
+
+
+def mul3(a, b=None, c=None, alpha=1.0):
+    """alpha * a * b * c elementwise (b, c optional)."""
+    _chk(a, "a")
+    out = torch.empty_like(a)
+    check(LIB.b200np_mul3(_ptr(a), _ptr(b), _ptr(c), float(alpha), _ptr(out), a.numel(), _stream()), "mul3")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

@@ -81,61 +81,54 @@ __global__ void col2im3x3s2_kernel(const float* __restrict__ dcol, const float* 
 // order (Chan et al.), writes mean / rstd and updates the running statistics like F.batch_norm(training=True) does.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kStatLanes = 8;
-__global__ void __launch_bounds__(256) bn_stats_l1_kernel(const float* __restrict__ x, float* __restrict__ part, long long R,
+// Statistics in fp64: sum and sum of squares per (slice, channel), folded in slice order.  The mean is handed to the
+// elementwise kernels as a (hi, lo) pair of floats (mean[c], mean[C + c]) and x - mean is formed as (x - hi) - lo: with
+// fp32 Welford statistics the mean carries an error of ~1e-6 standard deviations when |mean| >> std (a conv output with
+// a bias), which decides the sign of pre-activations that close to zero -- on a 61440 x 32 map a few ReLU gates differ
+// from the exact result, each worth ~1e-3 of the gradient and more of the second-order gradient (measured: torch's own
+// fp32 CUDA batch norm shows the same; its CPU kernel accumulates in double and does not).  DESIGN.md finding 25.
+__global__ void __launch_bounds__(256) bn_stats_l1_kernel(const float* __restrict__ x, double* __restrict__ part, long long R,
                                                           int C, long long rows_per_slice) {
-  __shared__ float s_n[kStatLanes][32], s_m[kStatLanes][32], s_q[kStatLanes][32];
+  __shared__ double s_s[kStatLanes][32], s_q[kStatLanes][32];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const long long r0 = (long long)blockIdx.y * rows_per_slice;
   const long long r1 = r0 + rows_per_slice < R ? r0 + rows_per_slice : R;
-  float n = 0.f, mean = 0.f, m2 = 0.f;
+  double sum = 0.0, sq = 0.0;
   if (c < C)
     for (long long r = r0 + rl; r < r1; r += kStatLanes) {
-      const float v = __ldg(x + r * C + c);
-      n += 1.f;
-      const float d = v - mean;
-      mean += d / n;
-      m2 = fmaf(d, v - mean, m2);
+      const double v = (double)__ldg(x + r * C + c);
+      sum += v;
+      sq = fma(v, v, sq);
     }
-  s_n[rl][cl] = n; s_m[rl][cl] = mean; s_q[rl][cl] = m2;
+  s_s[rl][cl] = sum; s_q[rl][cl] = sq;
   __syncthreads();
   if (rl == 0 && c < C) {
-    float N0 = s_n[0][cl], M0 = s_m[0][cl], Q0 = s_q[0][cl];
 #pragma unroll
-    for (int k = 1; k < kStatLanes; ++k) {
-      const float nb = s_n[k][cl];
-      if (nb > 0.f) {
-        const float tot = N0 + nb, d = s_m[k][cl] - M0;
-        M0 += d * (nb / tot);
-        Q0 += s_q[k][cl] + d * d * (N0 * nb / tot);
-        N0 = tot;
-      }
-    }
-    float* o = part + ((long long)blockIdx.y * C + c) * 3;
-    o[0] = N0; o[1] = M0; o[2] = Q0;
+    for (int k = 1; k < kStatLanes; ++k) { sum += s_s[k][cl]; sq += s_q[k][cl]; }
+    double* o = part + ((long long)blockIdx.y * C + c) * 2;
+    o[0] = sum; o[1] = sq;
   }
 }
-__global__ void bn_stats_l2_kernel(const float* __restrict__ part, int slices, int C, float eps, float* __restrict__ mean,
-                                   float* __restrict__ rstd, float* __restrict__ run_mean, float* __restrict__ run_var,
-                                   float momentum) {
+__global__ void bn_stats_l2_kernel(const double* __restrict__ part, int slices, int C, double rows, float eps,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ run_mean,
+                                   float* __restrict__ run_var, float momentum) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  float N0 = 0.f, M0 = 0.f, Q0 = 0.f;
+  double sum = 0.0, sq = 0.0;
   for (int s = 0; s < slices; ++s) {
-    const float* p = part + ((long long)s * C + c) * 3;
-    const float nb = p[0];
-    if (nb > 0.f) {
-      const float tot = N0 + nb, d = p[1] - M0;
-      M0 += d * (nb / tot);
-      Q0 += p[2] + d * d * (N0 * nb / tot);
-      N0 = tot;
-    }
+    sum += part[((long long)s * C + c) * 2];
+    sq += part[((long long)s * C + c) * 2 + 1];
   }
-  const float var = Q0 / N0;   // biased, as used for normalisation
-  mean[c] = M0;
-  rstd[c] = rsqrtf(var + eps);
-  if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * M0;
-  if (run_var) run_var[c] = (1.f - momentum) * run_var[c] + momentum * (N0 > 1.f ? Q0 / (N0 - 1.f) : var);
+  const double m = sum / rows;
+  double var = sq / rows - m * m;   // biased, as used for normalisation
+  if (var < 0.0) var = 0.0;
+  const float hi = (float)m;
+  mean[c] = hi;
+  mean[C + c] = (float)(m - (double)hi);
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * hi;
+  if (run_var) run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(rows > 1.0 ? var * rows / (rows - 1.0) : var);
 }
 
 // y = relu?( (x - mean) * rstd * scale' + shift ),  scale' = scale + plus_one  (FiLM: 1 + gamma)
@@ -146,7 +139,7 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ x, const float* __re
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += st) {
     const int c = (int)(i % C);
     const float sc = (scale ? __ldg(scale + c) : 0.f) + plus_one;
-    float v = (__ldg(x + i) - __ldg(mean + c)) * __ldg(rstd + c) * sc + (shift ? __ldg(shift + c) : 0.f);
+    float v = ((__ldg(x + i) - __ldg(mean + c)) - __ldg(mean + C + c)) * __ldg(rstd + c) * sc + (shift ? __ldg(shift + c) : 0.f);
     y[i] = relu ? fmaxf(v, 0.f) : v;
   }
 }
@@ -162,13 +155,13 @@ __global__ void __launch_bounds__(256) bn_act_bwd_l1_kernel(const float* __restr
   const long long r1 = r0 + rows_per_slice < R ? r0 + rows_per_slice : R;
   float a = 0.f, b = 0.f;
   if (c < C) {
-    const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+    const float mu = __ldg(mean + c), mlo = __ldg(mean + C + c), rs = __ldg(rstd + c);
     for (long long r = r0 + rl; r < r1; r += kStatLanes) {
       const long long i = r * C + c;
       float g = __ldg(dy + i);
       if (relu && !(__ldg(y + i) > 0.f)) g = 0.f;
       a += g;
-      b = fmaf(g, (__ldg(x + i) - mu) * rs, b);
+      b = fmaf(g, ((__ldg(x + i) - mu) - mlo) * rs, b);
     }
   }
   s_a[rl][cl] = a; s_b[rl][cl] = b;
@@ -201,9 +194,102 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dy, const floa
     float g = __ldg(dy + i);
     if (relu && !(__ldg(y + i) > 0.f)) g = 0.f;
     const float rs = __ldg(rstd + c);
-    const float xh = (__ldg(x + i) - __ldg(mean + c)) * rs;
+    const float xh = ((__ldg(x + i) - __ldg(mean + c)) - __ldg(mean + C + c)) * rs;
     const float sc = (scale ? __ldg(scale + c) : 0.f) + plus_one;
     dx[i] = rs * sc * (g - __ldg(dshift + c) * inv_rows - xh * __ldg(dscale + c) * inv_rows);
+  }
+}
+
+// ---- second order: the derivative of the BACKWARD above (MAML differentiates through the inner-loop gradient,
+// trainer/meta_learner_reg.py:116-130).  With G = dy * gate, xh = (x - mean) * rstd, s = scale + plus_one the backward is
+//   dx = s * rstd * (G - mean_r G - xh * mean_r(G xh)),   dscale = sum_r G xh,   dshift = sum_r G.
+// Given cotangents vx (of dx), vs (of dscale), vt (of dshift) and the per-channel means
+//   a = <G>, b = <G xh>, e = <vx>, c = <vx xh>, m = <vx G>,  S = m - e a - c b
+// the gradients of  L = <vx, dx> + <vs, dscale> + <vt, dshift>  are (checked against autograd in fp64):
+//   dL/ddy    = gate * ( s * rstd * (vx - e - xh c) + vs * xh + vt )
+//   dL/dx     = -s * rstd^2 * ( S xh + b (vx - e - c xh) + c (G - a - b xh) ) + vs * rstd * (G - a - b xh)
+//   dL/dscale = rstd * rows * S
+// level 1: per slice and channel the five sums.  S is a difference of products of means (a covariance written with raw
+// moments): in fp32 the cancellation cost 1e-2 of the outer gradient on the reference's own initialisation (torch's fp32
+// double backward loses 4e-3 there), so the moments are accumulated and combined in fp64 -- 5 doubles per thread in a
+// kernel that is bound by reading three fp32 tensors.
+__global__ void __launch_bounds__(256) bn_act_bwd2_l1_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                             const float* __restrict__ x, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ vx,
+                                                             double* __restrict__ part, long long R, int C,
+                                                             long long rows_per_slice, int relu) {
+  __shared__ double sm[5][kStatLanes][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const long long r0 = (long long)blockIdx.y * rows_per_slice;
+  const long long r1 = r0 + rows_per_slice < R ? r0 + rows_per_slice : R;
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (c < C) {
+    const float mu = __ldg(mean + c), mlo = __ldg(mean + C + c), rs = __ldg(rstd + c);
+    for (long long r = r0 + rl; r < r1; r += kStatLanes) {
+      const long long i = r * C + c;
+      float g = __ldg(dy + i);
+      if (relu && !(__ldg(y + i) > 0.f)) g = 0.f;
+      const double xh = (double)(((__ldg(x + i) - mu) - mlo) * rs), v = vx ? (double)__ldg(vx + i) : 0.0, gd = (double)g;
+      acc[0] += gd;
+      acc[1] += gd * xh;
+      acc[2] += v;
+      acc[3] += v * xh;
+      acc[4] += v * gd;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) sm[k][rl][cl] = acc[k];
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    double* o = part + ((long long)blockIdx.y * C + c) * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      double t = 0.0;
+#pragma unroll
+      for (int l = 0; l < kStatLanes; ++l) t += sm[k][l][cl];
+      o[k] = t;
+    }
+  }
+}
+// level 2: slices folded in order -> per channel a, b, e, c and S (stats[c][0..4]), and dL/dscale
+__global__ void bn_act_bwd2_l2_kernel(const double* __restrict__ part, int slices, int C, const float* __restrict__ rstd,
+                                      double rows, float* __restrict__ stats, float* __restrict__ gscale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int s = 0; s < slices; ++s)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) t[k] += part[((long long)s * C + c) * 5 + k];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) t[k] /= rows;
+  const double S = t[4] - t[2] * t[0] - t[3] * t[1];
+  stats[c * 5 + 0] = (float)t[0];
+  stats[c * 5 + 1] = (float)t[1];
+  stats[c * 5 + 2] = (float)t[2];
+  stats[c * 5 + 3] = (float)t[3];
+  stats[c * 5 + 4] = (float)S;
+  if (gscale) gscale[c] = (float)((double)__ldg(rstd + c) * rows * S);
+}
+__global__ void bn_act_bwd2_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
+                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                         const float* __restrict__ scale, float plus_one, const float* __restrict__ vx,
+                                         const float* __restrict__ vs, const float* __restrict__ vt,
+                                         const float* __restrict__ stats, float* __restrict__ gx, float* __restrict__ gdy,
+                                         long long total, int C, int relu) {
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += st) {
+    const int ch = (int)(i % C);
+    const bool open = !relu || __ldg(y + i) > 0.f;
+    const float g = open ? __ldg(dy + i) : 0.f;
+    const float rs = __ldg(rstd + ch), xh = ((__ldg(x + i) - __ldg(mean + ch)) - __ldg(mean + C + ch)) * rs;
+    const float s = (scale ? __ldg(scale + ch) : 0.f) + plus_one;
+    const float v = vx ? __ldg(vx + i) : 0.f, ws = vs ? __ldg(vs + ch) : 0.f, wt = vt ? __ldg(vt + ch) : 0.f;
+    const float* q = stats + ch * 5;
+    const float a = __ldg(q), b = __ldg(q + 1), e = __ldg(q + 2), c = __ldg(q + 3), S = __ldg(q + 4);
+    const float vr = v - e - c * xh, gr = g - a - b * xh;
+    if (gdy) gdy[i] = open ? s * rs * vr + ws * xh + wt : 0.f;
+    if (gx) gx[i] = -s * rs * rs * (S * xh + b * vr + c * gr) + ws * rs * gr;
   }
 }
 
@@ -232,7 +318,7 @@ extern "C" int b200np_col2im3x3s2(const float* dcol, const float* mask, float* d
   return launch_status();
 }
 extern "C" size_t b200np_bn_workspace(long long rows, int C) {
-  return (size_t)stat_slices(rows) * (size_t)C * 3 * sizeof(float);
+  return (size_t)stat_slices(rows) * (size_t)C * 2 * sizeof(double);
 }
 extern "C" int b200np_bn_act_fwd(const float* x, const float* scale, const float* shift, float plus_one, float eps,
                                  float* y, float* mean, float* rstd, float* run_mean, float* run_var, float momentum,
@@ -242,8 +328,9 @@ extern "C" int b200np_bn_act_fwd(const float* x, const float* scale, const float
   cudaStream_t st = as_stream(stream);
   const int slices = stat_slices(rows);
   const long long per = ceil_div(rows, slices);
-  bn_stats_l1_kernel<<<dim3((C + 31) / 32, slices), 256, 0, st>>>(x, (float*)ws, rows, C, per);
-  bn_stats_l2_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, slices, C, eps, mean, rstd, run_mean, run_var, momentum);
+  bn_stats_l1_kernel<<<dim3((C + 31) / 32, slices), 256, 0, st>>>(x, (double*)ws, rows, C, per);
+  bn_stats_l2_kernel<<<(C + 127) / 128, 128, 0, st>>>((const double*)ws, slices, C, (double)rows, eps, mean, rstd, run_mean,
+                                                      run_var, momentum);
   const long long total = rows * C;
   bn_act_fwd_kernel<<<ew_grid(total, 256), 256, 0, st>>>(x, mean, rstd, scale, shift, plus_one, y, total, C, relu);
   return launch_status(3);
@@ -262,6 +349,32 @@ extern "C" int b200np_bn_act_bwd(const float* dy, const float* y, const float* x
   bn_act_bwd_apply_kernel<<<ew_grid(total, 256), 256, 0, st>>>(dy, y, x, mean, rstd, scale, plus_one, dshift, dscale, dx,
                                                                total, C, 1.f / (float)rows, relu);
   return launch_status(3);
+}
+
+extern "C" size_t b200np_bn_workspace2(long long rows, int C) {
+  return (size_t)stat_slices(rows) * (size_t)C * 5 * sizeof(double) + (size_t)C * 5 * sizeof(float);
+}
+extern "C" int b200np_bn_act_bwd2(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
+                                  const float* scale, float plus_one, const float* vx, const float* vs, const float* vt,
+                                  float* gx, float* gdy, float* gscale, long long rows, int C, int relu, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  if (!dy || !y || !x || !mean || !rstd || rows <= 0 || C <= 0 || !ws) return B200NP_E_BADARG;
+  if (ws_bytes < b200np_bn_workspace2(rows, C)) return B200NP_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int slices = stat_slices(rows);
+  const long long per = ceil_div(rows, slices);
+  double* part = (double*)ws;
+  float* stats = (float*)(part + (size_t)slices * C * 5);
+  bn_act_bwd2_l1_kernel<<<dim3((C + 31) / 32, slices), 256, 0, st>>>(dy, y, x, mean, rstd, vx, part, rows, C, per, relu);
+  bn_act_bwd2_l2_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, slices, C, rstd, (double)rows, stats, gscale);
+  int launched = 2;
+  if (gx || gdy) {
+    const long long total = rows * C;
+    bn_act_bwd2_apply_kernel<<<ew_grid(total, 256), 256, 0, st>>>(dy, y, x, mean, rstd, scale, plus_one, vx, vs, vt, stats,
+                                                                  gx, gdy, total, C, relu);
+    ++launched;
+  }
+  return launch_status(launched);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

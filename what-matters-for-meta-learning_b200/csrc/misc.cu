@@ -196,6 +196,22 @@ extern "C" int b200np_repeat_rows_bwd(const float* dy, float* dx, long long rows
   return launch_status();
 }
 
+// out = alpha * a * b * c (b, c nullable = 1): the elementwise products of the second-order terms (tanh'' = -2 y dy v,
+// the MSE loss's constant Hessian 2/R)
+__global__ void mul3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                            float alpha, float* __restrict__ out, long long n) {
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += st)
+    out[i] = alpha * a[i] * (b ? b[i] : 1.f) * (c ? c[i] : 1.f);
+}
+extern "C" int b200np_mul3(const float* a, const float* b, const float* c, float alpha, float* out, long long n,
+                           void* stream) {
+  if (n <= 0) return B200NP_OK;
+  if (!a || !out) return B200NP_E_BADARG;
+  mul3_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(a, b, c, alpha, out, n);
+  return launch_status();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Partial-sum reducer shared by the split-K weight gradients and the column sums.
 // ------------------------------------------------------------------------------------------------

@@ -3,10 +3,12 @@
 ``B200NP_MMAML=1`` selects the B200 ``GatedConvModel`` below: same constructor, parameter / buffer names
 (``features.layer{i}_conv.*``, ``features.layer{i}_bn.running_*``, ``classifier.fully_connected.*``), initialisation
 (xavier-uniform weights, zero biases, networks/gated_conv_net.py:15-19) and ``forward(x, params=None, embeddings=None)``
-contract as the reference, with the arithmetic in libb200np (b200np/mmaml.py).  It is FIRST ORDER: a caller that builds
-a second-order graph through it (``MetaLearner(first_order=False)``, train.py:100) gets a loud error.  Without the
-variable -- the default -- this module hands out the reference's own classes, so ``MMAMLTrainer`` keeps working
-unmodified on the reference's PyTorch path.
+contract as the reference, with the arithmetic in libb200np (b200np/mmaml.py).  Second order is supported: under
+``torch.autograd.grad(..., create_graph=True)`` -- what ``MetaLearner(first_order=False)`` does (train.py:99,
+trainer/meta_learner_reg.py:116-122) -- the gradients come back with a graph built from the differentiable backward ops
+of b200np/second_order.py, so the outer gradient contains the second-order terms (tests/test_mmaml.py runs the
+reference's meta-step against golden vectors of the reference).  Without the variable -- the default -- this module
+hands out the reference's own classes.
 """
 import os
 from collections import OrderedDict

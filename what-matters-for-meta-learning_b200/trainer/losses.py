@@ -19,11 +19,13 @@ KIND = {"distractor": 0, "shapenet_3d": 1, "shapenet_1d": 2, "degree": 3}
 
 class _LossFn(Function):
     @staticmethod
-    def forward(ctx, kind, mu, y):
-        mu, y = mu.contiguous(), y.contiguous()
+    def forward(ctx, kind, mu_in, y):
+        mu, y = mu_in.contiguous(), y.contiguous()
+        ctx.mu_is_input = mu is mu_in
         want = kind != 3
         loss, dmu = ops.loss_fwd_bwd(mu, y, kind, want_grad=want)
-        ctx.dmu = dmu
+        ctx.dmu, ctx.kind = dmu, kind
+        ctx.save_for_backward(mu, y)
         # `loss` is a fresh 0-dim tensor, not a view: the reference trainer modifies the result in place
         # (`losses += kl * beta`, trainer/model_trainer.py:80), which autograd forbids on a view made inside a Function
         return loss
@@ -32,6 +34,12 @@ class _LossFn(Function):
     def backward(ctx, g):
         if ctx.dmu is None:
             raise RuntimeError("degree_loss is evaluation-only (no gradient in the reference either)")
+        if torch.is_grad_enabled():      # create_graph=True (second-order MAML, trainer/meta_learner_reg.py:116-122)
+            from b200np import second_order
+            mu, y = ctx.saved_tensors
+            if not ctx.mu_is_input:
+                raise NotImplementedError("second-order gradients of the loss need a contiguous prediction tensor")
+            return None, second_order.LossBwdP.apply(ctx.kind, mu, y, g), None
         return None, ops.scale_by_device_scalar(ctx.dmu, g.contiguous().view(1)), None
 
 
