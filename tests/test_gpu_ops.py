@@ -4,6 +4,7 @@
 Tolerances: integer results (argmax indices) bit-exact; fp32 CUDA-core kernels and the TF32X3
 (fp32-grade) tensor-core kernels <= 2e-5 relative L2; single-pass TF32 <= 3e-3 (its own bound).
 """
+import os
 import numpy as np
 import pytest
 import torch
@@ -457,3 +458,40 @@ def test_conv_fwd_relu_bits(hw, n, stride, skip):
     y, bits = ops.conv_fwd(x, ops.pack_conv_weight(w), b, stride, lib.ACT_RELU, lib.PREC_TF32X3, skip=sk, want_bits=True)
     assert bits is not None and torch.equal(bits, _pack_bits(y))
     assert 0.2 < float((y > 0).float().mean()) < 0.8
+
+
+_FAVOR_CHILD = r"""
+import sys, numpy as np, torch
+sys.path[:0] = [sys.argv[1], sys.argv[2]]
+from b200np import lib
+from b200np.engine import FavorAttentionFn
+T, H, nt, nc, d = 2, 8, 21, 15, 256
+M = int(d * np.log(d))
+g = torch.Generator().manual_seed(1)
+r = lambda *s: torch.randn(*s, generator=g)
+xq, xk, v, P, do = r(T * nt, H * d), r(T * nc, H * d), r(T * nc, H * d), r(M, d), r(T * nt, d * H)
+q_g, k_g, v_g = (t.cuda().requires_grad_() for t in (xq, xk, v))
+out = FavorAttentionFn.apply(lib.PREC_TF32X3, T, H, nt, nc, q_g, k_g, v_g, P.cuda())
+out.backward(do.cuda())
+np.savez(sys.argv[3], out=out.detach().cpu().numpy(), dq=q_g.grad.cpu().numpy(), dk=k_g.grad.cpu().numpy(), dv=v_g.grad.cpu().numpy())
+"""
+
+
+def test_favor_cluster_split_variants_agree(tmp_path):
+    """B200NP_FAVOR_SPLIT = 1 | 2 | 4 | 8 CTAs per (task, head) (thread-block cluster, DSMEM reduction in rank order): the
+    forward tile is the same sum in a different association, so outputs and gradients agree to fp32 rounding."""
+    import subprocess
+    import sys
+    from conftest import PKG, ROOT
+    res = {}
+    for S in (1, 2, 4, 8):
+        path = str(tmp_path / f"favor_{S}.npz")
+        env = dict(os.environ, B200NP_FAVOR_SPLIT=str(S))
+        r = subprocess.run([sys.executable, "-c", _FAVOR_CHILD, ROOT, PKG, path], capture_output=True, text=True, env=env,
+                           timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[S] = np.load(path)
+    for S in (2, 4, 8):
+        for k in ("out", "dq", "dk", "dv"):
+            a, b = res[S][k].astype(np.float64), res[1][k].astype(np.float64)
+            assert np.linalg.norm(a - b) <= 2e-6 * np.linalg.norm(b), (S, k)
