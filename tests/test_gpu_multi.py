@@ -51,6 +51,34 @@ if rank == 0:
     assert abs(loss_sharded - loss_full) < 1e-5 * abs(loss_full)
     assert err < 1e-4, err
 td.barrier()
+# ---- two-bucket overlapped gradient exchange (FusedAdam) == one all-reduce after the backward pass, eager and captured
+from b200np.optim import FusedAdam, GraphedStep
+shard = [t[lo:hi].contiguous() for t in batch]
+def train(buckets, graphed):
+    os.environ["B200NP_BUCKETS"] = buckets
+    torch.manual_seed(0)
+    model = ANPDistractor(cfg).to(dev)
+    opt = FusedAdam(FlatParams(model), lr=1e-3)
+    if graphed:
+        gs = GraphedStep(model, lossf, opt, shard, warmup=3)
+        for _ in range(3):
+            gs(shard)
+    else:
+        for _ in range(3):
+            opt.zero_grad()
+            mu, _, _ = model(shard[0], shard[1], shard[2]); lossf.calc_loss(mu, None, shard[3]).backward(); opt.step()
+    torch.cuda.synchronize()
+    return opt.flat.flat.clone(), opt
+ref, _ = train("0", False)
+for graphed in (False, True):
+    got, opt = train("1", graphed)
+    assert 0 < opt.flat.n_early < opt.flat.n_live
+    d = float((got - ref).abs().max())
+    assert d == 0.0, (graphed, d)
+    if rank == 0:
+        print(f"BUCKETS graphed={graphed}: parameters after 3 steps identical to the single all-reduce "
+              f"(early bucket {opt.flat.n_early} of {opt.flat.n_live} floats)", flush=True)
+td.barrier()
 td.destroy_process_group()
 """
 
@@ -63,5 +91,5 @@ def test_two_gpu_sharded_gradient_equals_full_batch(tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", "29641", str(script), ROOT]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert "RESULT" in out.stdout
-    print(out.stdout[out.stdout.index("RESULT"):].splitlines()[0])
+    assert "RESULT" in out.stdout and out.stdout.count("BUCKETS graphed=") == 2, out.stdout[-3000:]
+    print("\n".join(l for l in out.stdout.splitlines() if l.startswith(("RESULT", "BUCKETS"))))

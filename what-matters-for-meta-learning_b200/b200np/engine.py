@@ -76,6 +76,17 @@ USE_PRIORITIES = os.environ.get("B200NP_PRIO", "1") != "0"
 FORK = os.environ.get("B200NP_FORK", "early")   # where the decoder branch forks: early | late (see the forward)
 
 
+# Called at the start of every CNN trunk's backward with the data pointer of the trunk's first parameter.  By then every
+# gradient that does not belong to a trunk is complete (the trunks are the leaves of the backward pass), so a data-parallel
+# optimizer starts their all-reduce here and lets it run beside the trunk's backward (b200np/optim.py: FusedAdam).
+PRE_TRUNK_BACKWARD_HOOKS = []
+
+
+def _pre_trunk_backward(ptr):
+    for hook in list(PRE_TRUNK_BACKWARD_HOOKS):
+        hook(ptr)
+
+
 def _side_stream(key, priority=0):
     """One lazily created companion stream per key (the role and the handle of the stream it accompanies)."""
     s = _SIDE.get(key)
@@ -139,6 +150,7 @@ class TrunkFn(Function):
                 idxs.append(i)
             off += n
         ctx.img_agg, ctx.prec, ctx.Ns = img_agg, prec, Ns
+        ctx.first_param_ptr = c1w.data_ptr()
         ctx.imgs, ctx.acts, ctx.packs, ctx.idxs, ctx.bits = imgs, acts, packs, idxs, bits
         ctx.c1w_shape = tuple(c1w.shape)
         ctx.pool_idx = idxs  # exposed for parity tests (bit-exact argmax)
@@ -152,6 +164,7 @@ class TrunkFn(Function):
     @staticmethod
     def _backward(ctx, *douts):
         prec, Ns = ctx.prec, ctx.Ns
+        _pre_trunk_backward(ctx.first_param_ptr)
         y_last = ctx.acts[3][2]
         dy = torch.empty_like(y_last)
         off = 0
@@ -250,12 +263,14 @@ class EncoderW0Fn(Function):
             outs.append(ops.nhwc_to_nchw_flat(x4[off:off + n]))
             off += n
         ctx.prec, ctx.Ns, ctx.imgs = prec, Ns, imgs
+        ctx.first_param_ptr = w0.data_ptr()
         ctx.saved = (x1, x2, x3, x4, pidx, wd2, wd5, tuple(w0.shape), col2, col5, w2, w5)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *douts):
         prec, Ns = ctx.prec, ctx.Ns
+        _pre_trunk_backward(ctx.first_param_ptr)
         x1, x2, x3, x4, pidx, wd2, wd5, w0_shape, col2, col5, w2, w5 = ctx.saved
         d4 = torch.empty_like(x4)
         off = 0

@@ -14,12 +14,25 @@ from . import dist, ops
 
 
 class FlatParams:
-    def __init__(self, module, dead=lambda name: ".resnet.fc." in name):
+    """`late(name)`: parameters whose gradients are produced LAST by the backward pass -- the CNN trunks, which are the
+    leaves of the backward pass (`img_encoder.*`, the decoder's `conv1` / `resnet`; `encoder_w0.*` for the ShapeNet1D
+    family).  They are laid out after all the others, so that the data-parallel exchange can run as two contiguous
+    buckets: the dense / attention layers while the encoder CNN's backward is still computing, the CNNs at the end
+    (FusedAdam).  `trigger(name)`: the parameter whose trunk starts its backward only after every non-late gradient is
+    complete (the ENCODER CNN: the decoder CNN's backward starts right after `fc_mu`, on its own stream)."""
+
+    LATE = ("img_encoder.", "encoder_w0.", "decoder.conv1.", "decoder.resnet.")
+    TRIGGER = ("img_encoder.conv1.weight", "encoder_w0.0.weight")
+
+    def __init__(self, module, dead=lambda name: ".resnet.fc." in name, late=lambda name: name.startswith(FlatParams.LATE),
+                 trigger=lambda name: name in FlatParams.TRIGGER):
         named = list(module.named_parameters())
-        live = [(n, p) for n, p in named if not dead(n)]
+        alive = [(n, p) for n, p in named if not dead(n)]
+        live = [(n, p) for n, p in alive if not late(n)] + [(n, p) for n, p in alive if late(n)]
         rest = [(n, p) for n, p in named if dead(n)]
         dev = named[0][1].device
         pad = lambda k: (k + 3) // 4 * 4  # keep every view 16-byte aligned
+        self.n_early = sum(pad(p.numel()) for n, p in live if not late(n))
         self.n_live = sum(pad(p.numel()) for _, p in live)
         total = self.n_live + sum(pad(p.numel()) for _, p in rest)
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -34,29 +47,39 @@ class FlatParams:
             if off < self.n_live:
                 self.live.append((n, p, off, k))
             off += pad(k)
+        self.trigger_ptrs = {p.data_ptr() for n, p, _, _ in self.live if trigger(n)}
 
     def attach_grads(self):
         """Point every live parameter's .grad at its slice of the flat gradient buffer."""
         for _, p, off, k in self.live:
             p.grad = self.grad[off:off + k].view_as(p)
 
-    def gather_grads(self):
-        """After autograd: bring every .grad into the flat buffer -- ONE launch per 64 parameters
-        (`b200np_multi_copy`); parameters without a gradient get zeros.  Afterwards .grad is the flat view."""
+    def gather_grads(self, lo=0, hi=None, keep=None, skip_missing=False):
+        """After autograd: bring every .grad with offset in [lo, hi) into the flat buffer -- ONE launch per 64 parameters
+        (`b200np_multi_copy`); parameters without a gradient get zeros (`skip_missing`: are left for a later call).
+        Afterwards .grad is the flat view.  `keep`: a list that receives the source tensors (a caller that enqueues the
+        copy on another stream keeps them referenced until that stream has joined)."""
+        hi = self.n_live if hi is None else hi
+        keep = self._keep if keep is None else keep
         segs = []
         for _, p, off, k in self.live:
+            if off < lo or off >= hi:
+                continue
             view = self.grad[off:off + k].view_as(p)
             g = p.grad
             if g is None:
+                if skip_missing:
+                    continue
                 segs.append((None, off, k))
             elif g.data_ptr() != view.data_ptr():
                 if not g.is_contiguous():
                     g = g.contiguous()
-                self._keep.append(g)      # keep the source alive until the copy has been enqueued
+                keep.append(g)            # keep the source alive until the copy has been enqueued
                 segs.append((g, off, k))
             p.grad = view
         ops.multi_copy(self.grad, segs)
-        self._keep.clear()
+        if keep is self._keep:
+            self._keep.clear()
 
     def zero_grad(self):
         """Drop the gradients: autograd then hands each parameter its gradient tensor by reference (no
@@ -67,17 +90,52 @@ class FlatParams:
 
 class FusedAdam:
     """torch.optim.Adam semantics (train.py:52-56: lr from config, betas (0.9, 0.999), eps 1e-8,
-    optional L2 weight decay) as one kernel over the flat live-parameter segment."""
+    optional L2 weight decay) as one kernel over the flat live-parameter segment.
+
+    Data parallel (world size > 1): the gradient exchange runs as TWO buckets.  When the encoder CNN's backward starts
+    (engine.PRE_TRUNK_BACKWARD_HOOKS) every other gradient is complete: they are gathered and all-reduced on a second
+    stream while the encoder CNN's data / weight gradients are still being computed; the CNNs' own bucket (~20 % of the
+    bytes) follows at the end, and the Adam kernel waits for both.  Inside a captured step this is a graph branch.
+    `B200NP_BUCKETS=0`: one all-reduce after the backward pass."""
 
     def __init__(self, flat: FlatParams, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        import os
+        import weakref
         self.flat, self.lr, self.betas, self.eps, self.wd = flat, lr, betas, eps, weight_decay
         self.m = torch.zeros_like(flat.grad)
         self.v = torch.zeros_like(flat.grad)
         self.t = 0
         self.t_dev = torch.zeros(1, device=flat.grad.device, dtype=torch.int32)  # step count for graph replay
+        self._early_done, self._early_keep, self._comm = False, [], None
+        if os.environ.get("B200NP_BUCKETS", "1") != "0" and flat.n_early and flat.n_early < flat.n_live:
+            from . import engine
+            ref = weakref.ref(self)
+
+            def hook(ptr):
+                me = ref()
+                if me is None:
+                    engine.PRE_TRUNK_BACKWARD_HOOKS.remove(hook)
+                elif ptr in me.flat.trigger_ptrs:
+                    me._early_bucket()
+            engine.PRE_TRUNK_BACKWARD_HOOKS.append(hook)
 
     def zero_grad(self, set_to_none=False):
         self.flat.zero_grad()
+        self._early_done = False
+
+    def _early_bucket(self):
+        """The gradients laid out before the encoder CNN's: gather + all-reduce on the communication stream."""
+        if self._early_done or dist.world_size() == 1:
+            return
+        f = self.flat
+        main = torch.cuda.current_stream()
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(priority=-1)
+        self._comm.wait_stream(main)
+        with torch.cuda.stream(self._comm):
+            f.gather_grads(0, f.n_early, keep=self._early_keep, skip_missing=True)
+            dist.all_reduce_sum(f.grad[:f.n_early])
+        self._early_done = True
 
     def step(self):
         from .engine import nvtx_range
@@ -86,10 +144,23 @@ class FusedAdam:
 
     def _step(self):
         f = self.flat
-        f.gather_grads()
         world = dist.world_size()
-        if world > 1:
-            dist.all_reduce_grads(f.grad)
+        if world > 1 and self._early_done:
+            # whatever the early bucket did not find (a parameter whose gradient arrived later: none on the shipped
+            # models) is exchanged on its own, so the result never depends on the bucket boundary being right
+            late_early = [(p, off, k) for _, p, off, k in f.live
+                          if off < f.n_early and p.grad is not None and p.grad.data_ptr() != f.grad[off:off + k].data_ptr()]
+            torch.cuda.current_stream().wait_stream(self._comm)   # before anything else writes into the early segment
+            self._early_keep.clear()
+            f.gather_grads()
+            dist.all_reduce_sum(f.grad[f.n_early:f.n_live])
+            for _, off, k in late_early:
+                dist.all_reduce_sum(f.grad[off:off + k])
+            self._early_done = False
+        else:
+            f.gather_grads()
+            if world > 1:
+                dist.all_reduce_grads(f.grad)
         self.t += 1
         # the step counter is kept on the device so that a captured CUDA graph of the whole step stays valid
         ops.adam_step_dev(f.flat, f.grad, self.m, self.v, f.n_live, self.lr, self.betas[0], self.betas[1], self.eps,
