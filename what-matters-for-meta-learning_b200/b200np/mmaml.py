@@ -45,7 +45,7 @@ class Conv3x3S2Fn(Function):
         col, w, x_in, w_in = ctx.saved_tensors
         prec = ctx.prec
         if torch.is_grad_enabled():                     # create_graph=True
-            dx, dw, db = second_order.conv3x3s2_backward(prec, x_in, w_in, dy, ctx.needs_input_grad[1])
+            dx, dw, db = second_order.conv3x3s2_backward(prec, x_in, w_in, dy, ctx.needs_input_grad[1], col=col)
             return None, dx, dw, db
         N, H, W, Cin = ctx.xshape
         Cout, K = w.shape[0], Cin * 9

@@ -7,6 +7,8 @@ builds the MMAML learner with ``first_order=False``).  A custom Function whose b
 autograd gradients without a graph, i.e. it silently drops those second-order terms.  Here every backward op is itself a
 Function over the same C-ABI kernels, and the Functions are closed under differentiation:
 
+  ConvBwdP    (dx, dW, db) of the 3x3 stride-2 convolution with an explicit derivative (second order; one Function
+              per conv layer instead of five, because the loop that uses it is bound by the host)
   MatmulP     C = op(A) op(B)            backward = two MatmulP          (any order)
   Im2colP / Col2imP   adjoint pair       backward = the other one        (any order)
   ColSumP / BcastRowsP  adjoint pair                                     (any order)
@@ -230,18 +232,75 @@ class LossBwdP(Function):
 # ------------------------------------------------------------------------------------------------
 # the differentiable backward passes of the first-order Functions
 # ------------------------------------------------------------------------------------------------
-def conv3x3s2_backward(prec, x, w, dy, need_x):
-    """-> (dx | None, dw, db) of y = conv3x3_s2(x NHWC, w [Cout,Cin,3,3]) + b."""
-    Cout = w.shape[0]
-    dy2 = dy.reshape(-1, Cout)
-    col = Im2colP.apply(x)
-    dw = MatmulP.apply(prec, dy2, col, True, False).view_as(w)
-    db = ColSumP.apply(dy2)
-    dx = None
-    if need_x:
-        dcol = MatmulP.apply(prec, dy2, w.reshape(Cout, -1), False, False)
-        dx = Col2imP.apply(dcol, tuple(x.shape))
-    return dx, dw, db
+class ConvBwdP(Function):
+    """(dx, dW, db) of y = conv3x3_s2(x NHWC, W [Cout,Cin,3,3]) + b in ONE Function with an explicit derivative, instead of
+    the five generic ops it is made of: the reference's meta-learning loop is bound by the host, and a Python
+    `autograd.Function` costs ~17 us per application (`tools/bench_mmaml.py`).
+
+    With X = im2col(x) [M,K], G = dy [M,Cout]:   dW = G^T X,   dx = col2im(G W),   db = colsum(G).
+    For cotangents (Vx, Vw, Vb) and Vc = im2col(Vx):
+        d/dG = X Vw^T + Vc W^T + 1 Vb^T        d/dx = col2im(G Vw)        d/dW = G^T Vc
+    `col` is the im2col matrix the forward pass saved (X as a value; the graph goes through `x`)."""
+
+    @staticmethod
+    def forward(ctx, prec, x, w, dy, col, need_x):
+        x, w, dy = x.contiguous(), w.contiguous(), dy.contiguous()
+        Cout = w.shape[0]
+        M, K = col.shape
+        dw = ops.empty(tuple(w.shape), w)
+        ops.gemm(_p(dy), _p(col), _p(dw), Cout, K, M, 1, Cout, K, 1, K, prec=prec)          # dW = G^T X
+        db = ops.colsum(dy, M, Cout, Cout)
+        dx = None
+        if need_x:
+            dcol = ops.empty((M, K), dy)
+            ops.gemm(_p(dy), _p(w), _p(dcol), M, K, Cout, Cout, 1, K, 1, K, prec=prec)      # dcol = G W
+            dx = ops.col2im3x3s2(dcol, tuple(x.shape))
+        ctx.cfg = (prec, tuple(x.shape), need_x)
+        ctx.save_for_backward(w, dy, col)
+        ctx.set_materialize_grads(False)
+        return dx, dw, db
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, vx, vw, vb):
+        w, dy, col = ctx.saved_tensors
+        prec, xshape, need_x = ctx.cfg
+        Cout = w.shape[0]
+        M, K = col.shape
+        need = ctx.needs_input_grad       # (prec, x, w, dy, col, need_x)
+        vc = ops.im2col3x3s2(vx.contiguous()) if vx is not None else None
+        vw = None if vw is None else vw.contiguous()
+        g_x = g_w = g_dy = None
+        if need[3]:
+            g_dy = ops.empty((M, Cout), dy)
+            have = False
+            if vw is not None:                                                               # X Vw^T (+ 1 Vb^T)
+                ops.gemm(_p(col), _p(vw), _p(g_dy), M, Cout, K, K, 1, 1, K, Cout, prec=prec,
+                         bias=None if vb is None else _p(vb.contiguous()))
+                have = True
+            if vc is not None:                                                               # + Vc W^T
+                ops.gemm(_p(vc), _p(w), _p(g_dy), M, Cout, K, K, 1, 1, K, Cout, prec=prec, beta=1.0 if have else 0.0,
+                         bias=None if (have or vb is None) else _p(vb.contiguous()))
+                have = True
+            if not have:
+                g_dy = ops.repeat_rows(vb.contiguous().view(1, -1), M) if vb is not None else None
+            if g_dy is not None:
+                g_dy = g_dy.view(dy.shape)
+        if need[1] and need_x and vw is not None:                                            # col2im(G Vw)
+            t = ops.empty((M, K), dy)
+            ops.gemm(_p(dy), _p(vw), _p(t), M, K, Cout, Cout, 1, K, 1, K, prec=prec)
+            g_x = ops.col2im3x3s2(t, xshape)
+        if need[2] and vc is not None:                                                       # G^T Vc
+            g_w = ops.empty(tuple(w.shape), w)
+            ops.gemm(_p(dy), _p(vc), _p(g_w), Cout, K, M, 1, Cout, K, 1, K, prec=prec)
+        return None, g_x, g_w, g_dy, None, None
+
+
+def conv3x3s2_backward(prec, x, w, dy, need_x, col=None):
+    """-> (dx | None, dw, db) of y = conv3x3_s2(x NHWC, w [Cout,Cin,3,3]) + b, differentiable once more."""
+    if col is None:
+        col = ops.im2col3x3s2(x.detach().contiguous())
+    return ConvBwdP.apply(prec, x, w, dy, col, need_x)
 
 
 def linear_backward(act, prec, x, w, y, dy, need_x):
