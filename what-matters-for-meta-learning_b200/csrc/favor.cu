@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) favor_attn_bwd_kernel(
     const float* __restrict__ tk, const float* __restrict__ g, const float* __restrict__ v,
     const float* __restrict__ out, const float* __restrict__ A, const float* __restrict__ Dn,
     float* __restrict__ dU, float* __restrict__ dW, float* __restrict__ dv, float* __restrict__ ds_c2,
-    float* __restrict__ dt_c2, float* __restrict__ dg_part, int H, int nt, int nc, int d, int M, long long ldu) {
+    float* __restrict__ dt_c2, float* __restrict__ dg_part, int H, int nt, int nc, int d, int M, long long ldu, int S) {
   extern __shared__ float sm[];
   const int dp = d + 1;
   float* Eq = sm;                     // [nt][PITCH]
@@ -240,7 +240,13 @@ __global__ void __launch_bounds__(256) favor_attn_bwd_kernel(
   float* rq = s3 + nc;                // [nt][4] row-sum partials of dU
   float* rk = rq + nt * 4;            // [nc][4] row-sum partials of dW
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t = blockIdx.x / H, h = blockIdx.x % H;
+  // S CTAs (one cluster) per (task, head): every rank builds dA (cheap, needed by all), takes 1/S of the feature chunks
+  // and of the dv rows; rank 0 folds the row-sum partials of all ranks (in rank order) into ds / dt / dg
+  const uint32_t rank = S > 1 ? cluster_rank() : 0u;
+  const int pair = blockIdx.x / S;
+  const int t = pair / H, h = pair % H;
+  const int nchunk = (M + FC - 1) / FC, per = (nchunk + S - 1) / S;
+  const int f_lo = (int)rank * per * FC, f_hi = min(M, ((int)rank + 1) * per * FC);
   const float gmax = __ldg(g);
   const float rho = rsqrtf((float)M);
   const float rho_eps = rho * kEps;
@@ -281,18 +287,21 @@ __global__ void __launch_bounds__(256) favor_attn_bwd_kernel(
     An[p] = A[((long long)t * H + h) * nt * nc + p] / Ds[i];
   }
   __syncthreads();
-  for (int idx = tid; idx < nc * d; idx += 256) {
-    const int j = idx / d, e = idx - j * d;
-    float s = 0.f;
-    for (int i = 0; i < nt; ++i) s = fmaf(An[i * nc + j], dOs[i * dp + e], s);
-    dv[(((long long)t * nc + j) * H + h) * d + e] = s;
+  {
+    const int nj = (nc - (int)rank + S - 1) / S;          // dv rows j = rank, rank + S, ...
+    for (int idx = tid; idx < nj * d; idx += 256) {
+      const int jj = idx / d, e = idx - jj * d, j = (int)rank + jj * S;
+      float s = 0.f;
+      for (int i = 0; i < nt; ++i) s = fmaf(An[i * nc + j], dOs[i * dp + e], s);
+      dv[(((long long)t * nc + j) * H + h) * d + e] = s;
+    }
   }
 
   // chunk loop: thread = (feature f = tid%128, row parity tid/128); each warp owns one quarter
   // of the chunk's features for the rows it visits -> deterministic row-sum partials.
   const int f = tid & (FC - 1), half = tid >> 7, wq = (tid >> 5) & 3;
-  for (int f0 = 0; f0 < M; f0 += FC) {
-    const int fc = M - f0 < FC ? M - f0 : FC;
+  for (int f0 = f_lo; f0 < f_hi; f0 += FC) {
+    const int fc = f_hi - f0 < FC ? f_hi - f0 : FC;
     __syncthreads();
     for (int base = tid; base < (nt + nc) * FC; base += 256 * 8) {   // loads batched as in the forward kernel
       float raw[8];
@@ -336,21 +345,31 @@ __global__ void __launch_bounds__(256) favor_attn_bwd_kernel(
     }
   }
   __syncthreads();
-  for (int i = tid; i < nt; i += 256) {
-    const long long r = ((long long)t * nt + i) * H + h;
-    const float ds = -(rq[i * 4] + rq[i * 4 + 1] + rq[i * 4 + 2] + rq[i * 4 + 3]);
-    ds_c2[r] = c2 * ds;
-    dU[r * ldu + amq[r]] += ds;  // dm_i = ds_i routed to the first row-argmax
-  }
-  if (tid == 0) {
-    float dg = 0.f;
-    for (int j = 0; j < nc; ++j) {
-      const float dt = -(rk[j * 4] + rk[j * 4 + 1] + rk[j * 4 + 2] + rk[j * 4 + 3]);
-      dt_c2[((long long)t * nc + j) * H + h] = c2 * dt;
-      dg += dt;
+  if (S > 1) cluster_sync();     // every rank's row-sum partials (shared memory) and dU / dW chunks (global) are complete
+  if (rank == 0) {
+    for (int i = tid; i < nt; i += 256) {
+      const long long r = ((long long)t * nt + i) * H + h;
+      float acc = 0.f;
+      for (int q = 0; q < S; ++q)
+        for (int w = 0; w < 4; ++w) acc += S > 1 ? ld_cluster(rq + i * 4 + w, (uint32_t)q) : rq[i * 4 + w];
+      const float ds = -acc;
+      ds_c2[r] = c2 * ds;
+      dU[r * ldu + amq[r]] += ds;  // dm_i = ds_i routed to the first row-argmax (the element may be another rank's)
     }
-    dg_part[blockIdx.x] = dg;
+    if (tid == 0) {
+      float dg = 0.f;
+      for (int j = 0; j < nc; ++j) {
+        float acc = 0.f;
+        for (int q = 0; q < S; ++q)
+          for (int w = 0; w < 4; ++w) acc += S > 1 ? ld_cluster(rk + j * 4 + w, (uint32_t)q) : rk[j * 4 + w];
+        const float dt = -acc;
+        dt_c2[((long long)t * nc + j) * H + h] = c2 * dt;
+        dg += dt;
+      }
+      dg_part[pair] = dg;
+    }
   }
+  if (S > 1) cluster_sync();     // rank 0 has read the other ranks' shared memory
 }
 
 __global__ void favor_key_fixup_kernel(float* __restrict__ dW, const float* __restrict__ W,
@@ -367,7 +386,7 @@ __global__ void favor_key_fixup_kernel(float* __restrict__ dW, const float* __re
   }
 }
 
-// B200NP_FAVOR_SPLIT = 1 | 2 | 4 | 8 (default 4): CTAs per (task, head) of the forward kernel
+// B200NP_FAVOR_SPLIT = 1 | 2 | 4 | 8 (default 4): CTAs per (task, head) of the forward and backward kernels
 int favor_split() {
   static const int v = [] {
     const char* e = getenv("B200NP_FAVOR_SPLIT");
@@ -447,8 +466,23 @@ extern "C" int b200np_favor_attn_bwd(const float* d_out, const float* U, const f
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(favor_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return B200NP_E_LAUNCH;
-  favor_attn_bwd_kernel<<<T * H, 256, smem, as_stream(stream)>>>(d_out, U, W, sq, mq, amq, tk, g, v, out, A, Dn, dU, dW,
-                                                                 dv, ds_c2, dt_c2, dg_part, H, nt, nc, d, M, ldu);
+  int S = favor_split();
+  while (S > 1 && (M + FC - 1) / FC < S) S >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(T * H * S));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = S > 1 ? 1 : 0;
+  if (cudaLaunchKernelEx(&cfg, favor_attn_bwd_kernel, d_out, U, W, sq, mq, amq, tk, g, v, out, A, Dn, dU, dW, dv, ds_c2,
+                         dt_c2, dg_part, H, nt, nc, d, M, ldu, S) != cudaSuccess)
+    return B200NP_E_LAUNCH;
   return launch_status();
 }
 
