@@ -1,4 +1,5 @@
-"""Forward / first-order backward of the MMAML conv nets on libb200np kernels.
+"""Forward, backward and (through b200np/second_order.py) second-order backward of the MMAML conv nets on libb200np
+kernels.
 
 ``GatedConvModel`` (networks/gated_conv_net.py:167-212): four blocks of 3x3 stride-2 conv -> batch-statistics
 BatchNorm (``training=True`` always, no affine) -> FiLM ``x * (1 + gamma) + beta`` (:154-159) -> ReLU with 32/64/128/256

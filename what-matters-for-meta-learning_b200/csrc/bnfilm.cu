@@ -5,8 +5,8 @@
 //   * im2col / col2im for 3x3 stride-2 pad-1 convolutions on NHWC tensors with the column order k = ci*9 + tap, i.e.
 //     the flattening of torch's [Cout, Cin, 3, 3] weight: forward, weight gradient and data gradient are then plain
 //     strided GEMMs on the tcgen05 kernel (b200np_gemm) reading the parameter tensors as they are -- any channel count;
-//   * batch statistics per channel over all N*H*W rows (two-level, deterministic; Welford merge, so no E[x^2]-E[x]^2
-//     cancellation), the fused normalise + scale/shift + ReLU, and its backward (two more column reductions + one
+//   * batch statistics per channel over all N*H*W rows (two-level, deterministic; sums and sums of squares in fp64, the
+//     mean handed on as a (hi, lo) float pair -- see bn_stats_l1_kernel), the fused normalise + scale/shift + ReLU, and its backward (two more column reductions + one
 //     elementwise pass).  scale/shift cover both users: FiLM (scale = 1 + gamma, shift = beta) and affine BatchNorm
 //     (scale = weight, shift = bias).
 #include "common.cuh"
