@@ -172,6 +172,14 @@ typedef struct b200np_gemm_desc {
   size_t workspace_bytes;
   int sum_groups;         /* nonzero: the groups are concatenated along K into ONE product,
                              C_0 = act(alpha * sum_g sum_k A_g(m,k) B_g(k,n) + ...)  (K % 32 == 0) */
+  /* Implicit 3x3 stride-2 pad-1 convolution (tensor-core modes, groups == 1): operand A (conv_operand = 1, a_cs == 1) or
+   * B (conv_operand = 2, b_cs == 1) is not a matrix in memory but the VIRTUAL im2col matrix of the NHWC tensor
+   * [n, conv_H, conv_W, conv_C] the pointer addresses: element (m, k) with m = (image, oy, ox) over conv_H/2 x conv_W/2
+   * outputs and k = tap * conv_C + ci (TAP-major, tap = r*3 + s) is x[image, 2*oy + r - 1, 2*ox + s - 1, ci], zero outside
+   * the image; conv_C % 4 == 0.  The row stride of that operand is ignored.  Forward: A virtual, B = tap-major weight
+   * [Cout][9*Cin] (b200np_conv_weight_tapmajor); weight gradient: A = dY^T, B virtual.  No column matrix is written. */
+  int conv_operand;
+  int conv_H, conv_W, conv_C;
 } b200np_gemm_desc;
 /* bytes of scratch with which b200np_gemm spreads the K range of a GEMM with few output tiles over the idle
  * SMs (deterministic: partial tiles are reduced in a fixed order); 0 when the shape does not profit */
@@ -307,6 +315,10 @@ int b200np_adam_step_dev(float* p, const float* g, float* m, float* v, long long
  * Backward: dshift = sum g, dscale = sum g * xhat (g = dy gated by y > 0 when relu), dx = the usual batch-norm data
  * gradient.  Workspace: b200np_bn_workspace(rows, C) bytes.
  * ------------------------------------------------------------------------------------------ */
+/* tap-major <-> torch layout of a 3x3 conv weight: wt[co][tap*Cin + ci] = w[co][ci][tap] (to_tapmajor != 0) or the inverse */
+int b200np_conv_weight_tapmajor(const float* src, float* dst, int Cout, int Cin, int to_tapmajor, void* stream);
+/* col2im of a TAP-major column-gradient matrix [N*(H/2)*(W/2), 9*C] (k = tap*C + ci), C % 4 == 0: 16-byte gathers */
+int b200np_col2im3x3s2_tapmajor(const float* dcol, const float* mask, float* dx, int N, int H, int W, int C, void* stream);
 int b200np_im2col3x3s2(const float* x, float* col, int N, int H, int W, int C, void* stream);
 int b200np_col2im3x3s2(const float* dcol, const float* mask, float* dx, int N, int H, int W, int C, void* stream);
 size_t b200np_bn_workspace(long long rows, int C);

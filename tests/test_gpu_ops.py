@@ -502,3 +502,50 @@ def test_favor_cluster_split_variants_agree(tmp_path):
             if not e <= tol:
                 bad.append((S, k, e))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("N,H,Cin,Cout", [(3, 16, 32, 48), (2, 32, 48, 64), (5, 16, 8, 64), (70, 16, 32, 48)])
+def test_implicit_conv_gemm(prec, N, H, Cin, Cout):
+    """b200np_gemm with a VIRTUAL tap-major im2col operand (conv_operand): forward (A virtual), weight gradient (B virtual)
+    and the tap-major col2im, against F.conv2d and its autograd (3x3, stride 2, padding 1)."""
+    ops = _ops()
+    P = PRECS[prec]
+    x = rnd(N, Cin, H, H, seed=1)
+    w = rnd(Cout, Cin, 3, 3, seed=2, scale=0.2)
+    b = rnd(Cout, seed=3)
+    dy = rnd(N, Cout, H // 2, H // 2, seed=4)
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    y_ref = F.conv2d(xr, wr, b, stride=2, padding=1)
+    y_ref.backward(dy)
+    xg, dyg = nhwc(x), nhwc(dy)
+    wt = ops.conv_weight_tapmajor(w.float().cuda())
+    assert torch.equal(ops.conv_weight_tapmajor(wt, to_tapmajor=False).cpu(), w.float())
+    M, K = N * (H // 2) ** 2, 9 * Cin
+    y = torch.full((N, H // 2, H // 2, Cout), float("nan"), device="cuda")
+    ops.gemm(xg.data_ptr(), wt.data_ptr(), y.data_ptr(), M, Cout, K, K, 1, 1, K, Cout, bias=b.float().cuda().data_ptr(),
+             prec=P, conv=(1, H, H, Cin))
+    assert rel(y.permute(0, 3, 1, 2), y_ref) < TOL[prec]
+    dwt = torch.full((Cout, K), float("nan"), device="cuda")
+    ops.gemm(dyg.data_ptr(), xg.data_ptr(), dwt.data_ptr(), Cout, K, M, 1, Cout, K, 1, K, prec=P, conv=(2, H, H, Cin))
+    assert rel(ops.conv_weight_tapmajor(dwt, to_tapmajor=False), wr.grad) < TOL[prec]
+    dcol = torch.empty(M, K, device="cuda")
+    ops.gemm(dyg.data_ptr(), wt.data_ptr(), dcol.data_ptr(), M, K, Cout, Cout, 1, K, 1, K, prec=P)
+    dx = ops.col2im3x3s2_tapmajor(dcol, tuple(xg.shape))
+    assert rel(dx.permute(0, 3, 1, 2), xr.grad) < TOL[prec]
+    gate = (x > 0).float()
+    dxm = ops.col2im3x3s2_tapmajor(dcol, tuple(xg.shape), mask=nhwc(x))
+    assert rel(dxm.permute(0, 3, 1, 2), xr.grad * gate) < TOL[prec]
+
+
+def test_implicit_conv_gemm_refuses_what_it_cannot_do():
+    """The implicit convolution exists on the tensor-core path only: fp32 mode, a channel count that is not a multiple of
+    four or a product too small for a tile raise instead of silently taking another route."""
+    ops = _ops()
+    from b200np import lib
+    x = torch.zeros(2, 8, 8, 8, device="cuda")
+    wt = torch.zeros(16, 72, device="cuda")
+    y = torch.zeros(2, 4, 4, 16, device="cuda")
+    for prec, conv in ((lib.PREC_FP32_SIMT, (1, 8, 8, 8)), (lib.PREC_TF32X3, (1, 8, 8, 6)), (lib.PREC_TF32X3, (1, 8, 8, 8))):
+        with pytest.raises(lib.B200NPError):
+            ops.gemm(x.data_ptr(), wt.data_ptr(), y.data_ptr(), 32, 16, 72, 72, 1, 1, 72, 16, prec=prec, conv=conv)

@@ -74,6 +74,7 @@ _SIDE = {}
 MAIN_PRIORITY, DECODER_PRIORITY, WGRAD_PRIORITY = -2, -1, 0
 USE_PRIORITIES = os.environ.get("B200NP_PRIO", "1") != "0"
 FORK = os.environ.get("B200NP_FORK", "early")   # where the decoder branch forks: early | late (see the forward)
+W0_IMPLICIT = os.environ.get("B200NP_W0_IMPLICIT", "1") != "0"   # encoder_w0's 3x3 convs as implicit-convolution GEMMs
 
 
 # Called at the start of every CNN trunk's backward with the data pointer of the trunk's first parameter.  By then every
@@ -244,10 +245,24 @@ class EncoderW0Fn(Function):
             x3, pidx = ops.maxpool2x2_fwd(x2)
             x4 = ops.conv_fwd(x3, wd5, b5, 2, ACT_RELU, prec)
             col2 = col5 = None
+        elif W0_IMPLICIT:
+            # 32 -> 48 and 48 -> 64 channels do not fill the 64 x 64 tap-convolution tiles: the tcgen05 GEMM with a VIRTUAL
+            # im2col operand (b200np_gemm_desc.conv_operand: k = tap*C + ci, gathered as 16-byte words while the operand
+            # is staged) and a fused bias + ReLU epilogue -- no column matrix is written or read (it was 354 MB for the
+            # 32 -> 48 layer of 300 images, written once and read twice per step)
+            wd2 = wd5 = col2 = col5 = None
+            w2, w5 = ops.conv_weight_tapmajor(w2), ops.conv_weight_tapmajor(w5)      # [Cout, 9*Cin], tap-major
+            M2, K2 = N * (H // 4) * (W // 4), w2.shape[1]
+            x2 = ops.empty((N, H // 4, W // 4, w2.shape[0]), imgs[0])
+            ops.gemm(_p(x1), _p(w2), _p(x2), M2, w2.shape[0], K2, K2, 1, 1, K2, w2.shape[0], bias=_p(b2), act=ACT_RELU,
+                     prec=prec, conv=(1, H // 2, W // 2, x1.shape[-1]))
+            x3, pidx = ops.maxpool2x2_fwd(x2)
+            M5, K5 = N * (H // 16) * (W // 16), w5.shape[1]
+            x4 = ops.empty((N, H // 16, W // 16, w5.shape[0]), imgs[0])
+            ops.gemm(_p(x3), _p(w5), _p(x4), M5, w5.shape[0], K5, K5, 1, 1, K5, w5.shape[0], bias=_p(b5), act=ACT_RELU,
+                     prec=prec, conv=(1, H // 8, W // 8, x3.shape[-1]))
         else:
-            # 32 -> 48 and 48 -> 64 channels do not fill the 64 x 64 tap-convolution tiles: im2col (k = ci*9 + tap, the
-            # flattening of torch's weight) + the tcgen05 GEMM with a fused bias + ReLU epilogue; the backward is two more
-            # GEMMs on the same column matrix (82 % of encoder_w0's FLOPs used to run on CUDA cores)
+            # B200NP_W0_IMPLICIT=0: explicit im2col (k = ci*9 + tap, the flattening of torch's weight) + the tcgen05 GEMM
             wd2 = wd5 = None
             col2 = ops.im2col3x3s2(x1)
             x2 = ops.empty((N, H // 4, W // 4, w2.shape[0]), imgs[0])
@@ -277,12 +292,26 @@ class EncoderW0Fn(Function):
         for n, do in zip(Ns, douts):
             ops.nchw_flat_to_nhwc(do.contiguous(), x4[off:off + n], d4[off:off + n])
             off += n
-        if col2 is None:
+        if wd2 is not None:
             dw5, db5, _ = ops.conv_wgrad(x3, d4, 3, 2, prec)
             d3 = ops.conv_dgrad(d4, wd5, x3.shape, 2, prec, mask_src=None)
             d2 = ops.maxpool2x2_bwd(d3, pidx, x2)
             dw2, db2, _ = ops.conv_wgrad(x1, d2, 3, 2, prec)
             d1 = ops.conv_dgrad(d2, wd2, x1.shape, 2, prec, mask_src=x1)
+        elif col2 is None:
+            def conv_bwd(x_in, wt, dy, mask):     # wt: tap-major [Cout, 9*Cin]; x_in NHWC, the conv's input
+                Co, K = wt.shape
+                M = dy.numel() // Co
+                _, Hi, Wi, Ci = x_in.shape
+                dwt = ops.empty((Co, K), wt)
+                ops.gemm(_p(dy), _p(x_in), _p(dwt), Co, K, M, 1, Co, K, 1, K, prec=prec, conv=(2, Hi, Wi, Ci))   # dW = dY^T col(x)
+                db = ops.colsum(dy, M, Co, Co)
+                dcol = ops.empty((M, K), dy)
+                ops.gemm(_p(dy), _p(wt), _p(dcol), M, K, Co, Co, 1, K, 1, K, prec=prec)                            # dcol = dY W
+                return ops.conv_weight_tapmajor(dwt, to_tapmajor=False), db, ops.col2im3x3s2_tapmajor(dcol, x_in.shape, mask=mask)
+            dw5, db5, d3 = conv_bwd(x3, w5, d4, None)
+            d2 = ops.maxpool2x2_bwd(d3, pidx, x2)
+            dw2, db2, d1 = conv_bwd(x1, w2, d2, x1)
         else:
             def conv_bwd(col, w, dy, x_shape, mask):
                 M, K = col.shape

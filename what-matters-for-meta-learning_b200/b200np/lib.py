@@ -21,7 +21,8 @@ class GemmDesc(C.Structure):
                 ("M", _i), ("N", _i), ("K", _i), ("a_rs", _ll), ("a_cs", _ll), ("b_rs", _ll),
                 ("b_cs", _ll), ("ldc", _ll), ("alpha", _f), ("beta", _f), ("act", _i),
                 ("row_scale", _p), ("addend", _p), ("ld_add", _ll), ("precision", _i),
-                ("workspace", _p), ("workspace_bytes", _sz), ("sum_groups", _i)]
+                ("workspace", _p), ("workspace_bytes", _sz), ("sum_groups", _i),
+                ("conv_operand", _i), ("conv_H", _i), ("conv_W", _i), ("conv_C", _i)]
 
 
 # name: (restype, [argtypes])  -- one entry per symbol in include/b200np.h
@@ -71,6 +72,8 @@ SIGNATURES = {
     "b200np_adam_step_dev": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _f, _p]),
     "b200np_im2col3x3s2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "b200np_col2im3x3s2": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "b200np_conv_weight_tapmajor": (_i, [_p, _p, _i, _i, _i, _p]),
+    "b200np_col2im3x3s2_tapmajor": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "b200np_bn_workspace": (_sz, [_ll, _i]),
     "b200np_bn_act_fwd": (_i, [_p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _f, _ll, _i, _i, _p, _sz, _p]),
     "b200np_bn_act_bwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _ll, _i, _i, _p, _sz, _p]),

@@ -208,9 +208,10 @@ def maxpool2x2_bwd(dy, idx, x_saved):
 # GEMM and friends
 # ----------------------------------------------------------------------------------------------
 def gemm(A, B, Cmat, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, bias=None, alpha=1.0, beta=0.0, act=lib.ACT_NONE,
-         row_scale=None, addend=None, ld_add=0, prec=lib.PREC_FP32_SIMT, sum_groups=False):
+         row_scale=None, addend=None, ld_add=0, prec=lib.PREC_FP32_SIMT, sum_groups=False, conv=None):
     """A, B, Cmat, bias: device pointers (ints) or lists of up to 8 of them (grouped).  sum_groups: the groups
-    are K-slices of one product written to Cmat[0]."""
+    are K-slices of one product written to Cmat[0].  conv = (operand, H, W, C): operand 1 (A) or 2 (B) is the virtual
+    tap-major im2col matrix of the NHWC tensor its pointer addresses (include/b200np.h)."""
     d = GemmDesc()
     As = A if isinstance(A, (list, tuple)) else [A]
     Bs = B if isinstance(B, (list, tuple)) else [B]
@@ -227,6 +228,7 @@ def gemm(A, B, Cmat, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, bias=None, alpha=1.0,
     d.addend = 0 if addend is None else addend.data_ptr()
     d.ld_add, d.precision = ld_add, prec
     d.workspace, d.workspace_bytes, d.sum_groups = 0, 0, int(sum_groups)
+    d.conv_operand, d.conv_H, d.conv_W, d.conv_C = conv if conv is not None else (0, 0, 0, 0)
     ws_bytes = LIB.b200np_gemm_workspace(C.byref(d))
     if ws_bytes:  # split-K scratch for the GEMMs with too few output tiles to fill the chip
         ws = torch.empty(ws_bytes // 4, device="cuda", dtype=F32)
@@ -390,6 +392,27 @@ def col2im3x3s2(dcol, x_shape, mask=None):
     N, H, W, Cc = x_shape
     dx = empty(tuple(x_shape), dcol)
     check(LIB.b200np_col2im3x3s2(_ptr(dcol), _ptr(mask), _ptr(dx), N, H, W, Cc, _stream()), "col2im3x3s2")
+    return dx
+
+
+def conv_weight_tapmajor(w, to_tapmajor=True):
+    """[Cout, Cin, 3, 3] -> [Cout, 9 * Cin] with k = tap * Cin + ci, or back (same shapes reversed)."""
+    _chk(w, "w")
+    if to_tapmajor:
+        Cout, Cin = w.shape[0], w.shape[1]
+        out = empty((Cout, 9 * Cin), w)
+    else:
+        Cout, Cin = w.shape[0], w.shape[1] // 9
+        out = empty((Cout, Cin, 3, 3), w)
+    check(LIB.b200np_conv_weight_tapmajor(_ptr(w), _ptr(out), Cout, Cin, int(to_tapmajor), _stream()), "conv_weight_tapmajor")
+    return out
+
+
+def col2im3x3s2_tapmajor(dcol, x_shape, mask=None):
+    _chk(dcol, "dcol"), _chk(mask, "mask")
+    N, H, W, Cc = x_shape
+    dx = empty(tuple(x_shape), dcol)
+    check(LIB.b200np_col2im3x3s2_tapmajor(_ptr(dcol), _ptr(mask), _ptr(dx), N, H, W, Cc, _stream()), "col2im3x3s2_tapmajor")
     return dx
 
 

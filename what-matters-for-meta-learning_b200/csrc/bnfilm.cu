@@ -75,6 +75,58 @@ __global__ void col2im3x3s2_kernel(const float* __restrict__ dcol, const float* 
   }
 }
 
+// TAP-major variants (k = tap*C + ci) for the implicit-convolution GEMM (b200np_gemm_desc.conv_operand): the channel
+// vector of a pixel is contiguous in the column matrix, so everything moves as 16-byte words.
+__global__ void conv_weight_tapmajor_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin, int fwd) {
+  const int total = Cout * Cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i / (Cin * 9), rem = i - co * Cin * 9;
+    if (fwd) {                       // i indexes dst [co][tap][ci]
+      const int tap = rem / Cin, ci = rem - tap * Cin;
+      dst[i] = __ldg(src + (co * Cin + ci) * 9 + tap);
+    } else {                         // i indexes dst [co][ci][tap]
+      const int ci = rem / 9, tap = rem - ci * 9;
+      dst[i] = __ldg(src + (co * 9 + tap) * Cin + ci);
+    }
+  }
+}
+__global__ void col2im3x3s2_tapmajor_kernel(const float* __restrict__ dcol, const float* __restrict__ mask,
+                                            float* __restrict__ dx, int N, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2, C4 = C / 4;
+  const long long total = (long long)N * H * W * C4;
+  const long long st = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += st) {
+    const int c4 = (int)(i % C4);
+    const long long p = i / C4;
+    const int xx = (int)(p % W);
+    const long long q = p / W;
+    const int yy = (int)(q % H), n = (int)(q / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ty = yy + 1 - r;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= OH) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int tx = xx + 1 - s;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= OW) continue;
+        const float4 v = ldg4(dcol + (((long long)n * OH + oy) * OW + ox) * (9LL * C) + (r * 3 + s) * C + 4 * c4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    if (mask) {
+      const float4 mk = ldg4(mask + p * C + 4 * c4);
+      acc.x = mk.x > 0.f ? acc.x : 0.f; acc.y = mk.y > 0.f ? acc.y : 0.f;
+      acc.z = mk.z > 0.f ? acc.z : 0.f; acc.w = mk.w > 0.f ? acc.w : 0.f;
+    }
+    *reinterpret_cast<float4*>(dx + p * C + 4 * c4) = acc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Column statistics of a [R, C] matrix.  Level 1: block (32 channels x 8 row lanes) over a row slice -> (count, mean,
 // M2) per channel, merged across the 8 lanes in shared memory; level 2: one thread per channel merges the slices in
@@ -315,6 +367,20 @@ extern "C" int b200np_col2im3x3s2(const float* dcol, const float* mask, float* d
   if (!dcol || !dx || N <= 0 || C <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1)) return B200NP_E_BADARG;
   const long long total = (long long)N * H * W * C;
   col2im3x3s2_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(dcol, mask, dx, N, H, W, C);
+  return launch_status();
+}
+extern "C" int b200np_conv_weight_tapmajor(const float* src, float* dst, int Cout, int Cin, int to_tapmajor, void* stream) {
+  if (!src || !dst || Cout <= 0 || Cin <= 0) return B200NP_E_BADARG;
+  conv_weight_tapmajor_kernel<<<ew_grid((long long)Cout * Cin * 9, 256), 256, 0, as_stream(stream)>>>(src, dst, Cout, Cin,
+                                                                                                      to_tapmajor);
+  return launch_status();
+}
+extern "C" int b200np_col2im3x3s2_tapmajor(const float* dcol, const float* mask, float* dx, int N, int H, int W, int C,
+                                           void* stream) {
+  if (!dcol || !dx || N <= 0 || C <= 0 || (C & 3) || H < 2 || W < 2 || (H & 1) || (W & 1)) return B200NP_E_BADARG;
+  if (!aligned16(dcol) || !aligned16(dx) || (mask && !aligned16(mask))) return B200NP_E_BADARG;
+  const long long total = (long long)N * H * W * (C / 4);
+  col2im3x3s2_tapmajor_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(dcol, mask, dx, N, H, W, C);
   return launch_status();
 }
 extern "C" size_t b200np_bn_workspace(long long rows, int C) {

@@ -225,6 +225,7 @@ extern "C" int b200np_gemm(const b200np_gemm_desc* dp, void* stream) {
     int rc = launch_gemm_umma(g.d, g.a_vec, g.b_vec, as_stream(stream));
     if (rc != B200NP_E_UNSUPPORTED) return rc;
   }
+  if (d.conv_operand) return B200NP_E_UNSUPPORTED;   // the implicit convolution exists on the tensor-core path only
   if (d.sum_groups) {  // CUDA-core path: one accumulating launch per K-slice, epilogue on the last
     for (int i = 0; i < d.groups; ++i) {
       GemmArgs gi = g;

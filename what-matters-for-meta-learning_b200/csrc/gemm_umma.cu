@@ -64,7 +64,9 @@ constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3
 // that bias / beta*C / row_scale*addend / activation and the store all run on coalesced float4 rows.
 // 3xTF32: the B tile's hi and lo halves are adjacent, so one N = 128 MMA forms A_hi*[B_hi|B_lo] and an N = 64
 // MMA adds A_lo*B_hi to the cross-term columns; two rotating 128-column accumulator blocks (see umma.cuh).
-template <bool X3, bool AK, bool BK>
+// CONV: 0 = plain operands; 1 / 2 = operand A / B is the virtual im2col matrix of an implicit convolution (own
+// instantiations, so that the plain GEMMs carry none of its registers or branches)
+template <bool X3, bool AK, bool BK, int CONV = 0>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_umma_kernel(const GemmUArgs g) {
   constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kGA + kGB);
   constexpr uint32_t kCols = X3 ? 256u : 64u;
@@ -115,6 +117,33 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_umma_kernel(const GemmUA
   for (int j = 0; j < 2; ++j)
     b_off[j] = BK ? sw128_offset((tid >> 3) + 32 * j, tid & 7) : mn_off((tid & 15) >> 3, (tid >> 4) + 16 * j, tid & 7);
 
+  // implicit convolution (d.conv_operand): per-thread geometry of the virtual im2col operand.  cv_y / cv_x: input
+  // coordinates of tap (0, 0) of the thread's pixels (2*oy - 1, 2*ox - 1), cv_img: element offset of their image;
+  // cv_r / cv_s / cv_ci: the tap and first channel of the thread's four consecutive k.
+  int cv_y[4] = {0, 0, 0, 0}, cv_x[4] = {0, 0, 0, 0}, cv_r = 0, cv_s = 0, cv_ci = 0;
+  long long cv_img[4] = {0, 0, 0, 0};
+  const int cv_OW = d.conv_W >> 1, cv_OH = d.conv_H >> 1;
+  if (CONV != 0) {
+    const int rows = CONV == 1 ? 4 : 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i >= rows) break;
+      // A: output pixel = GEMM row m (K-block invariant); B: output pixel = contraction index of the first K-block
+      const long long pix = CONV == 1 ? (long long)m0 + (tid >> 3) + 32 * i
+                                                : (long long)kb_lo * 32 + (tid >> 4) + 16 * i;
+      const int ox = (int)(pix % cv_OW);
+      const long long q = pix / cv_OW;
+      cv_x[i] = 2 * ox - 1;
+      cv_y[i] = 2 * (int)(q % cv_OH) - 1;
+      cv_img[i] = (q / cv_OH) * d.conv_H * d.conv_W * d.conv_C;
+    }
+    if (CONV == 2) {        // B: this thread's four consecutive columns n = one tap, four channels
+      const int nn = n0 + (tid & 15) * 4, tap = nn / d.conv_C;
+      cv_ci = nn - tap * d.conv_C;
+      cv_r = tap / 3;
+      cv_s = tap - 3 * cv_r;
+    }
+  }
   float4 av0[4], bv0[2], av1[4], bv1[2];
   auto fetch = [&](int kb, float4 (&av)[4], float4 (&bv)[2]) {
     const int kbt = kb_lo + kb;
@@ -122,11 +151,22 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_umma_kernel(const GemmUA
     const int k0 = (kbt - (d.sum_groups ? gsel * KB_grp : 0)) * 32;
     const float* __restrict__ A = d.A[gsel];
     const float* __restrict__ B = d.B[gsel];
+    if (CONV == 1) {        // this thread's 4 consecutive k of the K-block: one tap, four channels
+      const int kk = k0 + (tid & 7) * 4, tap = kk / d.conv_C;
+      cv_ci = kk - tap * d.conv_C;
+      cv_r = tap / 3;
+      cv_s = tap - 3 * cv_r;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (AK) {
         const int m = m0 + (tid >> 3) + 32 * i, k = k0 + (tid & 7) * 4;
-        av[i] = load4_guarded(A + (long long)m * d.a_rs + k, m < M ? K - k : 0, g.a_vec);
+        if (CONV == 1) {   // virtual im2col row: the pixel geometry is K-block invariant, (tap, ci) row invariant
+          const int iy = cv_y[i] + cv_r, ix = cv_x[i] + cv_s;
+          av[i] = (k < K && iy >= 0 && iy < d.conv_H && ix >= 0 && ix < d.conv_W)
+                      ? ldg4(A + cv_img[i] + ((long long)iy * d.conv_W + ix) * d.conv_C + cv_ci)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else av[i] = load4_guarded(A + (long long)m * d.a_rs + k, m < M ? K - k : 0, g.a_vec);
       } else {
         const int k = k0 + (tid >> 5) + 8 * i, m = m0 + (tid & 31) * 4;
         av[i] = load4_guarded(A + (long long)k * d.a_cs + m, k < K ? M - m : 0, g.a_vec);
@@ -139,7 +179,24 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_umma_kernel(const GemmUA
         bv[j] = load4_guarded(B + (long long)n * d.b_cs + k, n < N ? K - k : 0, g.b_vec);
       } else {
         const int k = k0 + (tid >> 4) + 16 * j, n = n0 + (tid & 15) * 4;
-        bv[j] = load4_guarded(B + (long long)k * d.b_rs + n, k < K ? N - n : 0, g.b_vec);
+        if (CONV == 2) {   // virtual im2col column block: (tap, ci) is thread invariant, the pixel walks with k
+          const int iy = cv_y[j] + cv_r, ix = cv_x[j] + cv_s;
+          bv[j] = (k < K && n < N && iy >= 0 && iy < d.conv_H && ix >= 0 && ix < d.conv_W)
+                      ? ldg4(B + cv_img[j] + ((long long)iy * d.conv_W + ix) * d.conv_C + cv_ci)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else bv[j] = load4_guarded(B + (long long)k * d.b_rs + n, k < K ? N - n : 0, g.b_vec);
+      }
+    }
+    if (CONV == 2) {        // the next call fetches the next K-block: both pixels move on by 32
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        int ox = ((cv_x[j] + 1) >> 1) + 32, oy = (cv_y[j] + 1) >> 1;
+        while (ox >= cv_OW) {
+          ox -= cv_OW;
+          if (++oy == cv_OH) { oy = 0; cv_img[j] += (long long)d.conv_H * d.conv_W * d.conv_C; }
+        }
+        cv_x[j] = 2 * ox - 1;
+        cv_y[j] = 2 * oy - 1;
       }
     }
   };
@@ -294,19 +351,19 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_umma_kernel(const GemmUA
   }
 }
 
-template <bool X3, bool AK, bool BK>
+template <bool X3, bool AK, bool BK, int CONV = 0>
 int launch(const GemmUArgs& g, cudaStream_t st) {
   constexpr uint32_t kStageBytes = (X3 ? 2u : 1u) * (kGA + kGB);
   const size_t smem = kStages * kStageBytes + 1024 + 64;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_umma_kernel<X3, AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+    if (cudaFuncSetAttribute(gemm_umma_kernel<X3, AK, BK, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
       return B200NP_E_LAUNCH;
     configured = true;
   }
   dim3 grid((g.d.M + 127) / 128, (g.d.N + 63) / 64, (g.d.sum_groups ? 1 : g.d.groups) * g.splits);
-  gemm_umma_kernel<X3, AK, BK><<<grid, kGemmThreads, smem, st>>>(g);
+  gemm_umma_kernel<X3, AK, BK, CONV><<<grid, kGemmThreads, smem, st>>>(g);
   return launch_status();
 }
 
@@ -349,7 +406,14 @@ int launch_gemm_umma(const b200np_gemm_desc& d, int a_vec, int b_vec, cudaStream
   if (d.precision == B200NP_PREC_FP32_SIMT) return B200NP_E_UNSUPPORTED;
   if (d.K < 32 || d.N < 16 || (long long)d.M * d.N < 64 * 64) return B200NP_E_UNSUPPORTED;  // tiny: not worth a tile
   const bool AK = d.a_cs == 1, BK = d.b_rs == 1;
-  if (!AK && BK) return B200NP_E_UNSUPPORTED;
+  if (d.conv_operand) {   // implicit convolution: only here (no CUDA-core form), so every refusal is an error
+    if (d.groups != 1 || d.sum_groups || (d.conv_C & 3) || d.conv_C <= 0 || (d.conv_H & 1) || (d.conv_W & 1) ||
+        d.conv_H < 2 || d.conv_W < 2)
+      return B200NP_E_BADARG;
+    if (d.conv_operand == 1 ? !AK : (d.conv_operand != 2 || BK)) return B200NP_E_BADARG;
+    if (!aligned16(d.conv_operand == 1 ? d.A[0] : d.B[0])) return B200NP_E_BADARG;
+  } else if (!AK && BK) return B200NP_E_UNSUPPORTED;
+  if (!AK && BK) return B200NP_E_BADARG;
   if (d.sum_groups && d.K % 32 != 0) return B200NP_E_UNSUPPORTED;  // (A m-contiguous, B k-contiguous) never occurs on the path
   GemmUArgs g;
   g.d = d;
@@ -359,7 +423,13 @@ int launch_gemm_umma(const b200np_gemm_desc& d, int a_vec, int b_vec, cudaStream
   if ((size_t)g.splits * d.M * d.N * sizeof(float) > d.workspace_bytes || !d.workspace) g.splits = 1;
   const bool x3 = d.precision != B200NP_PREC_TF32;
   int rc;
-  if (AK && BK) rc = x3 ? launch<true, true, true>(g, st) : launch<false, true, true>(g, st);
+  if (d.conv_operand == 1) {
+    if (!BK) return B200NP_E_BADARG;   // forward form: weights k-contiguous
+    rc = x3 ? launch<true, true, true, 1>(g, st) : launch<false, true, true, 1>(g, st);
+  } else if (d.conv_operand == 2) {
+    if (AK) return B200NP_E_BADARG;    // weight-gradient form: A = dY^T
+    rc = x3 ? launch<true, false, false, 2>(g, st) : launch<false, false, false, 2>(g, st);
+  } else if (AK && BK) rc = x3 ? launch<true, true, true>(g, st) : launch<false, true, true>(g, st);
   else if (AK && !BK) rc = x3 ? launch<true, true, false>(g, st) : launch<false, true, false>(g, st);
   else rc = x3 ? launch<true, false, false>(g, st) : launch<false, false, false>(g, st);
   if (rc != B200NP_OK || g.splits == 1) return rc;
