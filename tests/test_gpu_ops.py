@@ -176,19 +176,20 @@ def test_pools_and_flatten():
     assert torch.equal(flat.cpu(), x2.reshape(3, -1).float())
     back = ops.nchw_flat_to_nhwc(flat, None, torch.empty(3, 2, 2, 64, device="cuda"), mask=False)
     assert torch.equal(from_nhwc(back).cpu(), x2.float())
-    # MaxPool2d(2,2)
-    x3 = F.relu(rnd(2, 48, 8, 8, seed=4))
-    x3[0, 0, 0:2, 0:2] = 1.5
-    x3.requires_grad_()
-    ref3, idx3 = F.max_pool2d(x3, 2, return_indices=True)
-    y3, i3 = ops.maxpool2x2_fwd(nhwc(x3.detach()))
-    assert torch.equal(from_nhwc(y3).cpu(), ref3.float())
-    iy, ix = idx3 // 8, idx3 % 8
-    assert torch.equal(from_nhwc(i3).cpu().long(), (iy % 2) * 2 + ix % 2)
-    g3 = rnd(*ref3.shape, seed=5)
-    ref3.backward(g3)
-    d3 = ops.maxpool2x2_bwd(nhwc(g3), i3, nhwc(x3.detach()))
-    assert rel(from_nhwc(d3), x3.grad * (x3 > 0)) < 1e-6
+    # MaxPool2d(2,2): 48 channels take the 16-byte kernels, 6 channels the scalar ones
+    for Cp in (48, 6):
+        x3 = F.relu(rnd(2, Cp, 8, 8, seed=4))
+        x3[0, 0, 0:2, 0:2] = 1.5
+        x3.requires_grad_()
+        ref3, idx3 = F.max_pool2d(x3, 2, return_indices=True)
+        y3, i3 = ops.maxpool2x2_fwd(nhwc(x3.detach()))
+        assert torch.equal(from_nhwc(y3).cpu(), ref3.float())
+        iy, ix = idx3 // 8, idx3 % 8
+        assert torch.equal(from_nhwc(i3).cpu().long(), (iy % 2) * 2 + ix % 2)
+        g3 = rnd(*ref3.shape, seed=5)
+        ref3.backward(g3)
+        d3 = ops.maxpool2x2_bwd(nhwc(g3), i3, nhwc(x3.detach()))
+        assert rel(from_nhwc(d3), x3.grad * (x3 > 0)) < 1e-6
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32x3", "tf32"])
