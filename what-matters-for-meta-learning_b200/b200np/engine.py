@@ -235,10 +235,11 @@ class EncoderW0Fn(Function):
         N = sum(Ns)
         _, H, W = imgs[0].shape[1:]
         x1 = ops.empty((N, H // 2, W // 2, w0.shape[0]), imgs[0])
-        off = 0
-        for im, n in zip(imgs, Ns):
-            ops.conv_small_fwd(im, w0, b0, out=x1[off:off + n], relu=True, prec=prec)
-            off += n
+        # the sources (context / target images) as ONE batch: one launch of the first conv and of its weight gradient
+        # instead of one per source (20 MB copied once against two half-filled launches each way)
+        img_all = imgs[0].contiguous() if n_src == 1 else torch.cat([im.reshape(im.shape[0], -1) for im in imgs]).view(
+            N, *imgs[0].shape[1:])
+        ops.conv_small_fwd(img_all, w0, b0, out=x1, relu=True, prec=prec)
         if prec == PREC_FP32_SIMT:
             wd2, wd5 = ops.pack_conv_weight(w2), ops.pack_conv_weight(w5)
             x2 = ops.conv_fwd(x1, wd2, b2, 2, ACT_RELU, prec)
@@ -277,7 +278,7 @@ class EncoderW0Fn(Function):
         for n in Ns:
             outs.append(ops.nhwc_to_nchw_flat(x4[off:off + n]))
             off += n
-        ctx.prec, ctx.Ns, ctx.imgs = prec, Ns, imgs
+        ctx.prec, ctx.Ns, ctx.imgs = prec, Ns, img_all
         ctx.first_param_ptr = w0.data_ptr()
         ctx.saved = (x1, x2, x3, x4, pidx, wd2, wd5, tuple(w0.shape), col2, col5, w2, w5)
         return tuple(outs)
@@ -325,15 +326,7 @@ class EncoderW0Fn(Function):
             dw5, db5, d3 = conv_bwd(col5, w5, d4, x3.shape, None)
             d2 = ops.maxpool2x2_bwd(d3, pidx, x2)
             dw2, db2, d1 = conv_bwd(col2, w2, d2, x1.shape, x1)
-        off, dw0, db0 = 0, None, None
-        for im, n in zip(ctx.imgs, Ns):
-            dw, db = ops.conv_small_wgrad(im, d1[off:off + n], w0_shape, prec)
-            if dw0 is None:
-                dw0, db0 = dw, db
-            else:
-                ops.axpy(dw0, dw)
-                ops.axpy(db0, db)
-            off += n
+        dw0, db0 = ops.conv_small_wgrad(ctx.imgs, d1, w0_shape, prec)
         return (None, None) + (None,) * len(Ns) + (dw0, db0, dw2, db2, dw5, db5)
 
 

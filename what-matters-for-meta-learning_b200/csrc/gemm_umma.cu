@@ -396,7 +396,7 @@ int gemm_umma_splits(const b200np_gemm_desc& d) {
   const int tiles = ((d.M + 127) / 128) * ((d.N + 63) / 64);
   const int KB = ((d.K + 31) / 32) * (d.sum_groups ? d.groups : 1);
   if (tiles * 2 > kNumSMs || KB < 8) return 1;
-  int s = kNumSMs / tiles;
+  int s = 2 * kNumSMs / tiles;   // two CTAs are resident per SM, and a CTA's K-blocks run one after the other
   if (s > KB / 4) s = KB / 4;
   return s > 1 ? s : 1;
 }
