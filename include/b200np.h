@@ -315,6 +315,11 @@ int b200np_adam_step_dev(float* p, const float* g, float* m, float* v, long long
  * Backward: dshift = sum g, dscale = sum g * xhat (g = dy gated by y > 0 when relu), dx = the usual batch-norm data
  * gradient.  Workspace: b200np_bn_workspace(rows, C) bytes.
  * ------------------------------------------------------------------------------------------ */
+/* im2col of an NCHW image with few channels for an R x R stride-2 convolution (the stems `nn.Conv2d(C,64,5,2,2)`,
+ * networks/ResNet.py; `encoder_w0[0]`, CNPShapeNet1D.py:47): col [N*(H/2)*(W/2), ld], col[m][ci*R*R + r*R + s], columns
+ * beyond Cin*R*R zero.  With b200np_gemm (forward: col x W^T + bias, ReLU; weight gradient: dY^T x col) it replaces the
+ * CUDA-core direct convolution where the tcgen05 stem kernel (1 channel, 5x5, 64 outputs) does not apply. */
+int b200np_im2col_small(const float* x, float* col, int N, int Cin, int H, int W, int R, int pad, int ld, void* stream);
 /* tap-major <-> torch layout of a 3x3 conv weight: wt[co][tap*Cin + ci] = w[co][ci][tap] (to_tapmajor != 0) or the inverse */
 int b200np_conv_weight_tapmajor(const float* src, float* dst, int Cout, int Cin, int to_tapmajor, void* stream);
 /* col2im of a TAP-major column-gradient matrix [N*(H/2)*(W/2), 9*C] (k = tap*C + ci), C % 4 == 0: 16-byte gathers */

@@ -550,3 +550,32 @@ def test_implicit_conv_gemm_refuses_what_it_cannot_do():
     for prec, conv in ((lib.PREC_FP32_SIMT, (1, 8, 8, 8)), (lib.PREC_TF32X3, (1, 8, 8, 6)), (lib.PREC_TF32X3, (1, 8, 8, 8))):
         with pytest.raises(lib.B200NPError):
             ops.gemm(x.data_ptr(), wt.data_ptr(), y.data_ptr(), 32, 16, 72, 72, 1, 1, 72, 16, prec=prec, conv=conv)
+
+
+@pytest.mark.parametrize("Cin,R,Cout", [(3, 5, 64), (1, 3, 32)])
+def test_small_cin_im2col_gemm_stem(Cin, R, Cout):
+    """b200np_im2col_small + b200np_gemm = the stride-2 stem convolution and its weight gradient (used where the tcgen05
+    stem kernel does not apply: 3-channel images), against F.conv2d."""
+    ops = _ops()
+    from b200np import lib
+    N, H = 6, 32
+    x, w, b = rnd(N, Cin, H, H, seed=1), rnd(Cout, Cin, R, R, seed=2, scale=0.2), rnd(Cout, seed=3)
+    dy = rnd(N, Cout, H // 2, H // 2, seed=4)
+    wr = w.clone().requires_grad_()
+    y_ref = F.conv2d(x, wr, b, stride=2, padding=R // 2)
+    y_ref.backward(dy)
+    col = ops.im2col_small(x.float().cuda(), R, R // 2)
+    K, M = Cin * R * R, N * (H // 2) ** 2
+    ref_col = F.unfold(x, R, padding=R // 2, stride=2).permute(0, 2, 1).reshape(M, K)
+    assert col.shape == (M, (K + 3) // 4 * 4)
+    assert torch.equal(col[:, :K].cpu(), ref_col.float()) and float(col[:, K:].abs().sum()) == 0.0
+    if K >= 32:   # the tensor-core GEMM needs one full K-block; thinner stems stay on the direct kernels
+        wc = w.float().cuda().contiguous()
+        y = torch.empty(M, Cout, device="cuda")
+        ops.gemm(col.data_ptr(), wc.data_ptr(), y.data_ptr(), M, Cout, K, col.shape[1], 1, 1, K, Cout,
+                 bias=b.float().cuda().data_ptr(), prec=lib.PREC_TF32X3)
+        assert rel(y.view(N, H // 2, H // 2, Cout).permute(0, 3, 1, 2), y_ref) < 2e-5
+        dyg = nhwc(dy)
+        dw = torch.empty(Cout, K, device="cuda")
+        ops.gemm(dyg.data_ptr(), col.data_ptr(), dw.data_ptr(), Cout, K, M, 1, Cout, col.shape[1], 1, K, prec=lib.PREC_TF32X3)
+        assert rel(dw.view_as(wc), wr.grad) < 2e-5

@@ -74,6 +74,7 @@ _SIDE = {}
 MAIN_PRIORITY, DECODER_PRIORITY, WGRAD_PRIORITY = -2, -1, 0
 USE_PRIORITIES = os.environ.get("B200NP_PRIO", "1") != "0"
 FORK = os.environ.get("B200NP_FORK", "early")   # where the decoder branch forks: early | late (see the forward)
+STEM_GEMM = os.environ.get("B200NP_STEM_GEMM", "1") != "0"       # stems without a tcgen05 stem kernel: im2col + GEMM
 W0_IMPLICIT = os.environ.get("B200NP_W0_IMPLICIT", "1") != "0"   # encoder_w0's 3x3 convs as implicit-convolution GEMMs
 
 
@@ -123,10 +124,22 @@ class TrunkFn(Function):
         if ops.relu_bits_supported(imgs[0].shape[1], c1w.shape[2], c1w.shape[0], prec):
             bits0 = torch.empty((N, H // 2, W // 2, 2), device=x0.device, dtype=torch.int32)
         off = 0
+        # Stems the tcgen05 stem kernel does not cover (3-channel tasks: 5x5 over RGB, K = 75) in the tensor-core modes:
+        # im2col of the thin NCHW input + the tcgen05 GEMM with a fused bias + ReLU epilogue, and dW = dY^T col in the
+        # backward -- the CUDA-core direct convolution and its weight gradient were 22 % of the ShapeNet3D step
+        stem_cols = [] if (STEM_GEMM and prec != PREC_FP32_SIMT and bits0 is None) else None
         for im, n in zip(imgs, Ns):
-            ops.conv_small_fwd(im, c1w, c1b, out=x0[off:off + n], relu=True, prec=prec,
-                               relu_bits=None if bits0 is None else bits0[off:off + n])
+            if stem_cols is not None:
+                R, K = c1w.shape[2], c1w.shape[1] * c1w.shape[2] * c1w.shape[3]
+                col = ops.im2col_small(im.contiguous(), R, R // 2)
+                ops.gemm(_p(col), _p(c1w), _p(x0[off:off + n]), col.shape[0], c1w.shape[0], K, col.shape[1], 1, 1, K,
+                         c1w.shape[0], bias=_p(c1b), act=ACT_RELU, prec=prec)
+                stem_cols.append(col)
+            else:
+                ops.conv_small_fwd(im, c1w, c1b, out=x0[off:off + n], relu=True, prec=prec,
+                                   relu_bits=None if bits0 is None else bits0[off:off + n])
             off += n
+        ctx.stem_cols = stem_cols
         x, acts, packs, bits, bits_x = x0, [], [], [], bits0
         for l in range(4):
             w1, b1, w2, b2, wsk, bsk = params[2 + 6 * l: 8 + 6 * l]
@@ -208,8 +221,16 @@ class TrunkFn(Function):
         fork()
         off, dw_acc, db_acc = 0, None, None
         with torch.cuda.stream(wst):
-            for im, n in zip(ctx.imgs, Ns):
-                dw, db = ops.conv_small_wgrad(im, dy[off:off + n], ctx.c1w_shape, prec)
+            for si, (im, n) in enumerate(zip(ctx.imgs, Ns)):
+                if ctx.stem_cols is not None:
+                    col, dyv = ctx.stem_cols[si], dy[off:off + n]
+                    Co, K, M = ctx.c1w_shape[0], col.shape[1], col.shape[0]
+                    Kw = ctx.c1w_shape[1] * ctx.c1w_shape[2] * ctx.c1w_shape[3]
+                    dw = ops.empty(ctx.c1w_shape, dyv)
+                    ops.gemm(_p(dyv), _p(col), _p(dw), Co, Kw, M, 1, Co, K, 1, Kw, prec=prec)      # dW = dY^T col
+                    db = ops.colsum(dyv, M, Co, Co)
+                else:
+                    dw, db = ops.conv_small_wgrad(im, dy[off:off + n], ctx.c1w_shape, prec)
                 if dw_acc is None:
                     dw_acc, db_acc = dw, db
                 else:

@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200np_adam_step_dev": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _p, _f, _p]),
     "b200np_im2col3x3s2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "b200np_col2im3x3s2": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "b200np_im2col_small": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "b200np_conv_weight_tapmajor": (_i, [_p, _p, _i, _i, _i, _p]),
     "b200np_col2im3x3s2_tapmajor": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "b200np_bn_workspace": (_sz, [_ll, _i]),

@@ -395,6 +395,17 @@ def col2im3x3s2(dcol, x_shape, mask=None):
     return dx
 
 
+def im2col_small(x, R, pad, ld=None):
+    """x NCHW [N, Cin, H, W] -> col [N*(H/2)*(W/2), ld] for an R x R stride-2 convolution (k = ci*R*R + r*R + s, the
+    flattening of torch's weight); ld defaults to Cin*R*R rounded up to a multiple of 4."""
+    _chk(x, "x")
+    N, Cin, H, W = x.shape
+    ld = (Cin * R * R + 3) // 4 * 4 if ld is None else ld
+    col = empty((N * (H // 2) * (W // 2), ld), x)
+    check(LIB.b200np_im2col_small(_ptr(x), _ptr(col), N, Cin, H, W, R, pad, ld, _stream()), "im2col_small")
+    return col
+
+
 def conv_weight_tapmajor(w, to_tapmajor=True):
     """[Cout, Cin, 3, 3] -> [Cout, 9 * Cin] with k = tap * Cin + ci, or back (same shapes reversed)."""
     _chk(w, "w")

@@ -75,6 +75,37 @@ __global__ void col2im3x3s2_kernel(const float* __restrict__ dcol, const float* 
   }
 }
 
+// im2col of an NCHW image with few input channels for an R x R stride-2 convolution (the stems: 5x5 over 3 channels,
+// networks/ResNet.py conv1; 3x3 over 1 channel, encoder_w0[0]): col[m][ci*R*R + r*R + s] = x[n, ci, 2*oy + r - pad, 2*ox + s - pad]
+// with row pitch `ld` (>= Cin*R*R, the tail is zero-filled): K = 9..75 is thin, but as a tcgen05 GEMM over this matrix
+// the stem and its weight gradient cost a fraction of the CUDA-core direct convolution.  thread = (row m, column k):
+// coalesced stores, gathers served by L1 (every input pixel is read R*R/4 times).
+__global__ void im2col_small_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int Cin, int H, int W, int R,
+                                    int pad, int ld) {
+  // threadIdx.y / blockIdx.x: one output row (image n, row oy); threadIdx.x: column k.  Everything that needs a division
+  // is done once per thread; the loop over ox walks one input row with stride 2 and stores 4 bytes at pitch ld, so that a
+  // warp writes 128 contiguous bytes per iteration.
+  const int OH = H / 2, OW = W / 2, RR = R * R, KK = Cin * RR;
+  const long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= (long long)N * OH) return;
+  const int oy = (int)(row % OH);
+  const long long n = row / OH;
+  for (int k = threadIdx.x; k < ld; k += blockDim.x) {
+    float* out = col + row * OW * ld + k;
+    bool rowok = false;
+    const float* src = x;
+    int ix = 0;
+    if (k < KK) {
+      const int ci = k / RR, rs = k - ci * RR, r = rs / R, sx = rs - r * R;
+      const int iy = 2 * oy + r - pad;
+      rowok = iy >= 0 && iy < H;
+      src = x + ((n * Cin + ci) * H + (rowok ? iy : 0)) * W;
+      ix = sx - pad;
+    }
+    for (int ox = 0; ox < OW; ++ox, ix += 2)
+      out[(long long)ox * ld] = (rowok && ix >= 0 && ix < W) ? __ldg(src + ix) : 0.f;
+  }
+}
 // TAP-major variants (k = tap*C + ci) for the implicit-convolution GEMM (b200np_gemm_desc.conv_operand): the channel
 // vector of a pixel is contiguous in the column matrix, so everything moves as 16-byte words.
 __global__ void conv_weight_tapmajor_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin, int fwd) {
@@ -367,6 +398,15 @@ extern "C" int b200np_col2im3x3s2(const float* dcol, const float* mask, float* d
   if (!dcol || !dx || N <= 0 || C <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1)) return B200NP_E_BADARG;
   const long long total = (long long)N * H * W * C;
   col2im3x3s2_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(dcol, mask, dx, N, H, W, C);
+  return launch_status();
+}
+extern "C" int b200np_im2col_small(const float* x, float* col, int N, int Cin, int H, int W, int R, int pad, int ld,
+                                   void* stream) {
+  if (!x || !col || N <= 0 || Cin <= 0 || R <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1) || ld < Cin * R * R)
+    return B200NP_E_BADARG;
+  const int tx = ld >= 128 ? 128 : (ld + 31) / 32 * 32, ty = 256 / tx;
+  const long long rows = (long long)N * (H / 2);
+  im2col_small_kernel<<<(unsigned)ceil_div(rows, ty), dim3(tx, ty), 0, as_stream(stream)>>>(x, col, N, Cin, H, W, R, pad, ld);
   return launch_status();
 }
 extern "C" int b200np_conv_weight_tapmajor(const float* src, float* dst, int Cout, int Cin, int to_tapmajor, void* stream) {

@@ -136,6 +136,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_umma_kernel(const GemmUA
       cv_x[i] = 2 * ox - 1;
       cv_y[i] = 2 * (int)(q % cv_OH) - 1;
       cv_img[i] = (q / cv_OH) * d.conv_H * d.conv_W * d.conv_C;
+      if (CONV == 1 && pix >= M) {   // a row of the last tile beyond the matrix: never in range (B rows are guarded by k < K)
+        cv_y[i] = -(1 << 28);
+        cv_img[i] = 0;
+      }
     }
     if (CONV == 2) {        // B: this thread's four consecutive columns n = one tap, four channels
       const int nn = n0 + (tid & 15) * 4, tap = nn / d.conv_C;
